@@ -1,0 +1,76 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see model.hpp header).
+//
+// Device-schedule restatement.  The ARITHMETIC of one update is the reference's
+// (GibbsSimple::conditional = gibbs-simple.go:171-258, UniformSampler::weighted_sample =
+// sampler.go:107-123, marginal count = chain.go:231-236); only the two things the device
+// build changes on purpose are substituted:
+//   * the variable ORDER of a sweep is supplied by the caller (the device's colour-sorted
+//     schedule) instead of the reference's random scan (sampler.go:135-174);
+//   * the uniform of each draw comes from the device's counter-based Philox stream
+//     U(seed; chain, sweep, var) instead of the shared MT19937 channel (rand/rand.go).
+// Updating the variables of one colour sequentially gives the same state as updating them
+// concurrently iff the colouring is proper, so a bit-exact match of this restatement with
+// the device trajectory validates gathers, index math, floor, inverse CDF, Philox,
+// counting AND the colouring.
+#pragma once
+#include "sampler.hpp"
+
+namespace oracle {
+
+// Stream tags — MUST match grample_b200/csrc/philox.cuh
+enum : uint32_t { kTagDraw32 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4 };
+
+inline double philox_uniform(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t var, int bits) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t out[4];
+    if (bits == 53) {
+        uint32_t ctr[4] = {var, sweep, chain >> 1, kTagDraw53};
+        Philox4x32::gen(ctr, key, out);
+        int a = 2 * (int)(chain & 1);
+        uint64_t x = (((uint64_t)out[a] << 32) | out[a + 1]) >> 11;
+        return (double)x * (1.0 / 9007199254740992.0);
+    }
+    uint32_t ctr[4] = {var, sweep, chain >> 2, kTagDraw32};
+    Philox4x32::gen(ctr, key, out);
+    return (double)out[chain & 3] * (1.0 / 4294967296.0);
+}
+
+inline int philox_init_value(uint64_t seed, uint32_t chain, uint32_t var, int card) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {var, 0u, chain >> 2, kTagInit};
+    uint32_t out[4];
+    Philox4x32::gen(ctr, key, out);
+    return (int)(((uint64_t)out[chain & 3] * (uint64_t)card) >> 32);
+}
+
+struct FixedUniform : Generator {
+    double next = 0.0;
+    double float64() override { return next; }
+    int64_t int63() override { throw Error("FixedUniform: only Float64 draws are defined"); }
+};
+
+// Runs `n_sweeps` systematic sweeps over `order` for one chain.  `state` is updated in
+// place; counts[off[v] + k] is incremented for every recorded draw when `record`.
+inline void sweep_chain(GibbsSimple& gs, const std::vector<int>& order, uint64_t seed, uint32_t chain,
+                        uint32_t sweep0, uint32_t n_sweeps, int bits, bool record, int* state,
+                        const std::vector<int>& count_off, double* counts) {
+    FixedUniform fu;
+    UniformSampler us(&fu, 1);
+    std::vector<double> w;
+    for (uint32_t s = 0; s < n_sweeps; s++) {
+        for (int v : order) {
+            gs.conditional(v, state, w);
+            fu.next = philox_uniform(seed, chain, sweep0 + s, (uint32_t)v, bits);
+            int k;
+            try {
+                k = us.weighted_sample((int64_t)w.size(), w.data(), w.size());
+            } catch (const Error&) {
+                k = (int)w.size() - 1;  // device convention for the (measure-zero) fall-through
+            }
+            state[v] = k;
+            if (record && !gs.pgm->vars[v].collapsed) counts[count_off[v] + k] += 1.0;
+        }
+    }
+}
+
+}  // namespace oracle
