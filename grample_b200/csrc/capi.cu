@@ -1,0 +1,840 @@
+// C ABI of grample_b200 (include/grample_b200.h): host orchestration around the kernels in
+// kernels.cuh.  There is no CPU fallback: every compute entry needs a CUDA device and fails
+// loudly without one.  Host-only models (device = -1) exist for schedule / blanket inspection.
+#include "../../include/grample_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_model.hpp"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CUDA_CHECK(expr)                                                                             \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            throw gb::Err(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);      \
+    } while (0)
+
+#define GB_TRY try {
+#define GB_END                        \
+    }                                 \
+    catch (const std::exception& e) { \
+        g_err = e.what();             \
+        return 1;                     \
+    }                                 \
+    return 0;
+
+template <typename T>
+T* dev_upload(const std::vector<T>& h) {
+    T* d = nullptr;
+    size_t n = h.empty() ? 1 : h.size();
+    CUDA_CHECK(cudaMalloc(&d, n * sizeof(T)));
+    if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+void require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1)
+        throw gb::Err("grample_b200: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= n) throw gb::Err("grample_b200: invalid device index " + std::to_string(device));
+    CUDA_CHECK(cudaSetDevice(device));
+}
+
+int grid_for(int64_t items, int threads) {
+    int64_t blocks = (items + threads - 1) / threads;
+    const int64_t cap = 148 * 8;  // B200: 148 SMs x 8 resident 256-thread CTAs
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+struct gb_model {
+    gb::HostModel h;
+    int device = -1;
+    std::vector<void*> allocs;
+    gb::DevModel dev{};
+    int32_t* d_order = nullptr;
+
+    ~gb_model() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            for (void* p : allocs) cudaFree(p);
+        }
+    }
+    template <typename T>
+    T* up(const std::vector<T>& v) {
+        T* d = dev_upload(v);
+        allocs.push_back(d);
+        return d;
+    }
+    void upload(int dev_index) {
+        device = dev_index;
+        if (device < 0) return;
+        require_device(device);
+        std::vector<int32_t> entry_var(h.total_card);
+        for (int v = 0; v < h.n_vars; v++)
+            for (int k = 0; k < h.card[v]; k++) entry_var[h.card_off[v] + k] = v;
+        std::vector<float> tab32(h.log_tab.begin(), h.log_tab.end());
+        dev.n_vars = h.n_vars;
+        dev.total_card = h.total_card;
+        dev.max_card = h.max_card;
+        dev.card = up(h.card);
+        dev.card_off = up(h.card_off);
+        dev.fixed = up(h.fixed);
+        dev.prog_off = up(h.prog_off);
+        dev.prog = up(h.prog);
+        dev.tab64 = up(h.log_tab);
+        dev.tab32 = up(tab32);
+        dev.entry_var = up(entry_var);
+        d_order = up(h.order);
+    }
+};
+
+namespace {
+
+struct Group {
+    gb_model* model = nullptr;
+    bool owns_model = false;
+    int32_t n_chains = 0, n_pad = 0;
+    uint64_t first_chain = 0;
+    uint32_t sweep = 0;  // next Philox sweep index
+    uint8_t* d_state = nullptr;
+    unsigned long long* d_counts = nullptr;
+    uint16_t* d_hist = nullptr;
+    gb::DevGroup dev{};
+};
+
+}  // namespace
+
+struct gb_chains {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t seed = 0;
+    int precision = GB_F64;
+    uint32_t flags = 0;
+    std::vector<Group> groups;
+    int64_t total_samples = 0;
+    double* d_merge = nullptr;  // [total_card]
+    double* d_wb = nullptr;     // [2*n_vars]
+    uint8_t* d_skip = nullptr;  // [n_vars]
+    double* d_merged_in = nullptr;
+    int32_t last_cw = -1;       // ConvergenceWindow of the last gb_chains_advance
+
+    ~gb_chains() {
+        cudaSetDevice(device);
+        for (auto& g : groups) {
+            cudaFree(g.d_state);
+            cudaFree(g.d_counts);
+            cudaFree(g.d_hist);
+            if (g.owns_model) delete g.model;
+        }
+        cudaFree(d_merge);
+        cudaFree(d_wb);
+        cudaFree(d_skip);
+        cudaFree(d_merged_in);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    const gb::HostModel& base() const { return groups[0].model->h; }
+};
+
+namespace {
+
+void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_chain, bool owns) {
+    if (!model) throw gb::Err("No model supplied");
+    if (model->device != c->device) throw gb::Err("model lives on a different device than the chains");
+    if (n_chains < 1) throw gb::Err("a chain group needs at least 1 chain");
+    if (first_chain % 4) throw gb::Err("first_chain_id must be a multiple of 4 (Philox quads)");
+    if (!c->groups.empty() && (model->h.n_vars != c->base().n_vars || model->h.card != c->base().card))
+        throw gb::Err("Cannot merge chain with different variables");
+    if (model->h.order.empty()) throw gb::Err("No Variables to select");
+    Group g;
+    g.model = model;
+    g.owns_model = owns;
+    g.n_chains = n_chains;
+    g.n_pad = (n_chains + 3) / 4 * 4;
+    g.first_chain = first_chain;
+    const gb::HostModel& h = model->h;
+    CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
+    CUDA_CHECK(cudaMalloc(&g.d_counts, (size_t)h.total_card * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(g.d_counts, 0, (size_t)h.total_card * sizeof(unsigned long long), c->stream));
+    if (c->flags & GB_CHAINS_HISTORY) {
+        size_t hb = (size_t)2 * h.total_card * g.n_pad * sizeof(uint16_t);
+        CUDA_CHECK(cudaMalloc(&g.d_hist, hb));
+        CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, hb, c->stream));
+    }
+    g.dev.state = g.d_state;
+    g.dev.counts = g.d_counts;
+    g.dev.hist = g.d_hist;
+    g.dev.n_chains = g.n_chains;
+    g.dev.n_pad = g.n_pad;
+    g.dev.first_chain = first_chain;
+    g.dev.seed_lo = (uint32_t)c->seed;
+    g.dev.seed_hi = (uint32_t)(c->seed >> 32);
+    const int64_t items = (int64_t)h.n_vars * (g.n_pad / 4);
+    gb::k_init_state<<<grid_for(items, 256), 256, 0, c->stream>>>(model->dev, g.dev);
+    CUDA_CHECK(cudaGetLastError());
+    c->groups.push_back(g);
+}
+
+template <typename Real, int MAXC, int CW>
+void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half) {
+    const int64_t items = (int64_t)n * (g.n_pad / 4);
+    gb::k_sweep_colour<Real, MAXC, CW><<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, d_vars, n,
+                                                                                   g.sweep, record, hist_half);
+}
+
+// one sweep of one group: one launch per colour
+void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
+    const gb::HostModel& h = g.model->h;
+    const int n_col = (int)h.colour_off.size() - 1;
+    const int mc = h.max_card;
+    for (int col = 0; col < n_col; col++) {
+        const int32_t* dv = g.model->d_order + h.colour_off[col];
+        const int32_t n = h.colour_off[col + 1] - h.colour_off[col];
+        if (n == 0) continue;
+        if (c->precision == GB_F32) {
+            if (mc <= 2) launch_colour<float, 2, 4>(c, g, dv, n, record, hist_half);
+            else if (mc <= 4) launch_colour<float, 4, 4>(c, g, dv, n, record, hist_half);
+            else if (mc <= 8) launch_colour<float, 8, 4>(c, g, dv, n, record, hist_half);
+            else if (mc <= 16) launch_colour<float, 16, 4>(c, g, dv, n, record, hist_half);
+            else if (mc <= 32) launch_colour<float, 32, 1>(c, g, dv, n, record, hist_half);
+            else launch_colour<float, 64, 1>(c, g, dv, n, record, hist_half);
+        } else {
+            if (mc <= 2) launch_colour<double, 2, 4>(c, g, dv, n, record, hist_half);
+            else if (mc <= 4) launch_colour<double, 4, 4>(c, g, dv, n, record, hist_half);
+            else if (mc <= 8) launch_colour<double, 8, 1>(c, g, dv, n, record, hist_half);
+            else if (mc <= 16) launch_colour<double, 16, 1>(c, g, dv, n, record, hist_half);
+            else if (mc <= 32) launch_colour<double, 32, 1>(c, g, dv, n, record, hist_half);
+            else launch_colour<double, 64, 1>(c, g, dv, n, record, hist_half);
+        }
+    }
+    g.sweep++;
+    if (record) c->total_samples += (int64_t)h.order.size() * g.n_chains;
+}
+
+void sweeps(gb_chains* c, int64_t n, int record, int hist_half) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    for (int64_t s = 0; s < n; s++)
+        for (auto& g : c->groups) sweep_group(c, g, record, hist_half);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// skip flags: bit0 = collapsed in any group, bit1 = fixed
+std::vector<uint8_t> collapsed_any(const gb_chains* c, std::vector<int>* first_group = nullptr) {
+    const int nv = c->base().n_vars;
+    std::vector<uint8_t> col(nv, 0);
+    if (first_group) first_group->assign(nv, -1);
+    for (size_t gi = 0; gi < c->groups.size(); gi++)
+        for (int v = 0; v < nv; v++)
+            if (c->groups[gi].model->h.collapsed[v] && !col[v]) {
+                col[v] = 1;
+                if (first_group) (*first_group)[v] = (int)gi;
+            }
+    return col;
+}
+
+void ensure_scratch(gb_chains* c) {
+    const gb::HostModel& h = c->base();
+    if (!c->d_merge) CUDA_CHECK(cudaMalloc(&c->d_merge, (size_t)h.total_card * sizeof(double)));
+    if (!c->d_merged_in) CUDA_CHECK(cudaMalloc(&c->d_merged_in, (size_t)h.total_card * sizeof(double)));
+    if (!c->d_wb) CUDA_CHECK(cudaMalloc(&c->d_wb, (size_t)2 * h.n_vars * sizeof(double)));
+    if (!c->d_skip) CUDA_CHECK(cudaMalloc(&c->d_skip, (size_t)h.n_vars));
+}
+
+void merge_partial(gb_chains* c) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    ensure_scratch(c);
+    const gb::HostModel& h = c->base();
+    std::vector<uint8_t> col = collapsed_any(c);
+    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, col.data(), col.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->d_merge, 0, (size_t)h.total_card * sizeof(double), c->stream));
+    for (auto& g : c->groups)
+        gb::k_merge_partial<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(g.model->dev, g.d_counts,
+                                                                              (double)g.n_chains, c->d_skip, c->d_merge);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // col goes out of scope
+}
+
+void merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    const gb::HostModel& h = c->base();
+    CUDA_CHECK(cudaMemcpyAsync(out, c->d_merge, (size_t)h.total_card * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<int> first;
+    std::vector<uint8_t> col = collapsed_any(c, &first);
+    for (int v = 0; v < h.n_vars; v++) {
+        if (collapsed_out) collapsed_out[v] = col[v];
+        if (!col[v]) continue;
+        const auto& m = c->groups[first[v]].model->h.coll_marg[v];  // chain.go:113-129: first chain found
+        for (int k = 0; k < h.card[v]; k++) out[h.card_off[v] + k] = m[k];
+    }
+}
+
+void convergence_partial(gb_chains* c, int measure, const double* merged) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    if (!(c->flags & GB_CHAINS_HISTORY)) throw gb::Err("chains were created without GB_CHAINS_HISTORY");
+    if (measure < 0 || measure > 3) throw gb::Err("unknown measure");
+    ensure_scratch(c);
+    const gb::HostModel& h = c->base();
+    std::vector<double> tmp;
+    if (!merged) {
+        merge_partial(c);
+        tmp.resize(h.total_card);
+        merge_finalize(c, tmp.data(), nullptr);
+        merged = tmp.data();
+    }
+    std::vector<uint8_t> skip = collapsed_any(c);
+    for (int v = 0; v < h.n_vars; v++)
+        if (h.fixed[v] >= 0) skip[v] = 1;
+    CUDA_CHECK(cudaMemcpyAsync(c->d_merged_in, merged, (size_t)h.total_card * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, skip.data(), skip.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->d_wb, 0, (size_t)2 * h.n_vars * sizeof(double), c->stream));
+    for (auto& g : c->groups) {
+        const int64_t items = (int64_t)h.n_vars * g.n_chains;
+        gb::k_chain_dist<<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, c->d_merged_in, c->d_skip,
+                                                                     measure, c->d_wb);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// chain.go:46-59, 69-88
+void convergence_finalize(const gb::HostModel& h, const double* wb, int32_t cw, int64_t total_chains,
+                          const uint8_t* collapsed, double* out) {
+    if (total_chains < 2) throw gb::Err("Convergence requires at least 2 chains");
+    const double n = (double)cw, m = (double)total_chains;
+    const double b_norm = n / (m - 1), w_factor = (n - 1) / n, b_factor = (m + 1) / (m * n);
+    for (int v = 0; v < h.n_vars; v++) {
+        if (collapsed[v] || h.fixed[v] >= 0) {
+            out[v] = 1.0;
+            continue;
+        }
+        double W = (1e-8 + wb[v]) / m;
+        double B = (1e-8 + wb[h.n_vars + v]) * b_norm;
+        double vhat = w_factor * W + b_factor * B;
+        out[v] = std::sqrt((4.0 * vhat) / (2.0 * W));
+    }
+}
+
+// gibbs-collapsed.go:98-314 as a pure function over the flattened model
+gb_model* collapse_model(const gb_model* src, int32_t var, uint64_t seed, int32_t* var_out, double* marg_out) {
+    const gb::HostModel& h = src->h;
+    if (src->device < 0) throw gb::Err("collapse needs a device-resident model (there is no CPU fallback)");
+    require_device(src->device);
+    if (var < 0) {  // lines 102-120: up to n tries for a tractable variable
+        std::vector<int32_t> elig;
+        for (int v = 0; v < h.n_vars; v++)
+            if (h.fixed[v] < 0 && !h.collapsed[v]) elig.push_back(v);
+        if (elig.empty()) throw gb::Err("Failure selecting random variable to collapse: No Variables to select");
+        for (int t = 0; t < h.n_vars; t++) {
+            int32_t pick = elig[0];
+            if (elig.size() > 1) {
+                gb::Philox4 r = gb::philox4x32_10((uint32_t)t, 0u, 0u, gb::kTagCollapse, (uint32_t)seed, (uint32_t)(seed >> 32));
+                pick = elig[(size_t)(((uint64_t)r.x * elig.size()) >> 32)];
+            }
+            if ((int)h.nbrs[pick].size() <= gb::kNeighborVarMax) {
+                var = pick;
+                break;
+            }
+        }
+        if (var < 0) throw gb::Err("Failed to randomly select a variable to collapse");
+    }
+    if (var >= h.n_vars) throw gb::Err("Invalid variable index: max is " + std::to_string(h.n_vars - 1));
+    if (h.fixed[var] >= 0) throw gb::Err("Can not collapse Fixed Val variable " + std::to_string(var));
+    if (h.collapsed[var]) throw gb::Err("Already collapsed variable " + std::to_string(var));
+
+    std::vector<int32_t> blanket;  // without var, ascending (the reference's map order is random)
+    bool self = false;
+    for (int32_t u : h.nbrs[var]) {
+        if (u == var) self = true;
+        else blanket.push_back(u);
+    }
+    if (!self) throw gb::Err("Collapsing variable not in its own blanket");
+    if (blanket.empty()) throw gb::Err("New function would have 0 variables");
+    int64_t new_size = 1;
+    for (int32_t u : blanket) {
+        new_size *= h.card[u];
+        if (new_size > gb::kMaxTabSize)
+            throw gb::Err("Function over " + std::to_string(blanket.size()) + " vars has size > " + std::to_string(gb::kMaxTabSize));
+    }
+    if ((int)blanket.size() > gb::kNeighborVarMaxDev) throw gb::Err("blanket exceeds the device limit");
+
+    const auto& vf = h.var_funcs[var];
+    gb::CollapsePlan pl{};
+    pl.n_b = (int32_t)blanket.size();
+    pl.n_f = (int32_t)vf.size();
+    pl.card_v = h.card[var];
+    pl.new_size = new_size;
+    for (int b = 0; b < pl.n_b; b++) {
+        pl.bcard[b] = h.card[blanket[b]];
+        pl.bfixed[b] = h.fixed[blanket[b]];
+    }
+    std::vector<int32_t> f_tab_off, f_stride_v, f_stride_b((size_t)pl.n_f * pl.n_b, 0);
+    for (int fi = 0; fi < pl.n_f; fi++) {
+        const gb::Factor& f = h.funcs[vf[fi]];
+        f_tab_off.push_back((int32_t)f.off);
+        int32_t sv = 0;
+        for (size_t i = 0; i < f.vars.size(); i++) {
+            if (f.vars[i] == var) {
+                sv = (int32_t)f.strides[i];  // Eval reads the value of every scope slot from the state
+                continue;
+            }
+            int b = (int)(std::lower_bound(blanket.begin(), blanket.end(), f.vars[i]) - blanket.begin());
+            f_stride_b[(size_t)fi * pl.n_b + b] += (int32_t)f.strides[i];
+        }
+        f_stride_v.push_back(sv);
+    }
+    int32_t* d_off = dev_upload(f_tab_off);
+    int32_t* d_sv = dev_upload(f_stride_v);
+    int32_t* d_sb = dev_upload(f_stride_b);
+    pl.f_tab_off = d_off;
+    pl.f_stride_v = d_sv;
+    pl.f_stride_b = d_sb;
+    double *d_new = nullptr, *d_marg = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_new, (size_t)new_size * sizeof(double)));
+    std::vector<double> marg(pl.card_v, 1e-12);  // line 138-140
+    d_marg = dev_upload(marg);
+    gb::k_collapse<<<(int)((new_size + 255) / 256), 256>>>(pl, src->dev.tab64, d_new, d_marg);
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<double> new_tab((size_t)new_size);
+    CUDA_CHECK(cudaMemcpy(new_tab.data(), d_new, (size_t)new_size * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(marg.data(), d_marg, marg.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_off); cudaFree(d_sv); cudaFree(d_sb); cudaFree(d_new); cudaFree(d_marg);
+    gb::norm_marginal(marg);  // line 263
+
+    // lines 275-290: append the new factor, drop the variable's old factors, keep order
+    auto out = std::make_unique<gb_model>();
+    gb::HostModel& n = out->h;
+    n.n_vars = h.n_vars;
+    n.card = h.card;
+    n.fixed = h.fixed;
+    n.collapsed = h.collapsed;
+    n.coll_marg = h.coll_marg;
+    std::vector<uint8_t> drop(h.funcs.size(), 0);
+    for (int32_t fi : vf) drop[fi] = 1;
+    for (size_t fi = 0; fi < h.funcs.size(); fi++) {
+        if (drop[fi]) continue;
+        const gb::Factor& f = h.funcs[fi];
+        n.add_factor(f.vars, h.log_tab.data() + f.off, f.size, true);
+    }
+    n.add_factor(blanket, new_tab.data(), new_size, true);
+    n.collapsed[var] = 1;
+    n.coll_marg[var] = marg;  // lines 310-313
+    n.build_derived();
+    out->upload(src->device);
+    if (var_out) *var_out = var;
+    if (marg_out) std::copy(marg.begin(), marg.end(), marg_out);
+    return out.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gb_last_error(void) { return g_err.c_str(); }
+int gb_version(void) { return 100; }
+int gb_device_count(int* n_out) {
+    GB_TRY
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    *n_out = n;
+    GB_END
+}
+
+// ------------------------------------------------------------------ model
+int gb_model_create(int32_t n_vars, const int32_t* card, const int32_t* fixed, int32_t n_funcs,
+                    const int32_t* scope_off, const int32_t* scope_vars, const int64_t* tab_off,
+                    const double* tables_raw, int device, gb_model** out) {
+    GB_TRY
+    auto m = std::make_unique<gb_model>();
+    m->h = gb::make_model(n_vars, card, fixed, n_funcs, scope_off, scope_vars, tab_off, tables_raw);
+    m->upload(device);
+    *out = m.release();
+    GB_END
+}
+int gb_model_load_uai(const char* uai_path, const char* evid_path, int device, gb_model** out) {
+    GB_TRY
+    auto m = std::make_unique<gb_model>();
+    m->h = gb::load_uai(uai_path, evid_path);
+    m->upload(device);
+    *out = m.release();
+    GB_END
+}
+void gb_model_destroy(gb_model* m) { delete m; }
+
+int gb_model_n_vars(const gb_model* m, int32_t* out) { *out = m->h.n_vars; return 0; }
+int gb_model_n_funcs(const gb_model* m, int32_t* out) { *out = (int32_t)m->h.funcs.size(); return 0; }
+int gb_model_total_card(const gb_model* m, int32_t* out) { *out = m->h.total_card; return 0; }
+int gb_model_cards(const gb_model* m, int32_t* out) { std::copy(m->h.card.begin(), m->h.card.end(), out); return 0; }
+int gb_model_fixed(const gb_model* m, int32_t* out) { std::copy(m->h.fixed.begin(), m->h.fixed.end(), out); return 0; }
+int gb_model_collapsed(const gb_model* m, int32_t* out) {
+    for (int v = 0; v < m->h.n_vars; v++) out[v] = m->h.collapsed[v];
+    return 0;
+}
+#define GB_FUNC_CHECK(f) \
+    if ((f) < 0 || (f) >= (int32_t)m->h.funcs.size()) throw gb::Err("function index out of range")
+int gb_model_func_arity(const gb_model* m, int32_t f, int32_t* out) {
+    GB_TRY GB_FUNC_CHECK(f);
+    *out = (int32_t)m->h.funcs[f].vars.size();
+    GB_END
+}
+int gb_model_func_scope(const gb_model* m, int32_t f, int32_t* out) {
+    GB_TRY GB_FUNC_CHECK(f);
+    std::copy(m->h.funcs[f].vars.begin(), m->h.funcs[f].vars.end(), out);
+    GB_END
+}
+int gb_model_func_table_size(const gb_model* m, int32_t f, int64_t* out) {
+    GB_TRY GB_FUNC_CHECK(f);
+    *out = m->h.funcs[f].size;
+    GB_END
+}
+int gb_model_func_log_table(const gb_model* m, int32_t f, double* out) {
+    GB_TRY GB_FUNC_CHECK(f);
+    const gb::Factor& fn = m->h.funcs[f];
+    std::copy(m->h.log_tab.begin() + fn.off, m->h.log_tab.begin() + fn.off + fn.size, out);
+    GB_END
+}
+int gb_model_blanket_size(const gb_model* m, int32_t var, int32_t* out) {
+    GB_TRY
+    if (var < 0 || var >= m->h.n_vars) throw gb::Err("Invalid variable index");
+    *out = (int32_t)m->h.nbrs[var].size();
+    GB_END
+}
+int gb_model_function_count(const gb_model* m, int32_t var, int32_t* out) {
+    GB_TRY
+    if (var < 0 || var >= m->h.n_vars) throw gb::Err("Invalid variable index");
+    *out = (int32_t)m->h.var_funcs[var].size();
+    GB_END
+}
+int gb_model_schedule(const gb_model* m, int32_t* n_order, int32_t* n_colours, int32_t* order, int32_t* colour_off) {
+    GB_TRY
+    if (n_order) *n_order = (int32_t)m->h.order.size();
+    if (n_colours) *n_colours = (int32_t)m->h.colour_off.size() - 1;
+    if (order) std::copy(m->h.order.begin(), m->h.order.end(), order);
+    if (colour_off) std::copy(m->h.colour_off.begin(), m->h.colour_off.end(), colour_off);
+    GB_END
+}
+int gb_model_collapse(const gb_model* src, int32_t var, uint64_t seed, int32_t* collapsed_var_out,
+                      double* marginal_out, gb_model** out) {
+    if (collapsed_var_out) *collapsed_var_out = -1;
+    GB_TRY *out = collapse_model(src, var, seed, collapsed_var_out, marginal_out);
+    GB_END
+}
+
+int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int32_t* states,
+                   const int32_t* vars, double* out) {
+    GB_TRY
+    if (m->device < 0) throw gb::Err("gb_conditional needs a device-resident model (there is no CPU fallback)");
+    require_device(m->device);
+    const gb::HostModel& h = m->h;
+    for (int s = 0; s < n_states; s++) {
+        int v = vars[s];
+        if (v < 0 || v >= h.n_vars) throw gb::Err("Invalid variable index");
+        if (h.fixed[v] >= 0) throw gb::Err("Selected sample variable " + std::to_string(v) + " which has FixedVal=" + std::to_string(h.fixed[v]));
+        if (h.prog_off[v] < 0) throw gb::Err("variable " + std::to_string(v) + " is collapsed: it has no factors to sample from");
+        for (int u = 0; u < h.n_vars; u++) {
+            int x = states[(size_t)s * h.n_vars + u];
+            if (x < 0 || x >= h.card[u]) throw gb::Err("Value " + std::to_string(x) + " invalid for cardinality " + std::to_string(h.card[u]));
+        }
+    }
+    int32_t *d_states = nullptr, *d_vars = nullptr;
+    double* d_out = nullptr;
+    const size_t ns = (size_t)n_states;
+    CUDA_CHECK(cudaMalloc(&d_states, ns * h.n_vars * sizeof(int32_t)));
+    CUDA_CHECK(cudaMalloc(&d_vars, ns * sizeof(int32_t)));
+    CUDA_CHECK(cudaMalloc(&d_out, ns * gb::kProbeStride * sizeof(double)));
+    CUDA_CHECK(cudaMemcpy(d_states, states, ns * h.n_vars * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d_vars, vars, ns * sizeof(int32_t), cudaMemcpyHostToDevice));
+    const int blocks = (n_states + 127) / 128;
+    if (precision == GB_F32) gb::k_conditional<float><<<blocks, 128>>>(m->dev, n_states, d_states, d_vars, d_out);
+    else gb::k_conditional<double><<<blocks, 128>>>(m->dev, n_states, d_states, d_vars, d_out);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(out, d_out, ns * gb::kProbeStride * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_states); cudaFree(d_vars); cudaFree(d_out);
+    GB_END
+}
+
+// ------------------------------------------------------------------ chains
+int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* chains_per_model,
+                     uint64_t seed, uint64_t first_chain_id, int precision, uint32_t flags, int device,
+                     gb_chains** out) {
+    GB_TRY
+    if (n_groups < 1) throw gb::Err("at least one chain group is required");
+    if (precision != GB_F64 && precision != GB_F32) throw gb::Err("unknown precision");
+    require_device(device);
+    auto c = std::make_unique<gb_chains>();
+    c->device = device;
+    c->seed = seed;
+    c->precision = precision;
+    c->flags = flags;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    uint64_t first = first_chain_id;
+    for (int g = 0; g < n_groups; g++) {
+        add_group(c.get(), models[g], chains_per_model[g], first, false);
+        first += (uint64_t)((chains_per_model[g] + 3) / 4 * 4);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *out = c.release();
+    GB_END
+}
+int gb_chains_add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_chain_id) {
+    GB_TRY
+    CUDA_CHECK(cudaSetDevice(c->device));
+    add_group(c, model, n_chains, first_chain_id, false);
+    GB_END
+}
+void gb_chains_destroy(gb_chains* c) { delete c; }
+int gb_chains_n_groups(const gb_chains* c, int32_t* out) { *out = (int32_t)c->groups.size(); return 0; }
+int gb_chains_n_chains(const gb_chains* c, int64_t* out) {
+    int64_t n = 0;
+    for (auto& g : c->groups) n += g.n_chains;
+    *out = n;
+    return 0;
+}
+
+int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record) {
+    GB_TRY sweeps(c, n_sweeps, record, -1);
+    GB_END
+}
+int gb_chains_burnin(gb_chains* c, int64_t n_sweeps) {
+    GB_TRY sweeps(c, n_sweeps, 0, -1);
+    GB_END
+}
+int gb_chains_advance(gb_chains* c, int32_t cw) {
+    GB_TRY
+    if (cw < 0) throw gb::Err("Invalid convergence window");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    c->last_cw = cw;
+    const int32_t half = cw / 2;
+    if (c->flags & GB_CHAINS_HISTORY) {
+        for (auto& g : c->groups)
+            CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, (size_t)2 * g.model->h.total_card * g.n_pad * sizeof(uint16_t), c->stream));
+        if (half > 65535) throw gb::Err("convergence window too large for 16-bit half-window histograms");
+        sweeps(c, (int64_t)cw + 1 - 2 * half, 1, -1);
+        sweeps(c, half, 1, 0);
+        sweeps(c, half, 1, 1);
+    } else {
+        sweeps(c, (int64_t)cw + 1, 1, -1);
+    }
+    GB_END
+}
+int gb_chains_total_samples(const gb_chains* c, int64_t* out) { *out = c->total_samples; return 0; }
+int gb_chains_synchronize(gb_chains* c) {
+    GB_TRY
+    CUDA_CHECK(cudaSetDevice(c->device));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    GB_END
+}
+
+int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out) {
+    GB_TRY
+    merge_partial(c);
+    merge_finalize(c, out, collapsed_out);
+    GB_END
+}
+int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out) {
+    GB_TRY
+    merge_partial(c);
+    *dev_ptr_out = c->d_merge;
+    *n_out = c->base().total_card;
+    GB_END
+}
+int gb_chains_merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
+    GB_TRY merge_finalize(c, out, collapsed_out);
+    GB_END
+}
+
+int gb_chains_convergence(gb_chains* c, int measure, const double* merged, double* out) {
+    GB_TRY
+    int64_t total = 0;
+    for (auto& g : c->groups) total += g.n_chains;
+    if (total < 2) throw gb::Err("Convergence requires at least 2 chains");
+    if (c->last_cw < 2) throw gb::Err("Total seen < Convergence Window: run gb_chains_advance first");
+    convergence_partial(c, measure, merged);
+    const gb::HostModel& h = c->base();
+    std::vector<double> wb((size_t)2 * h.n_vars);
+    CUDA_CHECK(cudaMemcpy(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> col = collapsed_any(c);
+    convergence_finalize(h, wb.data(), c->last_cw, total, col.data(), out);
+    GB_END
+}
+int gb_chains_convergence_partial_dev(gb_chains* c, int measure, const double* merged, double** dev_ptr_out,
+                                      int64_t* n_out) {
+    GB_TRY
+    convergence_partial(c, measure, merged);
+    *dev_ptr_out = c->d_wb;
+    *n_out = (int64_t)2 * c->base().n_vars;
+    GB_END
+}
+int gb_convergence_finalize(const gb_chains* c, const double* wb, int32_t cw, int64_t total_chains,
+                            const int32_t* collapsed, double* out) {
+    GB_TRY
+    const gb::HostModel& h = c->base();
+    std::vector<uint8_t> col(h.n_vars, 0);
+    for (int v = 0; v < h.n_vars; v++) col[v] = collapsed ? (collapsed[v] != 0) : 0;
+    convergence_finalize(h, wb, cw, total_chains, col.data(), out);
+    GB_END
+}
+
+int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                    int measure, int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out,
+                    int32_t* n_chosen_out) {
+    if (n_chosen_out) *n_chosen_out = 0;
+    GB_TRY
+    CUDA_CHECK(cudaSetDevice(c->device));
+    int64_t total = 0;
+    for (auto& g : c->groups) total += g.n_chains;
+    if (total < 2) throw gb::Err("At least 2 chains required for adaptation");
+    if ((int32_t)c->groups.size() >= max_groups) return 0;  // adaptive.go:62-64
+    const gb::HostModel& b = base->h;
+    std::vector<uint8_t> col = collapsed_any(c);
+    std::vector<int32_t> cand;  // adaptive.go:81-87: blanket sizes on the ORIGINAL graph
+    for (int v = 0; v < b.n_vars; v++) {
+        int sz = (int)b.nbrs[v].size();
+        if (b.fixed[v] < 0 && !col[v] && sz > 1 && sz <= gb::kNeighborVarMax) cand.push_back(v);
+    }
+    if (cand.empty()) return 0;
+    std::vector<int32_t> targets;
+    if ((int32_t)cand.size() <= new_chain_count) {
+        targets = cand;
+    } else {
+        std::vector<double> conv(b.n_vars);
+        convergence_partial(c, measure, nullptr);
+        std::vector<double> wb((size_t)2 * b.n_vars);
+        CUDA_CHECK(cudaMemcpy(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        convergence_finalize(b, wb.data(), cw, total, col.data(), conv.data());
+        // adaptive.go:111-119: sort descending, take from the END (= lowest scores); ties by id
+        std::stable_sort(cand.begin(), cand.end(), [&](int32_t x, int32_t y) { return conv[x] > conv[y]; });
+        for (int i = 0; i < new_chain_count; i++) targets.push_back(cand[cand.size() - 1 - i]);
+    }
+    uint64_t first = first_chain_id;
+    int n_done = 0;
+    for (int32_t v : targets) {
+        gb_model* nm = collapse_model(base, v, 0, nullptr, nullptr);
+        try {
+            add_group(c, nm, chains_per_new_model, first, true);
+        } catch (...) {
+            delete nm;
+            throw;
+        }
+        first += (uint64_t)((chains_per_new_model + 3) / 4 * 4);
+        // adaptive.go:145: NewChain(..., burnIn=2) — two single-variable steps; one un-recorded
+        // sweep (>= 2 updates) is the sweep-granular equivalent
+        sweep_group(c, c->groups.back(), 0, -1);
+        if (chosen_out) chosen_out[n_done] = v;
+        n_done++;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    if (n_chosen_out) *n_chosen_out = n_done;
+    GB_END
+}
+
+int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out) {
+    GB_TRY
+    if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Group& g = c->groups[group];
+    const int nv = g.model->h.n_vars;
+    std::vector<uint8_t> st((size_t)nv * g.n_pad);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpy(st.data(), g.d_state, st.size(), cudaMemcpyDeviceToHost));
+    for (int ch = 0; ch < g.n_chains; ch++)
+        for (int v = 0; v < nv; v++) out[(size_t)ch * nv + v] = st[(size_t)v * g.n_pad + ch];
+    GB_END
+}
+int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in) {
+    GB_TRY
+    if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Group& g = c->groups[group];
+    const gb::HostModel& h = g.model->h;
+    std::vector<uint8_t> st((size_t)h.n_vars * g.n_pad, 0);
+    for (int ch = 0; ch < g.n_chains; ch++)
+        for (int v = 0; v < h.n_vars; v++) {
+            int x = in[(size_t)ch * h.n_vars + v];
+            if (x < 0 || x >= h.card[v]) throw gb::Err("Value " + std::to_string(x) + " invalid for cardinality " + std::to_string(h.card[v]));
+            if (h.fixed[v] >= 0 && x != h.fixed[v]) throw gb::Err("state contradicts FixedVal of variable " + std::to_string(v));
+            st[(size_t)v * g.n_pad + ch] = (uint8_t)x;
+        }
+    for (int ch = g.n_chains; ch < g.n_pad; ch++)  // padding chains mirror the last real chain
+        for (int v = 0; v < h.n_vars; v++) st[(size_t)v * g.n_pad + ch] = st[(size_t)v * g.n_pad + g.n_chains - 1];
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpy(g.d_state, st.data(), st.size(), cudaMemcpyHostToDevice));
+    GB_END
+}
+int gb_chains_group_counts(gb_chains* c, int32_t group, uint64_t* out) {
+    GB_TRY
+    if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Group& g = c->groups[group];
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpy(out, g.d_counts, (size_t)g.model->h.total_card * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    GB_END
+}
+int gb_chains_group_history(gb_chains* c, int32_t group, uint16_t* out) {
+    GB_TRY
+    if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
+    if (!(c->flags & GB_CHAINS_HISTORY)) throw gb::Err("chains were created without GB_CHAINS_HISTORY");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Group& g = c->groups[group];
+    const int tc = g.model->h.total_card;
+    std::vector<uint16_t> hh((size_t)2 * tc * g.n_pad);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpy(hh.data(), g.d_hist, hh.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < (size_t)2 * tc; r++)
+        for (int ch = 0; ch < g.n_chains; ch++) out[r * g.n_chains + ch] = hh[r * g.n_pad + ch];
+    GB_END
+}
+
+// ------------------------------------------------------------------ scoring (host)
+int gb_error_suite(int32_t n_vars, const int32_t* card, const int32_t* fixed1, const double* marg1,
+                   const int32_t* fixed2, const double* marg2, double* out8) {
+    GB_TRY
+    int cnt = 0;
+    for (int v = 0; v < n_vars; v++)
+        if ((!fixed1 || fixed1[v] < 0) && (!fixed2 || fixed2[v] < 0)) cnt++;
+    if (cnt < 1) throw gb::Err("No un-fixed vars to score");
+    double mean[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+    size_t off = 0;
+    for (int v = 0; v < n_vars; v++) {
+        const bool fx = (fixed1 && fixed1[v] >= 0) || (fixed2 && fixed2[v] >= 0);
+        // error.go order: MeanAbs, MaxAbs, Hellinger, JS
+        const int which[4] = {GB_MEAN_ABS, GB_MAX_ABS, GB_HELLINGER, GB_JS};
+        for (int i = 0; i < 4; i++) {
+            double d = fx ? 0.0 : gb::measure_host(which[i], marg1 + off, marg2 + off, card[v]);
+            mean[i] += d;
+            mx[i] = std::fmax(d, mx[i]);
+        }
+        off += card[v];
+    }
+    for (int i = 0; i < 4; i++) mean[i] /= (double)cnt;
+    out8[0] = mean[0]; out8[1] = mx[0]; out8[2] = mean[1]; out8[3] = mx[1];
+    out8[4] = mean[2]; out8[5] = mx[2]; out8[6] = mean[3]; out8[7] = mx[3];
+    GB_END
+}
+int gb_mar_load(const char* path, int32_t* n_vars_out, int32_t* total_card_out, int32_t* card_out, double* marg_out) {
+    GB_TRY
+    std::vector<int32_t> card;
+    std::vector<double> marg;
+    gb::load_mar(path, card, marg);
+    if (n_vars_out) *n_vars_out = (int32_t)card.size();
+    if (total_card_out) *total_card_out = (int32_t)marg.size();
+    if (card_out) std::copy(card.begin(), card.end(), card_out);
+    if (marg_out) std::copy(marg.begin(), marg.end(), marg_out);
+    GB_END
+}
+
+}  // extern "C"

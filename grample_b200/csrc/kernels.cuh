@@ -1,0 +1,420 @@
+// sm_100a kernels of the Gibbs hot path.  Reference lines each kernel replaces (paths
+// relative to the reference root):
+//   K1/K2 k_sweep_colour      sampler/gibbs-simple.go:163-271 (SampleVar) + sampler/sampler.go:90-130
+//                             (WeightedSample) + sampler/chain.go:221-246 (oneSample: marginal count,
+//                             history) for every (variable of one colour, chain); the collapsed
+//                             sampler (gibbs-collapsed.go:317-334) is the same arithmetic over a
+//                             model whose factor set excludes the collapsed variables.
+//   K3    k_collapse          sampler/gibbs-collapsed.go:205-260 (sum the variable out of its blanket)
+//   K4    k_chain_dist        sampler/chain.go:253-290 (ChainDist) + model/error.go:81-249
+//   K5    k_conditional       sampler/gibbs-simple.go:171-258 for caller-supplied states
+//   K6    k_init_state        sampler/gibbs-simple.go:103-111 (uniform start, FixedVal honoured)
+//
+// Data layout: state[var][chain] uint8, chain fastest, rows padded to a multiple of 4 chains so a
+// thread reads the states of 4 consecutive chains of one neighbour with one 32-bit load and a
+// warp's loads of one neighbour are contiguous (coalesced).  One Philox call serves the 4 chains.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <type_traits>
+
+#include "philox.cuh"
+
+namespace gb {
+
+constexpr int kNeighborVarMaxDev = 12;  // sampler.NeighborVarMax
+constexpr int kMaxCardDev = 64;         // GB_MAX_CARD
+
+struct DevModel {
+    int32_t n_vars, total_card, max_card;
+    const int32_t* card;        // [n_vars]
+    const int32_t* card_off;    // [n_vars+1]
+    const int32_t* fixed;       // [n_vars]
+    const int32_t* prog_off;    // [n_vars], -1 when the variable has no program
+    const int32_t* prog;        // update programs (host_model.hpp::build_programs)
+    const double* tab64;        // log-space tables
+    const float* tab32;
+    const int32_t* entry_var;   // [total_card] variable of each marginal entry
+};
+
+struct DevGroup {
+    uint8_t* state;              // [n_vars][n_pad]
+    unsigned long long* counts;  // [total_card]
+    uint16_t* hist;              // [2][total_card][n_pad] or nullptr
+    int32_t n_chains, n_pad;
+    uint64_t first_chain;        // global id of local chain 0 (multiple of 4)
+    uint32_t seed_lo, seed_hi;
+};
+
+template <typename Real>
+__device__ __forceinline__ const Real* tables_of(const DevModel& m);
+template <>
+__device__ __forceinline__ const double* tables_of<double>(const DevModel& m) { return m.tab64; }
+template <>
+__device__ __forceinline__ const float* tables_of<float>(const DevModel& m) { return m.tab32; }
+
+// gibbs-simple.go:227-258: log-weights -> floored un-normalised weights, in place.
+// float64 follows the reference literally (min-shift only when min < -8, sequential floor with
+// a running total).  float32 uses a max-shift instead (the floor is scale-invariant; min-shift
+// would overflow float32 for wide conditionals) and a multiply in place of the divide.
+template <typename Real, int MAXC>
+__device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], int card) {
+    if constexpr (std::is_same<Real, double>::value) {
+        double mn = w[0];
+#pragma unroll
+        for (int k = 1; k < MAXC; k++)
+            if (k < card && w[k] < mn) mn = w[k];
+        if (mn < -8.0) {
+#pragma unroll
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) w[k] = w[k] - (mn - 1.5);
+        }
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < card) {
+                const double e = exp(w[k]);
+                tot += e;
+                w[k] = e;
+            }
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < card && w[k] / tot < 1e-6) {
+                const double d = tot * 1e-6;
+                tot += d;
+                w[k] += d;
+            }
+    } else {
+        float mx = w[0];
+#pragma unroll
+        for (int k = 1; k < MAXC; k++)
+            if (k < card && w[k] > mx) mx = w[k];
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < card) {
+                const float e = __expf(w[k] - mx);
+                tot += e;
+                w[k] = e;
+            }
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < card && w[k] < tot * 1e-6f) {
+                const float d = tot * 1e-6f;
+                tot += d;
+                w[k] += d;
+            }
+    }
+}
+
+// sampler.go:107-123: re-sum, r = U * tot, first k with r <= w[k].  The (measure-zero)
+// fall-through that the reference turns into an error selects the last value here.
+template <typename Real, int MAXC>
+__device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real u) {
+    Real tot = 0;
+#pragma unroll
+    for (int k = 0; k < MAXC; k++)
+        if (k < card) tot += w[k];
+    Real r = u * tot;
+    int sel = card - 1;
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < MAXC; k++)
+        if (k < card && !done) {
+            if (r <= w[k]) {
+                sel = k;
+                done = true;
+            } else {
+                r -= w[k];
+            }
+        }
+    return sel;
+}
+
+// ------------------------------------------------------------------ K1/K2
+// One launch = one colour of one group.  Work item = (variable of the colour, quad of 4 chains);
+// consecutive threads take consecutive quads of the same variable.  CW = chains whose weight
+// vectors are held in registers at once (4 for small cardinalities, 1 for wide ones).
+template <typename Real, int MAXC, int CW>
+__global__ void __launch_bounds__(256)
+k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ vars, const int32_t n_vars_c,
+               const uint32_t sweep, const int record, const int hist_half) {
+    const Real* __restrict__ tab = tables_of<Real>(m);
+    const int32_t n_quads = g.n_pad >> 2;
+    const int64_t total = (int64_t)n_vars_c * n_quads;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t item = base + threadIdx.x;
+        const bool active = item < total;
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (!active) continue;
+        const int32_t j = (int32_t)(item / n_quads);
+        const int32_t q = (int32_t)(item - (int64_t)j * n_quads);
+        const int32_t v = __ldg(vars + j);
+        const int32_t card = __ldg(m.card + v);
+        const int32_t* __restrict__ prog = m.prog + __ldg(m.prog_off + v);
+        const int nf = __ldg(prog);
+
+        // uniforms for the 4 chains of the quad
+        const uint32_t chain0 = (uint32_t)(g.first_chain + 4u * (uint32_t)q);
+        Real u[4];
+        if constexpr (std::is_same<Real, double>::value) {
+            const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 1, kTagDraw53, g.seed_lo, g.seed_hi);
+            const Philox4 b = philox4x32_10((uint32_t)v, sweep, (chain0 >> 1) + 1u, kTagDraw53, g.seed_lo, g.seed_hi);
+            u[0] = u53(a.x, a.y); u[1] = u53(a.z, a.w); u[2] = u53(b.x, b.y); u[3] = u53(b.z, b.w);
+        } else {
+            const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 2, kTagDraw32, g.seed_lo, g.seed_hi);
+            u[0] = (float)(a.x >> 8) * (1.0f / 16777216.0f);
+            u[1] = (float)(a.y >> 8) * (1.0f / 16777216.0f);
+            u[2] = (float)(a.z >> 8) * (1.0f / 16777216.0f);
+            u[3] = (float)(a.w >> 8) * (1.0f / 16777216.0f);
+        }
+
+        int x[4];
+#pragma unroll
+        for (int cb = 0; cb < 4; cb += CW) {
+            Real w[CW][MAXC];
+#pragma unroll
+            for (int ci = 0; ci < CW; ci++)
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) w[ci][k] = 0;
+            const int32_t* __restrict__ p = prog + 1;
+            for (int f = 0; f < nf; f++) {
+                const int tab_off = __ldg(p), sv = __ldg(p + 1), no = __ldg(p + 2);
+                p += 3;
+                int b[CW];
+#pragma unroll
+                for (int ci = 0; ci < CW; ci++) b[ci] = tab_off;
+                for (int o = 0; o < no; o++) {
+                    const int ov = __ldg(p), os = __ldg(p + 1);
+                    p += 2;
+                    const uint32_t s4 = *reinterpret_cast<const uint32_t*>(g.state + (size_t)ov * g.n_pad + 4 * q);
+#pragma unroll
+                    for (int ci = 0; ci < CW; ci++) b[ci] += (int)((s4 >> (8 * (cb + ci))) & 0xffu) * os;
+                }
+#pragma unroll
+                for (int k = 0; k < MAXC; k++)
+                    if (k < card) {
+#pragma unroll
+                        for (int ci = 0; ci < CW; ci++) w[ci][k] += __ldg(tab + b[ci] + k * sv);
+                    }
+            }
+#pragma unroll
+            for (int ci = 0; ci < CW; ci++) {
+                stabilise_exp_floor<Real, MAXC>(w[ci], card);
+                x[cb + ci] = inverse_cdf<Real, MAXC>(w[ci], card, u[cb + ci]);
+            }
+        }
+        const uint32_t packed = (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
+        *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + 4 * q) = packed;
+
+        if (record) {
+            const int nvalid = min(4, g.n_chains - 4 * q);  // >= 1 for every launched quad except pure padding
+            const int32_t coff = __ldg(m.card_off + v);
+            // chain.go:231-236: Marginal[value] += 1 — aggregated over the warp when it holds one variable
+            const int v0 = __shfl_sync(mask, v, __ffs(mask) - 1);
+            const bool uniform = __all_sync(mask, v == v0);
+            if (uniform) {
+                for (int k = 0; k < card; k++) {
+                    int c = 0;
+#pragma unroll
+                    for (int ci = 0; ci < 4; ci++) c += (ci < nvalid && x[ci] == k) ? 1 : 0;
+                    const int s = __reduce_add_sync(mask, c);
+                    if (lane == __ffs(mask) - 1 && s) atomicAdd(g.counts + coff + k, (unsigned long long)s);
+                }
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++)
+                    if (ci < nvalid) atomicAdd(g.counts + coff + x[ci], 1ull);
+            }
+            // chain.go:237: ChainHistory[v].Add(value) — kept as per-chain half-window histograms
+            if (hist_half >= 0 && g.hist) {
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++)
+                    if (ci < nvalid) {
+                        uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + x[ci]) * g.n_pad + 4 * q + ci;
+                        *h = (uint16_t)(*h + 1);
+                    }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K6
+__global__ void __launch_bounds__(256) k_init_state(const DevModel m, const DevGroup g) {
+    const int32_t n_quads = g.n_pad >> 2;
+    const int64_t total = (int64_t)m.n_vars * n_quads;
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = (int32_t)(item / n_quads);
+        const int32_t q = (int32_t)(item - (int64_t)v * n_quads);
+        const int32_t fx = __ldg(m.fixed + v);
+        uint32_t packed;
+        if (fx >= 0) {
+            packed = (uint32_t)fx * 0x01010101u;
+        } else {
+            const uint32_t card = (uint32_t)__ldg(m.card + v);
+            const uint32_t chain0 = (uint32_t)(g.first_chain + 4u * (uint32_t)q);
+            const Philox4 a = philox4x32_10((uint32_t)v, 0u, chain0 >> 2, kTagInit, g.seed_lo, g.seed_hi);
+            packed = __umulhi(a.x, card) | (__umulhi(a.y, card) << 8) | (__umulhi(a.z, card) << 16) |
+                     (__umulhi(a.w, card) << 24);
+        }
+        *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + 4 * q) = packed;
+    }
+}
+
+// ------------------------------------------------------------------ K5
+// states: int32 [n_states][n_vars]; out: double [n_states][kOutStride] floored weights e[k]
+constexpr int kProbeStride = 64;
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_conditional(const DevModel m, const int32_t n_states, const int32_t* __restrict__ states,
+              const int32_t* __restrict__ vars, double* __restrict__ out) {
+    const Real* __restrict__ tab = tables_of<Real>(m);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_states) return;
+    const int32_t* st = states + (size_t)s * m.n_vars;
+    const int v = vars[s];
+    const int card = m.card[v];
+    Real w[kProbeStride];
+    for (int k = 0; k < kProbeStride; k++) w[k] = 0;
+    const int32_t* p = m.prog + m.prog_off[v];
+    const int nf = *p++;
+    for (int f = 0; f < nf; f++) {
+        const int tab_off = p[0], sv = p[1], no = p[2];
+        p += 3;
+        int b = tab_off;
+        for (int o = 0; o < no; o++, p += 2) b += st[p[0]] * p[1];
+        for (int k = 0; k < card; k++) w[k] += tab[b + k * sv];
+    }
+    stabilise_exp_floor<Real, kProbeStride>(w, card);
+    for (int k = 0; k < kProbeStride; k++) out[(size_t)s * kProbeStride + k] = k < card ? (double)w[k] : 0.0;
+}
+
+// ------------------------------------------------------------------ K3
+struct CollapsePlan {
+    int32_t n_b;            // blanket size without the collapsed variable (<= 11)
+    int32_t n_f;            // factors touching the collapsed variable
+    int32_t card_v;
+    int64_t new_size;       // entries of the new table
+    int32_t bcard[kNeighborVarMaxDev];
+    int32_t bfixed[kNeighborVarMaxDev];
+    const int32_t* f_tab_off;   // [n_f]
+    const int32_t* f_stride_v;  // [n_f]
+    const int32_t* f_stride_b;  // [n_f][n_b] stride of blanket position b in factor f (0 if absent)
+};
+
+__global__ void __launch_bounds__(256)
+k_collapse(const CollapsePlan pl, const double* __restrict__ tab, double* __restrict__ new_tab,
+           double* __restrict__ marg /*[card_v], pre-set to 1e-12*/) {
+    __shared__ double s_marg[kMaxCardDev];
+    for (int k = threadIdx.x; k < pl.card_v; k += blockDim.x) s_marg[k] = 0.0;
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < pl.new_size) {
+        int d[kNeighborVarMaxDev];
+        int64_t rem = e;
+        bool reachable = true;  // VariableIter(honorFixed) never visits other values of fixed vars
+        for (int b = pl.n_b - 1; b >= 0; b--) {
+            d[b] = (int)(rem % pl.bcard[b]);
+            rem /= pl.bcard[b];
+            if (pl.bfixed[b] >= 0 && d[b] != pl.bfixed[b]) reachable = false;
+        }
+        double acc = 0.0;
+        if (reachable) {
+            for (int x = 0; x < pl.card_v; x++) {
+                double s = 0.0;
+                for (int f = 0; f < pl.n_f; f++) {
+                    int idx = pl.f_tab_off[f] + x * pl.f_stride_v[f];
+                    for (int b = 0; b < pl.n_b; b++) idx += d[b] * pl.f_stride_b[f * pl.n_b + b];
+                    s += tab[idx];
+                }
+                const double val = exp(s);
+                acc += val;
+                atomicAdd(&s_marg[x], val);
+            }
+        }
+        // Function.UseLogSpace on the new factor (function.go:126-142)
+        new_tab[e] = log(acc < 1e-6 ? acc + 1e-6 : acc);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < pl.card_v; k += blockDim.x)
+        if (s_marg[k] != 0.0) atomicAdd(marg + k, s_marg[k]);
+}
+
+// ------------------------------------------------------------------ K4
+// model/error.go:81-249 on two length-card vectors given as accessors
+template <typename FA, typename FB>
+__device__ __forceinline__ double measure_dev(int which, int card, FA A, FB B) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int c = 0; c < card; c++) { t1 += A(c); t2 += B(c); }
+    if (t1 < 1e-12) t1 = 1e-12;
+    if (t2 < 1e-12) t2 = 1e-12;
+    double acc = 0.0;
+    if (which == 0) {
+        for (int c = 0; c < card; c++) {
+            const double e = fabs(A(c) / t1 - B(c) / t2);
+            if (c == 0 || e > acc) acc = e;
+        }
+        return acc;
+    } else if (which == 1) {
+        for (int c = 0; c < card; c++) acc += fabs(A(c) / t1 - B(c) / t2);
+        return acc / (double)card;
+    } else if (which == 2) {
+        for (int c = 0; c < card; c++) {
+            const double dd = sqrt(A(c) / t1) - sqrt(B(c) / t2);
+            acc += dd * dd;
+        }
+        return sqrt(acc) / sqrt(2.0);
+    }
+    double k1 = 0.0, k2 = 0.0;
+    for (int c = 0; c < card; c++) {
+        const double p1 = A(c) / t1, p2 = B(c) / t2, mid = (p1 + p2) * 0.5;
+        const double qq = mid < 1e-12 ? 1e-12 : mid;
+        const double x1 = p1 < 1e-12 ? 1e-12 : p1, x2 = p2 < 1e-12 ? 1e-12 : p2;
+        k1 += x1 * log2(x1 / qq);
+        k2 += x2 * log2(x2 / qq);
+    }
+    return 0.5 * (k1 + k2);
+}
+
+// item = (variable, chain): within = d(hist1, hist2), between = d(merged, hist1 + hist2), every
+// histogram bin seeded with 1e-8 (chain.go:264-287); sums over chains into wb[v], wb[n_vars+v].
+__global__ void __launch_bounds__(256)
+k_chain_dist(const DevModel m, const DevGroup g, const double* __restrict__ merged,
+             const uint8_t* __restrict__ skip, const int which, double* __restrict__ wb) {
+    const int64_t total = (int64_t)m.n_vars * g.n_chains;
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(item / g.n_chains);
+        const int ch = (int)(item - (int64_t)v * g.n_chains);
+        if (skip[v]) continue;
+        const int card = m.card[v], coff = m.card_off[v];
+        const uint16_t* h1 = g.hist + (size_t)coff * g.n_pad + ch;
+        const uint16_t* h2 = g.hist + ((size_t)m.total_card + coff) * g.n_pad + ch;
+        const size_t st = (size_t)g.n_pad;
+        auto A1 = [&](int c) { return 1e-8 + (double)h1[c * st]; };
+        auto A2 = [&](int c) { return 1e-8 + (double)h2[c * st]; };
+        auto A12 = [&](int c) { return (1e-8 + (double)h1[c * st]) + (1e-8 + (double)h2[c * st]); };
+        auto M = [&](int c) { return merged[coff + c]; };
+        const double within = measure_dev(which, card, A1, A2);
+        const double between = measure_dev(which, card, M, A12);
+        atomicAdd(wb + v, within);
+        atomicAdd(wb + m.n_vars + v, between);
+    }
+}
+
+// this device's contribution to MergeChains (chain.go:131-144): every chain starts at the
+// uniform marginal 1/card (model/variable.go:45) and adds its counts
+__global__ void __launch_bounds__(256)
+k_merge_partial(const DevModel m, const unsigned long long* __restrict__ counts, const double n_chains,
+                const uint8_t* __restrict__ skip, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.total_card) return;
+    const int v = m.entry_var[i];
+    if (skip[v]) return;
+    out[i] += n_chains * (1.0 / (double)m.card[v]) + (double)counts[i];
+}
+
+}  // namespace gb

@@ -1,0 +1,184 @@
+/* grample_b200 — C ABI of the B200-native Gibbs hot path.
+ *
+ * This is the drop-in boundary for the reference's `sampler` package (the part of
+ * CraigKelly/grample that cmd/root.go drives).  The reference is pure Go with no FFI of its
+ * own; every entry point below names the Go function(s) it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the cgo binding a maintainer adds on the Go side.
+ *
+ * Conventions
+ *   - opaque handles, plain pointers and sizes only (no C++/torch types);
+ *   - every function returns 0 on success, non-zero on error; the message is available from
+ *     gb_last_error() (thread-local), mirroring Go's `(value, error)` returns;
+ *   - caller-allocated output buffers; host pointers unless a name says `_dev`;
+ *   - every entry point selects its handle's CUDA device itself (goroutines migrate threads);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails loudly.
+ *
+ * Layouts
+ *   - a model is given as CSR arrays: card[n_vars], fixed[n_vars] (-1 = free), factor scopes
+ *     scope_vars[scope_off[f] .. scope_off[f+1]) (first variable most significant, last
+ *     fastest — model/function.go:180-202) and RAW (non-log) tables tables[tab_off[f] ..);
+ *   - marginal vectors are flat: sum(card) doubles, variable-major;
+ *   - chain state is uint8 `state[var][chain]` on the device (chain index fastest).
+ */
+#ifndef GRAMPLE_B200_H
+#define GRAMPLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gb_model gb_model;   /* factor graph + sampler bookkeeping, host + device copies */
+typedef struct gb_chains gb_chains; /* a population of chains (grouped by model) on ONE device   */
+
+/* sampler.NeighborVarMax (sampler/gibbs-collapsed.go:93) and model.maxTabSize (model/function.go:59) */
+#define GB_NEIGHBOR_VAR_MAX 12
+#define GB_MAX_TAB_SIZE (1 << 23)
+#define GB_MAX_CARD 64 /* device limit on variable cardinality */
+
+/* model.Measure implementations (model/error.go:81-249) */
+enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 };
+/* arithmetic type of the sweep kernels */
+enum gb_precision { GB_F64 = 0, GB_F32 = 1 };
+/* gb_chains_create flags */
+#define GB_CHAINS_HISTORY 1u /* keep per-chain half-window histograms (needed by gb_chains_convergence*) */
+
+const char* gb_last_error(void);
+int gb_version(void);
+int gb_device_count(int* n_out);
+
+/* ------------------------------------------------------------------ model
+ * gb_model_create   replaces sampler.NewGibbsSimple's bookkeeping (sampler/gibbs-simple.go:25-115:
+ *                   Function.UseLogSpace with the 1e-6 eps rule model/function.go:126-142,
+ *                   var->factor lists in m.Funcs order, validation :92-99) plus
+ *                   GibbsCollapsed.FunctionsChanged (sampler/gibbs-collapsed.go:44-78: neighbour sets),
+ *                   and builds the device CSR + colour schedule.
+ * gb_model_load_uai replaces model.NewModelFromFile + UAIReader.ReadModel/ApplyEvidence
+ *                   (model/model.go:52-112, model/uai.go:53-249); evid_path may be NULL. */
+int gb_model_create(int32_t n_vars, const int32_t* card, const int32_t* fixed, int32_t n_funcs,
+                    const int32_t* scope_off, const int32_t* scope_vars, const int64_t* tab_off,
+                    const double* tables_raw, int device, gb_model** out);
+int gb_model_load_uai(const char* uai_path, const char* evid_path, int device, gb_model** out);
+void gb_model_destroy(gb_model* m);
+
+int gb_model_n_vars(const gb_model* m, int32_t* out);
+int gb_model_n_funcs(const gb_model* m, int32_t* out);
+int gb_model_total_card(const gb_model* m, int32_t* out);            /* sum(card) */
+int gb_model_cards(const gb_model* m, int32_t* out /*[n_vars]*/);
+int gb_model_fixed(const gb_model* m, int32_t* out /*[n_vars]*/);
+int gb_model_collapsed(const gb_model* m, int32_t* out /*[n_vars]*/);
+/* factor f: arity/scope/table (log space, as the sampler sees it) — test & Go-shim read-back */
+int gb_model_func_arity(const gb_model* m, int32_t f, int32_t* out);
+int gb_model_func_scope(const gb_model* m, int32_t f, int32_t* out /*[arity]*/);
+int gb_model_func_table_size(const gb_model* m, int32_t f, int64_t* out);
+int gb_model_func_log_table(const gb_model* m, int32_t f, double* out /*[size]*/);
+/* (*GibbsCollapsed).BlanketSize / FunctionCount (sampler/gibbs-collapsed.go:81-88) */
+int gb_model_blanket_size(const gb_model* m, int32_t var, int32_t* out);
+int gb_model_function_count(const gb_model* m, int32_t var, int32_t* out);
+/* colour-sorted sweep order of the free, non-collapsed variables: order[n_order],
+ * colour_off[n_colours+1].  Pass NULL outputs to query sizes only. */
+int gb_model_schedule(const gb_model* m, int32_t* n_order, int32_t* n_colours, int32_t* order, int32_t* colour_off);
+
+/* (*GibbsCollapsed).Collapse (sampler/gibbs-collapsed.go:98-314) as a pure function: returns a NEW
+ * model in which `var` is summed out of its blanket (K3 collapse_marginalise on the device).
+ * var < 0: pick uniformly among free, un-collapsed variables with blanket <= GB_NEIGHBOR_VAR_MAX,
+ * at most n_vars tries (lines 102-120), using `seed`.  Same error cases as the reference
+ * (fixed / already collapsed / empty new scope / table > GB_MAX_TAB_SIZE).
+ * collapsed_var_out / marginal_out[card] may be NULL. */
+int gb_model_collapse(const gb_model* src, int32_t var, uint64_t seed, int32_t* collapsed_var_out,
+                      double* marginal_out, gb_model** out);
+
+/* K5 conditional_probe — the parity hook for sampler/gibbs-simple.go:171-258: for a
+ * caller-supplied full state, the floored un-normalised weights e[k] exactly as SampleVar
+ * leaves them before WeightedSample (float64 or float32 arithmetic).  n_states states are
+ * evaluated in one launch: states[n_states][n_vars], vars[n_states], out[n_states][GB_MAX_CARD]. */
+int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int32_t* states,
+                   const int32_t* vars, double* out);
+
+/* ------------------------------------------------------------------ chains
+ * gb_chains_create replaces the chain-construction loop cmd/root.go:381-430 +
+ * sampler.NewChain (sampler/chain.go:151-175) for ALL chains of one device at once:
+ * group g holds chains_per_model[g] chains over models[g] (one group per distinct
+ * collapsed variant; `simple` uses a single group).  Chain ids are global:
+ * first_chain_id + local index; the Philox stream is keyed by (seed, global chain id) so
+ * results do not depend on how chains are sharded across devices (shard sizes must be
+ * multiples of 4).  Initial state: FixedVal or a uniform draw (gibbs-simple.go:103-111). */
+int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* chains_per_model,
+                     uint64_t seed, uint64_t first_chain_id, int precision, uint32_t flags, int device,
+                     gb_chains** out);
+/* adaptive.go:130-154: append a group of new chains over a (collapsed) model */
+int gb_chains_add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_chain_id);
+void gb_chains_destroy(gb_chains* c);
+int gb_chains_n_groups(const gb_chains* c, int32_t* out);
+int gb_chains_n_chains(const gb_chains* c, int64_t* out);
+
+/* `n_sweeps` systematic colour sweeps of every chain; one sweep updates every free,
+ * un-collapsed variable once (= n_free reference steps, chain.go:221-246).  record != 0 adds
+ * each draw to the marginal counts (chain.go:231-236) and TotalSampleCount. */
+int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record);
+/* burn-in (chain.go:167-172): un-recorded.  The reference counts single-variable steps;
+ * callers convert with ceil(steps / n_free). */
+int gb_chains_burnin(gb_chains* c, int64_t n_sweeps);
+/* One reference "round" for all chains — (*Chain).AdvanceChain (chain.go:180-218) + the
+ * WaitGroup barrier (cmd/root.go:475-479): cw+1 recorded sweeps, the last 2*(cw/2) of which
+ * fill the first/second half-window histograms (buffer/circular.go semantics). */
+int gb_chains_advance(gb_chains* c, int32_t cw);
+/* sum of Chain.TotalSampleCount over this device's chains (cmd/root.go:488-491) */
+int gb_chains_total_samples(const gb_chains* c, int64_t* out);
+int gb_chains_synchronize(gb_chains* c);
+
+/* sampler.MergeChains (sampler/chain.go:96-148) over this device's chains: for every variable
+ * the sum over chains of Marginal (each chain starts at uniform 1/card, model/variable.go:45,
+ * plus its counts); a variable collapsed in ANY group is reported with that group's local
+ * marginal and collapsed_out[v] = 1.  out[sum(card)], collapsed_out[n_vars] (may be NULL). */
+int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out);
+/* Multi-device form: this device's un-merged contribution is written to a DEVICE buffer of
+ * sum(card) doubles (collapsed variables zero) so the host plumbing can all-reduce it in
+ * place (NCCL); finalize overwrites collapsed variables and copies to the host. */
+int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out);
+int gb_chains_merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out);
+
+/* sampler.ChainConvergence + (*Chain).ChainDist (chain.go:32-92, 253-290) with `measure`
+ * (K4 on the device).  merged == NULL: merge this device's chains first.  out[n_vars]. */
+int gb_chains_convergence(gb_chains* c, int measure, const double* merged, double* out);
+/* Multi-device form: per-variable sums of within/between distances over this device's chains
+ * into a DEVICE buffer [2*n_vars] (W then B) to be all-reduced, then finalised with the global
+ * chain count. */
+int gb_chains_convergence_partial_dev(gb_chains* c, int measure, const double* merged, double** dev_ptr_out,
+                                      int64_t* n_out);
+int gb_convergence_finalize(const gb_chains* c, const double* wb /*[2*n_vars] host*/, int32_t cw,
+                            int64_t total_chains, const int32_t* collapsed /*[n_vars]*/, double* out);
+
+/* (*ConvergenceSampler).Adapt (sampler/adaptive.go:57-157): choose up to new_chain_count
+ * variables (candidate filter :81-87, LOWEST convergence scores :102-119, ties by variable id),
+ * collapse each on a fresh clone of `base`, append one group of chains_per_new_model chains per
+ * variable with 2 burn-in steps (:145).  No-op at max_groups (reference MaxChains=128, :49).
+ * chosen_out[new_chain_count] / n_chosen_out may be NULL.  The new models are owned by `c`. */
+int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                    int measure, int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out,
+                    int32_t* n_chosen_out);
+
+/* state access for tests / the Go shim's LastSample: state[chain][var] int32 (host) */
+int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out);
+int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in);
+/* raw marginal counts of one group: uint64 [sum(card)] */
+int gb_chains_group_counts(gb_chains* c, int32_t group, uint64_t* out);
+/* per-chain half-window histograms of one group: uint16 [2][sum(card)][n_chains] */
+int gb_chains_group_history(gb_chains* c, int32_t group, uint16_t* out);
+
+/* ------------------------------------------------------------------ scoring (host)
+ * model.NewErrorSuite (model/error.go:28-78).  fixed arrays may be NULL (= all free).
+ * out8: MeanMeanAbs, MaxMeanAbs, MeanMaxAbs, MaxMaxAbs, MeanHellinger, MaxHellinger, MeanJS, MaxJS */
+int gb_error_suite(int32_t n_vars, const int32_t* card, const int32_t* fixed1, const double* marg1,
+                   const int32_t* fixed2, const double* marg2, double* out8);
+/* UAIReader.ReadMargSolution (model/uai.go:252-332): card_out[n_vars], marg_out[sum(card)];
+ * pass NULL outputs to query n_vars / total_card. */
+int gb_mar_load(const char* path, int32_t* n_vars_out, int32_t* total_card_out, int32_t* card_out,
+                double* marg_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAMPLE_B200_H */

@@ -1,0 +1,150 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/grample_b200.h declares, fails loudly without a GPU, and the host-side model logic
+(UAI parsing, flattening, colouring, scoring) agrees with the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import grample_b200 as gb
+import oracle
+from grample_b200 import _lib
+
+HAS_GPU = gb.device_count() > 0
+
+
+def header_symbols():
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = header_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/grample_b200.h but not exported"
+    assert declared == gb.exported_symbols()  # the Python binding covers the whole header
+    assert lib.gb_version() == 100
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(res):
+    with pytest.raises(gb.GrampleError, match="no CUDA device"):
+        gb.Model.from_uai(res("one.uai"), device=0)
+    m = gb.Model.from_uai(res("Grids_11.uai"), device=-1)  # host-only metadata is allowed
+    with pytest.raises(gb.GrampleError, match="no CPU fallback"):
+        m.conditional(np.zeros((1, 100), np.int32), [0])
+    with pytest.raises(gb.GrampleError, match="no CPU fallback"):
+        m.collapse(0)
+    with pytest.raises(gb.GrampleError):
+        gb.Chains(m, 4, device=0)
+
+
+@pytest.mark.parametrize("name,evid", [("one.uai", False), ("sample.uai", False), ("Grids_11.uai", False),
+                                        ("Promedus_11.uai", True), ("Pedigree_11.uai", True),
+                                        ("ObjectDetection_11.uai", False), ("dv-rel_1.uai", True)])
+def test_uai_reader_and_log_tables_match_oracle(res, name, evid):
+    dm = gb.Model.from_uai(res(name), use_evidence=evid, device=-1)
+    om = oracle.Model.load(res(name), use_evidence=evid)
+    assert dm.n_vars == om.n_vars and dm.n_funcs == om.n_funcs
+    assert np.array_equal(dm.cards, om.cards) and np.array_equal(dm.fixed, om.fixed)
+    osamp = oracle.Sampler(oracle.Generator(1), om, collapsed=True)  # converts the tables to log space
+    for f in range(dm.n_funcs):
+        assert np.array_equal(dm.func_scope(f), om.func_scope(f))
+        assert np.array_equal(dm.func_log_table(f), om.func_table(f))  # same eps rule, same libm log
+    for v in range(dm.n_vars):
+        assert dm.blanket_size(v) == osamp.blanket_size(v)
+        assert dm.function_count(v) == osamp.function_count(v)
+    # from_arrays on the oracle's flattening gives the same model
+    dm2 = gb.Model.from_arrays(*oracle.Model.load(res(name), use_evidence=evid).flatten(), device=-1)
+    assert np.array_equal(dm2.schedule()[0], dm.schedule()[0])
+
+
+def test_model_errors(res, tmp_path):
+    """uai.go / model.go / function.go error cases"""
+    bad = tmp_path / "bad.uai"
+    for text in ("", "MARKOV\n1\n2\n1\n1 0\n3\n 0.1 0.2 0.7\n", "FOO\n1\n2\n1\n1 0\n2\n 0.5 0.5\n",
+                 "MARKOV\n1\n2\n1\n1 5\n2\n 0.5 0.5\n", "MARKOV\n1\n2\n1\n1 0\n2\n 0.5 abc\n"):
+        bad.write_text(text)
+        with pytest.raises(gb.GrampleError):
+            gb.Model.from_uai(str(bad), device=-1)
+    with pytest.raises(gb.GrampleError):
+        gb.Model.from_uai(str(tmp_path / "missing.uai"), device=-1)
+    # all variables fixed (model.go:138-140); fixed value out of range (variable.go:84-88)
+    with pytest.raises(gb.GrampleError):
+        gb.Model.from_arrays([2], [1], [0, 1], [0], [0, 2], [0.5, 0.5], device=-1)
+    with pytest.raises(gb.GrampleError):
+        gb.Model.from_arrays([2, 2], [-1, 2], [0, 2], [0, 1], [0, 4], [1, 1, 1, 1], device=-1)
+    # a variable in no factor (gibbs-simple.go:96-99)
+    with pytest.raises(gb.GrampleError):
+        gb.Model.from_arrays([2, 2], [-1, -1], [0, 1], [0], [0, 2], [0.5, 0.5], device=-1)
+    # table larger than maxTabSize (function.go:77-79)
+    with pytest.raises(gb.GrampleError):
+        gb.Model.from_arrays([2] * 24, [-1] * 24, [0, 24], list(range(24)), [0, 1 << 24], np.ones(1 << 24), device=-1)
+
+
+def test_schedule_is_proper_colouring(res):
+    for name, evid, ncol in (("Grids_11.uai", False, 2), ("Promedus_11.uai", True, 4), ("Pedigree_11.uai", True, 5),
+                             ("ObjectDetection_11.uai", False, 7)):
+        dm = gb.Model.from_uai(res(name), use_evidence=evid, device=-1)
+        order, coff = dm.schedule()
+        assert len(coff) - 1 == ncol
+        fixed = dm.fixed
+        assert sorted(order.tolist()) == [v for v in range(dm.n_vars) if fixed[v] < 0]
+        colour = {}
+        for c in range(ncol):
+            for v in order[coff[c]:coff[c + 1]]:
+                colour[int(v)] = c
+        for f in range(dm.n_funcs):
+            sc = [int(v) for v in dm.func_scope(f) if int(v) in colour]
+            assert len({colour[v] for v in sc}) == len(set(sc))
+
+
+def test_ising_generator_layout():
+    card, fixed, scope_off, scope_vars, tab_off, tables = gb.ising_torus(10, 10, seed=1)
+    assert len(card) == 100 and len(scope_off) == 301 and tab_off[-1] == 1000
+    scopes = [scope_vars[scope_off[f]:scope_off[f + 1]].tolist() for f in range(300)]
+    assert scopes[:3] == [[0], [1], [2]]
+    assert scopes[100:110] == [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [5, 6], [6, 7], [7, 8], [8, 9], [0, 9]]
+    assert scopes[200:210] == [[0, 10], [10, 20], [20, 30], [30, 40], [40, 50], [50, 60], [60, 70], [70, 80], [80, 90], [0, 90]]
+    t = tables[tab_off[100]:tab_off[101]]
+    assert t[0] == t[3] and t[1] == t[2] and t[0] * t[1] == pytest.approx(1.0)
+    dm = gb.Model.from_arrays(card, fixed, scope_off, scope_vars, tab_off, tables, device=-1)
+    order, coff = dm.schedule()
+    assert coff.tolist() == [0, 50, 100]
+    assert all(((v // 10) + (v % 10)) % 2 == 0 for v in order[:50])
+    om = oracle.Model.create(card, fixed, scope_off, scope_vars, tab_off, tables)
+    assert om.n_funcs == 300
+
+
+def test_error_suite_and_mar_reader_match_reference_vectors(res):
+    """model/error_test.go:92-119 and uai_test.go:144-171 through the product's host API"""
+    es = gb.error_suite([3, 3], [30.0, 40.0, 30.0] * 2, [90.0, 5.0, 5.0, 60.0, 30.0, 10.0])
+    exp = dict(MeanMeanAbsError=.30000000, MaxMeanAbsError=.39999999, MeanMaxAbsError=.45000000,
+               MaxMaxAbsError=.60000000, MeanHellinger=.35109087, MaxHellinger=.46528369,
+               MeanJSDiverge=.18806933, MaxJSDiverge=.29645726)
+    for k, v in exp.items():
+        assert es[k] == pytest.approx(v, rel=1e-7), k
+    es = gb.error_suite([2, 2], [250.0, 750.0, 25.1, 75.3], [42.0, 42.0, 3.1, 3.1])
+    assert es["MeanHellinger"] == pytest.approx(0.18459191128251448, rel=1e-8)
+    assert es["MeanJSDiverge"] == pytest.approx(0.0487949406953985, rel=1e-8)
+    with pytest.raises(gb.GrampleError):
+        gb.error_suite([2], [1, 1], [1, 1], fixed1=[1])
+    cards, marg = gb.mar_load(res("one.uai.MAR"))
+    assert cards.tolist() == [2] and marg.tolist() == [0.25, 0.75]
+    cards, marg = gb.mar_load(res("Grids_11.uai.merlin.MAR"))  # PR section is skipped
+    assert len(cards) == 100 and marg[0] == pytest.approx(0.997878)
+    for name in ("Grids_11", "Promedus_11", "Pedigree_11", "ObjectDetection_11"):
+        cards, marg = gb.mar_load(res(f"{name}.uai.MAR"))
+        s = oracle.solution_load(res(f"{name}.uai.MAR"))
+        assert np.array_equal(cards, s.cards) and np.array_equal(marg, s.marginals)
+        rng = np.random.default_rng(0)
+        other = rng.random(len(marg)) + 0.01
+        a = gb.error_suite(cards, marg, other)
+        b = oracle.error_suite(cards, s.marginal_list(), np.split(other, np.cumsum(cards)[:-1]))
+        for k in a:
+            assert a[k] == pytest.approx(b[k], rel=1e-12)

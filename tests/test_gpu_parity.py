@@ -1,0 +1,408 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for states / counts / indices; 1e-9 relative for float64
+conditionals (north_star asks 1e-6), 1e-4 relative for float32.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+gb = pytest.importorskip("grample_b200")
+
+MODELS = [("one.uai", False), ("sample.uai", False), ("deterministic.uai", False), ("Grids_11.uai", False),
+          ("Promedus_11.uai", True), ("Pedigree_11.uai", True), ("ObjectDetection_11.uai", False),
+          ("dv-rel_1.uai", True)]
+
+
+def load_pair(res, name, evid):
+    dm = gb.Model.from_uai(res(name), use_evidence=evid, device=0)
+    om = oracle.Model.load(res(name), use_evidence=evid)
+    return dm, om
+
+
+def random_states(rng, cards, fixed, n):
+    st = np.zeros((n, len(cards)), dtype=np.int32)
+    for v, c in enumerate(cards):
+        st[:, v] = fixed[v] if fixed[v] >= 0 else rng.integers(c, size=n)
+    return st
+
+
+# ------------------------------------------------------------------ parity level 1: conditionals (K5)
+@pytest.mark.parametrize("name,evid", MODELS)
+def test_conditional_probe_f64(res, name, evid):
+    dm, om = load_pair(res, name, evid)
+    samp = oracle.Sampler(oracle.Generator(3), om)
+    rng = np.random.default_rng(11)
+    cards, fixed = dm.cards, dm.fixed
+    free = np.nonzero(fixed < 0)[0]
+    n = 64 if len(free) > 1 else 4
+    states = random_states(rng, cards, fixed, n)
+    vs = rng.choice(free, size=n)
+    got = dm.conditional(states, vs, precision=gb.F64)
+    for i in range(n):
+        ref = samp.conditional(int(vs[i]), states[i])
+        assert np.allclose(got[i], ref, rtol=1e-9, atol=0), (name, int(vs[i]))
+
+
+@pytest.mark.parametrize("name,evid", MODELS)
+def test_conditional_probe_f32(res, name, evid):
+    dm, om = load_pair(res, name, evid)
+    samp = oracle.Sampler(oracle.Generator(3), om)
+    rng = np.random.default_rng(12)
+    cards, fixed = dm.cards, dm.fixed
+    free = np.nonzero(fixed < 0)[0]
+    n = 64 if len(free) > 1 else 4
+    states = random_states(rng, cards, fixed, n)
+    vs = rng.choice(free, size=n)
+    got = dm.conditional(states, vs, precision=gb.F32)
+    for i in range(n):
+        ref = samp.conditional(int(vs[i]), states[i])
+        p, q = got[i] / got[i].sum(), ref / ref.sum()
+        assert np.allclose(p, q, rtol=1e-4, atol=0), (name, int(vs[i]))
+
+
+def test_conditional_errors(res):
+    dm, _ = load_pair(res, "Promedus_11.uai", True)
+    st = random_states(np.random.default_rng(1), dm.cards, dm.fixed, 1)
+    with pytest.raises(gb.GrampleError):  # gibbs-simple.go:167-169
+        dm.conditional(st, [158])
+    bad = st.copy()
+    bad[0, 0] = 2
+    with pytest.raises(gb.GrampleError):  # function.go:193-195
+        dm.conditional(bad, [1])
+
+
+# ------------------------------------------------------------------ initial state (K6)
+@pytest.mark.parametrize("name,evid", [("Grids_11.uai", False), ("Pedigree_11.uai", True), ("ObjectDetection_11.uai", False)])
+def test_init_state(res, name, evid):
+    dm, _ = load_pair(res, name, evid)
+    n_chains, seed, first = 10, 99, 8
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, device=0)
+    st = ch.get_state(0, n_chains)
+    cards, fixed = dm.cards, dm.fixed
+    for c in range(n_chains):
+        for v in range(dm.n_vars):
+            exp = fixed[v] if fixed[v] >= 0 else oracle.philox_init_value(seed, first + c, v, int(cards[v]))
+            assert st[c, v] == exp
+    # state round trip through the ABI
+    rng = np.random.default_rng(0)
+    new = random_states(rng, cards, fixed, n_chains)
+    ch.set_state(0, new)
+    assert np.array_equal(ch.get_state(0, n_chains), new)
+    bad = new.copy()
+    bad[0, 0] = int(cards[0])
+    with pytest.raises(gb.GrampleError):
+        ch.set_state(0, bad)
+
+
+# ------------------------------------------------------------------ sweeps (K1): bit-exact trajectories
+@pytest.mark.parametrize("name,evid,n_chains,n_sweeps", [
+    ("one.uai", False, 4, 50), ("sample.uai", False, 6, 40), ("deterministic.uai", False, 8, 40),
+    ("Grids_11.uai", False, 16, 12), ("Promedus_11.uai", True, 8, 6), ("Pedigree_11.uai", True, 8, 6),
+    ("ObjectDetection_11.uai", False, 8, 10), ("dv-rel_1.uai", True, 5, 8)])
+def test_sweep_bitexact_f64(res, name, evid, n_chains, n_sweeps):
+    dm, om = load_pair(res, name, evid)
+    order, coff = dm.schedule()
+    seed, first = 4242, 12
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0)
+    st0 = ch.get_state(0, n_chains)
+    ch.burnin(2)
+    ch.sweep(n_sweeps, record=True)
+    st1 = ch.get_state(0, n_chains)
+    counts = ch.group_counts(0).astype(np.float64)
+    assert ch.total_samples == n_sweeps * len(order) * n_chains
+
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, _ = samp.sweep_run(order, seed, first, st0, 0, 2, bits=53, record=False)
+    ost, ocounts = samp.sweep_run(order, seed, first, ost, 2, n_sweeps, bits=53, record=True)
+    assert np.array_equal(ost, st1)
+    assert np.array_equal(ocounts, counts)
+    # every sampled variable is recorded exactly once per sweep per chain; fixed ones never
+    per_var = np.add.reduceat(counts, np.concatenate([[0], np.cumsum(dm.cards)[:-1]]))
+    exp = np.where(dm.fixed < 0, n_sweeps * n_chains, 0)
+    assert np.array_equal(per_var, exp)
+
+
+def test_sweep_independent_of_sharding(res):
+    """Philox is keyed by the global chain id: chains 8..15 of a 16-chain run == an 8-chain shard."""
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    a = gb.Chains(dm, 16, seed=7, first_chain_id=0, device=0)
+    b = gb.Chains(dm, 8, seed=7, first_chain_id=8, device=0)
+    assert np.array_equal(a.get_state(0, 16)[8:], b.get_state(0, 8))
+    a.sweep(9)
+    b.sweep(9)
+    assert np.array_equal(a.get_state(0, 16)[8:], b.get_state(0, 8))
+
+
+def test_colouring_is_proper(res):
+    for name, evid in MODELS:
+        dm = gb.Model.from_uai(res(name), use_evidence=evid, device=0)
+        order, coff = dm.schedule()
+        fixed = dm.fixed
+        assert sorted(order.tolist()) == [v for v in range(dm.n_vars) if fixed[v] < 0]
+        colour = {}
+        for c in range(len(coff) - 1):
+            for v in order[coff[c]:coff[c + 1]]:
+                colour[int(v)] = c
+        for f in range(dm.n_funcs):
+            sc = [int(v) for v in dm.func_scope(f) if int(v) in colour]
+            assert len({colour[v] for v in sc}) == len(set(sc)), (name, f)
+
+
+# ------------------------------------------------------------------ MergeChains (a9)
+def test_merged_marginals(res):
+    dm, _ = load_pair(res, "Pedigree_11.uai", True)
+    n_chains = 12
+    ch = gb.Chains(dm, n_chains, seed=5, device=0)
+    ch.sweep(20)
+    counts = ch.group_counts(0).astype(np.float64)
+    merged, col = ch.merged_marginals()
+    prior = np.concatenate([np.full(c, n_chains / c) for c in dm.cards])
+    assert np.allclose(merged, counts + prior, rtol=1e-14)
+    assert not col.any()
+    p, n = ch.merge_partial_dev()
+    assert n == dm.total_card and p
+    m2, _ = ch.merge_finalize()
+    assert np.array_equal(m2, merged)
+
+
+# ------------------------------------------------------------------ collapse (K3) + collapsed sweeps (K2)
+@pytest.mark.parametrize("name,evid,vars_", [
+    ("sample.uai", False, [0, 1, 2]), ("deterministic.uai", False, [0, 1, 2]), ("Grids_11.uai", False, [0, 37, 99]),
+    ("Promedus_11.uai", True, [0, 5, 100, 300]), ("Pedigree_11.uai", True, [1, 50, 200, 384]),
+    ("ObjectDetection_11.uai", False, None)])
+def test_collapse_parity(res, name, evid, vars_):
+    dm, om = load_pair(res, name, evid)
+    if vars_ is None:  # ObjectDetection: card 11 -> only small blankets fit the 2^23 cap
+        vars_ = [v for v in range(dm.n_vars) if dm.blanket_size(v) <= 5][:3]
+        assert vars_
+    for v in vars_:
+        if dm.fixed[v] >= 0:
+            continue
+        oc = om.clone()
+        osamp = oracle.Sampler(oracle.Generator(2), oc, collapsed=True)
+        assert dm.blanket_size(v) == osamp.blanket_size(v)
+        assert dm.function_count(v) == osamp.function_count(v)
+        try:
+            ov, omarg = osamp.collapse(v)
+        except oracle.OracleError:
+            with pytest.raises(gb.GrampleError):
+                dm.collapse(v)
+            continue
+        nm, dv, dmarg = dm.collapse(v)
+        assert dv == ov == v
+        assert np.allclose(dmarg, omarg, rtol=1e-9)
+        assert nm.collapsed.tolist() == oc.collapsed.tolist()
+        assert nm.n_funcs == oc.n_funcs
+        for f in range(nm.n_funcs):
+            assert nm.func_scope(f).tolist() == oc.func_scope(f).tolist()
+            assert np.allclose(nm.func_log_table(f), oc.func_table(f), rtol=1e-9, atol=1e-12)
+        # K2: sweeps over the collapsed model, bit-exact against the oracle's collapsed sampler
+        order, _ = nm.schedule()
+        assert v not in order
+        n_chains, seed = 8, 31
+        ch = gb.Chains(nm, n_chains, seed=seed, device=0)
+        st0 = ch.get_state(0, n_chains)
+        ch.sweep(5)
+        ost, ocounts = osamp.sweep_run(order, seed, 0, st0, 0, 5, bits=53, record=True)
+        assert np.array_equal(ost, ch.get_state(0, n_chains))
+        assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+        merged, col = ch.merged_marginals()
+        assert col[v] == 1
+        o = int(np.cumsum(np.concatenate([[0], dm.cards]))[v])
+        assert np.allclose(merged[o:o + dm.cards[v]], omarg, rtol=1e-9)
+
+
+def test_working_gibbs_collapsed(res):
+    """sampler/gibbs-collapsed_test.go:14-48 through the C ABI"""
+    dm, _ = load_pair(res, "deterministic.uai", False)
+    assert dm.collapsed.tolist() == [0, 0, 0]
+    for i in range(3):
+        nm, v, marg = dm.collapse(i)
+        assert v == i
+        assert nm.collapsed.tolist() == [int(j == i) for j in range(3)]
+        assert marg[0] == pytest.approx(0.5, rel=1e-5) and marg[1] == pytest.approx(0.5, rel=1e-5)
+
+
+def test_full_gibbs_collapsed(res):
+    """sampler/gibbs-collapsed_test.go:51-111 through the C ABI (Collapse is a pure function here)"""
+    dm, _ = load_pair(res, "sample.uai", False)
+    m1, v, _ = dm.collapse(0)
+    assert v == 0 and m1.collapsed.tolist() == [1, 0, 0]
+    m2, v, _ = m1.collapse(1)
+    assert v == 1 and m2.collapsed.tolist() == [1, 1, 0]
+    r1, _, _ = dm.collapse(-1, seed=42)
+    assert int(r1.collapsed.sum()) == 1
+    r2, _, _ = r1.collapse(-1, seed=43)
+    assert int(r2.collapsed.sum()) == 2
+    with pytest.raises(gb.GrampleError):  # at least one variable must remain uncollapsed
+        r2.collapse(-1, seed=44)
+    with pytest.raises(gb.GrampleError):
+        m1.collapse(0)  # already collapsed
+    pm, _ = load_pair(res, "Promedus_11.uai", True)
+    with pytest.raises(gb.GrampleError):
+        pm.collapse(158)  # fixed by evidence
+    with pytest.raises(gb.GrampleError):
+        pm.collapse(100000)
+
+
+def test_merge_collapsed_any_group_wins(res):
+    """chain.go:113-139 / chain_test.go:49-66: collapsed in any chain -> that chain's marginal, no summation"""
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    nm, v, marg = dm.collapse(17)
+    ch = gb.Chains([dm, nm], [8, 4], seed=3, device=0)
+    ch.sweep(10)
+    merged, col = ch.merged_marginals()
+    assert col.tolist() == [int(i == 17) for i in range(100)]
+    assert np.allclose(merged[34:36], marg, rtol=1e-12)
+    c0, c1 = ch.group_counts(0).astype(float), ch.group_counts(1).astype(float)
+    exp = c0 + c1 + 12 * 0.5
+    exp[34:36] = marg
+    assert np.allclose(merged, exp, rtol=1e-14)
+    assert c1[34:36].sum() == 0  # the collapsed variable is never sampled in its own group
+
+
+# ------------------------------------------------------------------ convergence (K4)
+@pytest.mark.parametrize("name,evid", [("Grids_11.uai", False), ("Pedigree_11.uai", True), ("ObjectDetection_11.uai", False)])
+def test_chain_convergence_parity(res, name, evid):
+    dm, _ = load_pair(res, name, evid)
+    n_chains, cw = 6, 20
+    ch = gb.Chains(dm, n_chains, seed=77, history=True, device=0)
+    ch.burnin(5)
+    ch.advance(cw)
+    assert ch.total_samples == (cw + 1) * len(dm.schedule()[0]) * n_chains
+    hist = ch.group_history(0, n_chains)  # [2][total_card][n_chains]
+    merged, _ = ch.merged_marginals()
+    cards, fixed = dm.cards, dm.fixed
+    offs = np.concatenate([[0], np.cumsum(cards)])
+    # oracle chains carrying the same windows (chain 0 holds the whole merged marginal)
+    ochains = []
+    for c in range(n_chains):
+        marg = [merged[offs[v]:offs[v + 1]] if c == 0 else np.zeros(cards[v]) for v in range(dm.n_vars)]
+        oc = oracle.Chain.from_marginals(cards, marg, cw=cw)
+        for v in range(dm.n_vars):
+            if fixed[v] >= 0:
+                oc.set_history(v, [0] * cw)
+                continue
+            seq = []
+            for half in range(2):
+                h = hist[half, offs[v]:offs[v + 1], c]
+                assert h.sum() == cw // 2
+                for k in range(cards[v]):
+                    seq += [k] * int(h[k])
+            oc.set_history(v, seq)
+        ochains.append(oc)
+    free = fixed < 0
+    for which in (gb.HELLINGER, gb.JS, gb.MAX_ABS, gb.MEAN_ABS):
+        got = ch.convergence(which)
+        ref = oracle.chain_convergence(ochains, which, dm.n_vars)
+        assert np.allclose(got[free], ref[free], rtol=1e-9), which
+        assert np.all(got[~free] == 1.0)
+    # multi-device form gives the same numbers
+    p, n = ch.convergence_partial_dev(gb.HELLINGER, merged)
+    assert n == 2 * dm.n_vars and p
+
+
+def test_convergence_requires_history_and_chains(res):
+    dm, _ = load_pair(res, "sample.uai", False)
+    ch = gb.Chains(dm, 4, seed=1, history=False, device=0)
+    ch.advance(10)
+    with pytest.raises(gb.GrampleError):
+        ch.convergence()
+    ch1 = gb.Chains(dm, 1, seed=1, history=True, device=0)
+    ch1.advance(10)
+    with pytest.raises(gb.GrampleError):  # chain.go:33-35
+        ch1.convergence()
+    ch2 = gb.Chains(dm, 4, seed=1, history=True, device=0)
+    with pytest.raises(gb.GrampleError):  # chain.go:255-257
+        ch2.convergence()
+
+
+# ------------------------------------------------------------------ adaptive (a12)
+def test_adapt(res):
+    dm, om = load_pair(res, "Pedigree_11.uai", True)
+    cw, per = 20, 8
+    ch = gb.Chains(dm, per, seed=9, history=True, device=0)
+    ch.burnin(5)
+    ch.advance(cw)
+    conv = ch.convergence(gb.HELLINGER)
+    fixed = dm.fixed
+    cand = [v for v in range(dm.n_vars) if fixed[v] < 0 and 1 < dm.blanket_size(v) <= 12]
+    chosen = ch.adapt(dm, 4, per, cw, first_chain_id=per)
+    assert len(chosen) == 4 and ch.n_groups == 5 and ch.n_chains == 5 * per
+    assert set(chosen) <= set(cand)
+    others = [conv[v] for v in cand if v not in chosen]
+    assert max(conv[v] for v in chosen) <= min(others) + 1e-12  # LOWEST scores (adaptive.go:111-119)
+    merged, col = ch.merged_marginals()
+    assert sorted(np.nonzero(col)[0].tolist()) == sorted(chosen)
+    ch.advance(cw)
+    conv2 = ch.convergence(gb.HELLINGER)
+    assert np.all(conv2[np.nonzero(col)[0]] == 1.0)
+    # already-collapsed variables are no longer candidates
+    chosen2 = ch.adapt(dm, 4, per, cw, first_chain_id=5 * per)
+    assert not (set(chosen2) & set(chosen))
+    # no-op at the group cap (adaptive.go:62-64)
+    assert ch.adapt(dm, 4, per, cw, first_chain_id=9 * per, max_groups=ch.n_groups) == []
+
+
+# ------------------------------------------------------------------ parity level 2: statistics vs .MAR
+def test_objectdetection_marginals_f32(res):
+    """the reference algorithm reaches mean Hellinger < 0.01 on ObjectDetection_11 at
+    ~1 M recorded updates; the device sampler must do no worse at equal recorded updates."""
+    dm, _ = load_pair(res, "ObjectDetection_11.uai", False)
+    cards, mar = gb.mar_load(res("ObjectDetection_11.uai.MAR"))
+    ch = gb.Chains(dm, 512, seed=2024, precision=gb.F32, device=0)
+    ch.burnin(200)
+    ch.sweep(40)  # 512 * 40 * 60 = 1.23 M recorded updates
+    merged, _ = ch.merged_marginals()
+    es = gb.error_suite(cards, mar, merged)
+    assert ch.total_samples == 512 * 40 * 60
+    assert es["MeanHellinger"] < 0.01, es
+
+
+def test_f32_matches_f64_statistically(res):
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    out = []
+    for prec in (gb.F64, gb.F32):
+        ch = gb.Chains(dm, 2048, seed=5, precision=prec, device=0)
+        ch.burnin(100)
+        ch.sweep(100)
+        m, _ = ch.merged_marginals()
+        out.append(m.reshape(-1, 2) / m.reshape(-1, 2).sum(1, keepdims=True))
+    # same target distribution; 204800 samples per variable -> se ~ 1e-3 (chains are correlated: be generous)
+    assert np.abs(out[0] - out[1]).max() < 0.05
+
+
+def test_small_model_exact_marginals(res):
+    """one.uai is a single 0.25/0.75 factor: the sampler's marginal must converge to it."""
+    dm, _ = load_pair(res, "one.uai", False)
+    for prec in (gb.F64, gb.F32):
+        ch = gb.Chains(dm, 1024, seed=1, precision=prec, device=0)
+        ch.sweep(200)
+        m, _ = ch.merged_marginals()
+        assert m[1] / m.sum() == pytest.approx(0.75, abs=0.005)
+
+
+# ------------------------------------------------------------------ full-size properties (config 5 shape)
+def test_ising_large_properties():
+    """512x512 torus, 4096 chains (the bench uses 1024x1024 x 65536): size-independent invariants."""
+    H = W = 512
+    arrays = gb.ising_torus(H, W, wmax=0.5)
+    dm = gb.Model.from_arrays(*arrays, device=0)
+    order, coff = dm.schedule()
+    assert len(coff) - 1 == 2 and len(order) == H * W  # checkerboard
+    n_chains, n_sweeps = 4096, 3
+    ch = gb.Chains(dm, n_chains, seed=3, precision=gb.F32, device=0)
+    ch.sweep(n_sweeps)
+    counts = ch.group_counts(0).reshape(-1, 2)
+    assert np.all(counts.sum(1) == n_chains * n_sweeps)
+    assert ch.total_samples == H * W * n_chains * n_sweeps
+    merged, _ = ch.merged_marginals()
+    assert np.allclose(merged.reshape(-1, 2).sum(1), n_chains * (n_sweeps + 1))
+    # sign of the unary field shows in the marginals on average (weak couplings)
+    card, fixed, scope_off, scope_vars, tab_off, tables = arrays
+    h_pos = tables[0:2 * H * W:2] > tables[1:2 * H * W:2]  # e^h > e^-h -> value 0 favoured
+    p0 = counts[:, 0] / counts.sum(1)
+    assert p0[h_pos].mean() > 0.55 and p0[~h_pos].mean() < 0.45
