@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — variable-updates/sec of the Gibbs sweep hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[4] — synthetic 1024x1024 binary Ising torus
+(1 M variables, 3 M factors), 2-colour sweep, float32 arithmetic, 65536 chains per GPU
+(64 GiB of uint8 state per GPU, so inputs are far larger than the 126 MB L2 and no flush is
+needed between timed steps).  One "step" = one systematic sweep of every chain
+(n_vars x chains recorded single-variable updates).  Chains shard across GPUs with no
+data-path collective (weak scaling: fixed chains per GPU); the only exchange is the all-reduce
+of the marginal counts at the monitor interval, which is part of the e2e figure.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--chains C] [--side S]
+
+Under torchrun (N > 1) every rank drives its own GPU; times are device times (CUDA events on
+the library's stream), max over ranks.  `--impl reference` times the reference algorithm's CPU
+restatement (oracle, "lean" variant, one thread per host core) on a bounded sample of the same
+workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "variable_updates_per_sec"
+UNIT = "updates/s"
+GATHER_BYTES_PER_UPDATE = 5.0  # 4 distinct neighbours read + 1 state byte written (uint8 state)
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
+    ap.add_argument("--side", type=int, default=1024, help="torus side (variables = side^2)")
+    ap.add_argument("--wmax", type=float, default=4.9)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.3 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[5 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def cpu_reference_throughput(arrays, seconds, threads):
+    """The reference algorithm's CPU restatement (oracle, lean variant) on a bounded sample of the
+    workload: `threads` chains over the same model, one std::thread each (chain.go:197-215)."""
+    import oracle
+    om = oracle.Model.create(*arrays)
+    # calibrate on a short run, then size the sample for ~`seconds`
+    ups, secs = oracle.throughput(om, n_threads=threads, steps=20000, seed=1, lean=True)
+    rate = ups / max(secs, 1e-9)
+    steps = max(20000, int(rate * seconds / threads))
+    ups, secs = oracle.throughput(om, n_threads=threads, steps=steps, seed=2, lean=True)
+    return ups / secs, ups, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import grample_b200 as gb
+    threads = os.cpu_count() or 1
+    arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)
+    import oracle
+    om = oracle.Model.create(*arrays)
+    per_step = max(20000, int(2.0e5 * 1.0))  # recorded updates per thread per step (bounded sample)
+    for _ in range(args.warmup):
+        oracle.throughput(om, n_threads=threads, steps=per_step // 4, seed=1, lean=True)
+    tot_u, tot_s = 0, 0.0
+    for i in range(args.steps):
+        ups, secs = oracle.throughput(om, n_threads=threads, steps=per_step, seed=10 + i, lean=True)
+        tot_u += ups
+        tot_s += secs
+    value = tot_u / tot_s
+    sample = (f"{threads} chains x {per_step} recorded single-variable updates per step on the {args.side}x{args.side} "
+              f"Ising torus (random scan, float64, lean bookkeeping), {args.steps} steps")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"ising_torus_{args.side}x{args.side}", "chains": threads, "schedule": "random scan"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+    import grample_b200 as gb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prec = gb.F32 if args.precision == "f32" else gb.F64
+    t_setup = time.time()
+    arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)
+    model = gb.Model.from_arrays(*arrays, device=dev)
+    n_vars = model.n_vars
+    order, coff = model.schedule()
+    n_colours = len(coff) - 1
+    chains = gb.Chains(model, args.chains, seed=20260101, first_chain_id=rank * args.chains, precision=prec, device=dev)
+    chains.synchronize()
+    setup_s = time.time() - t_setup
+    updates_per_step = n_vars * args.chains  # per GPU
+
+    for _ in range(args.warmup):
+        chains.sweep(1, record=True)
+    chains.synchronize()
+
+    # ---------------- timed region: exactly K steps, device time, max over ranks
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = chains.launch_count
+    barrier()
+    t0 = time.time()
+    ms = chains.sweep_timed(args.steps, record=True)
+    barrier()
+    t1 = time.time()
+    launches = chains.launch_count - launches0
+    clocks = sampler.stop(t0, t1)
+    if dist is not None:
+        t = torch.tensor([ms], device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * updates_per_step * args.steps / (ms * 1e-3)
+
+    # ---------------- e2e: the call a user makes each monitor interval (cmd/root.go:475-539):
+    # advance -> MergeChains read back to the host -> score.  H2D inside: the collapsed flags the
+    # merge uploads; D2H: the merged marginals (sum(card) float64) + the sample count.
+    total_card = model.total_card
+    mar = np.full(total_card, 0.5)
+    cards = model.cards
+    barrier()
+    e0 = time.time()
+    for _ in range(args.steps):
+        chains.sweep(1, record=True)
+        if dist is not None:
+            ptr, n = chains.merge_partial_dev()
+            # all-reduce of the marginal counts over NVLink at the monitor interval
+            buf = torch.empty(0)
+            arr = _DevArray(ptr, n)
+            tens = torch.as_tensor(arr, device=f"cuda:{dev}")
+            dist.all_reduce(tens)
+            merged, _ = chains.merge_finalize()
+        else:
+            merged, _ = chains.merged_marginals()
+        _ = chains.total_samples
+    barrier()
+    e_ms = (time.time() - e0) * 1e3
+    if dist is not None:
+        t = torch.tensor([e_ms], device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e2e_value = world * updates_per_step * args.steps / (e_ms * 1e-3)
+    score = gb.error_suite(cards, mar, merged)  # host scoring of the read-back (untimed sanity use)
+
+    # ---------------- roofline of the dominant kernel (one launch = one colour of one sweep)
+    peak, peak_src = hbm_peak()
+    launch_ms = ms / (args.steps * n_colours)
+    updates_per_launch = updates_per_step / n_colours
+    achieved = GATHER_BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_colour<float,2,4>",
+                "algorithmic_bytes_per_update": GATHER_BYTES_PER_UPDATE, "updates_per_launch": updates_per_launch,
+                "launch_ms": launch_ms}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, ups, secs = cpu_reference_throughput(arrays, args.cpu_seconds, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{threads} chains x {ups // threads} recorded updates on the same {args.side}x{args.side} Ising torus, "
+                         f"random scan float64 oracle (lean bookkeeping), {secs:.1f} s"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"ising_torus_{args.side}x{args.side}", "variables": n_vars, "factors": 3 * n_vars,
+                       "chains_per_gpu": args.chains, "colours": n_colours, "wmax": args.wmax, "state": "uint8 [var][chain]",
+                       "l2_policy": "inputs (state %.1f GiB per GPU) larger than L2, no flush" % (n_vars * args.chains / 2**30),
+                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
+                       "setup_seconds": round(setup_s, 2)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_vars),
+                    "d2h_bytes_per_step": int(total_card * 8 + 8), "ms_per_step": e_ms / args.steps,
+                    "path": "gb_chains_sweep + gb_chains_merged_marginals (host buffers) per step"},
+            "roofline": roofline, "sanity": {"mean_hellinger_vs_uniform": score["MeanHellinger"]}}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of a device float64 buffer owned by the library, so
+    torch.distributed can all-reduce it in place."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

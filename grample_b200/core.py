@@ -184,6 +184,18 @@ class Chains:
     def sweep(self, n_sweeps, record=True):
         check(lib().gb_chains_sweep(self.h, int(n_sweeps), int(record)))
 
+    def sweep_timed(self, n_sweeps, record=True):
+        """sweeps bracketed by CUDA events on the library's stream; returns device milliseconds"""
+        ms = C.c_float()
+        check(lib().gb_chains_sweep_timed(self.h, int(n_sweeps), int(record), C.byref(ms)))
+        return ms.value
+
+    @property
+    def launch_count(self):
+        v = C.c_int64()
+        check(lib().gb_chains_launch_count(self.h, C.byref(v)))
+        return v.value
+
     def burnin(self, n_sweeps):
         check(lib().gb_chains_burnin(self.h, int(n_sweeps)))
 

@@ -132,6 +132,8 @@ struct gb_chains {
     uint8_t* d_skip = nullptr;  // [n_vars]
     double* d_merged_in = nullptr;
     int32_t last_cw = -1;       // ConvergenceWindow of the last gb_chains_advance
+    int64_t launches = 0;       // kernels launched on behalf of this handle
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     ~gb_chains() {
         cudaSetDevice(device);
@@ -145,6 +147,8 @@ struct gb_chains {
         cudaFree(d_wb);
         cudaFree(d_skip);
         cudaFree(d_merged_in);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
     }
     const gb::HostModel& base() const { return groups[0].model->h; }
@@ -185,6 +189,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     g.dev.seed_hi = (uint32_t)(c->seed >> 32);
     const int64_t items = (int64_t)h.n_vars * (g.n_pad / 4);
     gb::k_init_state<<<grid_for(items, 256), 256, 0, c->stream>>>(model->dev, g.dev);
+    c->launches++;
     CUDA_CHECK(cudaGetLastError());
     c->groups.push_back(g);
 }
@@ -194,6 +199,7 @@ void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int
     const int64_t items = (int64_t)n * (g.n_pad / 4);
     gb::k_sweep_colour<Real, MAXC, CW><<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, d_vars, n,
                                                                                    g.sweep, record, hist_half);
+    c->launches++;
 }
 
 // one sweep of one group: one launch per colour
@@ -264,6 +270,7 @@ void merge_partial(gb_chains* c) {
     for (auto& g : c->groups)
         gb::k_merge_partial<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(g.model->dev, g.d_counts,
                                                                               (double)g.n_chains, c->d_skip, c->d_merge);
+    c->launches += (int64_t)c->groups.size();
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaStreamSynchronize(c->stream));  // col goes out of scope
 }
@@ -306,6 +313,7 @@ void convergence_partial(gb_chains* c, int measure, const double* merged) {
         const int64_t items = (int64_t)h.n_vars * g.n_chains;
         gb::k_chain_dist<<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, c->d_merged_in, c->d_skip,
                                                                      measure, c->d_wb);
+        c->launches++;
     }
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -609,6 +617,21 @@ int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record) {
     GB_TRY sweeps(c, n_sweeps, record, -1);
     GB_END
 }
+int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_out) {
+    GB_TRY
+    CUDA_CHECK(cudaSetDevice(c->device));
+    if (!c->ev0) {
+        CUDA_CHECK(cudaEventCreate(&c->ev0));
+        CUDA_CHECK(cudaEventCreate(&c->ev1));
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    sweeps(c, n_sweeps, record, -1);
+    CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+    CUDA_CHECK(cudaEventSynchronize(c->ev1));
+    CUDA_CHECK(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
+    GB_END
+}
+int gb_chains_launch_count(const gb_chains* c, int64_t* out) { *out = c->launches; return 0; }
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps) {
     GB_TRY sweeps(c, n_sweeps, 0, -1);
     GB_END

@@ -73,7 +73,6 @@ struct HostModel {
         if (sz != n_raw) throw Err("Read table size " + std::to_string(n_raw) + " != Clique size " + std::to_string(sz));
         f.off = (int64_t)log_tab.size();
         f.size = sz;
-        log_tab.reserve(log_tab.size() + sz);
         const double eps = 1e-6;
         for (int64_t i = 0; i < sz; i++) {
             double v = raw[i];

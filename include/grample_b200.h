@@ -118,6 +118,11 @@ int gb_chains_n_chains(const gb_chains* c, int64_t* out);
  * un-collapsed variable once (= n_free reference steps, chain.go:221-246).  record != 0 adds
  * each draw to the marginal counts (chain.go:231-236) and TotalSampleCount. */
 int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record);
+/* gb_chains_sweep bracketed by CUDA events on the handle's own stream (device time of exactly
+ * these sweeps, in milliseconds); returns after they finish.  Measurement hook for bench.py. */
+int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_out);
+/* number of kernels launched on behalf of this handle so far */
+int gb_chains_launch_count(const gb_chains* c, int64_t* out);
 /* burn-in (chain.go:167-172): un-recorded.  The reference counts single-variable steps;
  * callers convert with ceil(steps / n_free). */
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps);
