@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
     ap.add_argument("--side", type=int, default=1024, help="torus side (variables = side^2)")
     ap.add_argument("--wmax", type=float, default=4.9)
-    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--precision", default="table", choices=["table", "f32", "f64"],
+                    help="table: float64 conditionals tabulated per neighbour configuration, integer sweep")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -161,7 +162,9 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    prec = gb.F32 if args.precision == "f32" else gb.F64
+    prec = {"table": gb.TABLE, "f32": gb.F32, "f64": gb.F64}[args.precision]
+    kernel = {"table": "k_sweep_tab<16>", "f32": "k_sweep_colour<float,2,4>", "f64": "k_sweep_colour<double,2,4>"}[args.precision]
+    dtype = {"table": "u32", "f32": "f32", "f64": "f64"}[args.precision]
     t_setup = time.time()
     arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)
     model = gb.Model.from_arrays(*arrays, device=dev)
@@ -231,7 +234,7 @@ def run_native(args):
     updates_per_launch = updates_per_step / n_colours
     achieved = GATHER_BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_colour<float,2,4>",
+                "traffic": None, "peak_source": peak_src, "kernel": kernel,
                 "algorithmic_bytes_per_update": GATHER_BYTES_PER_UPDATE, "updates_per_launch": updates_per_launch,
                 "launch_ms": launch_ms}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
@@ -256,8 +259,8 @@ def run_native(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"ising_torus_{args.side}x{args.side}", "variables": n_vars, "factors": 3 * n_vars,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"mode": args.precision, "workload": f"ising_torus_{args.side}x{args.side}", "variables": n_vars, "factors": 3 * n_vars,
                        "chains_per_gpu": args.chains, "colours": n_colours, "wmax": args.wmax, "state": "uint8 [var][chain]",
                        "l2_policy": "inputs (state %.1f GiB per GPU) larger than L2, no flush" % (n_vars * args.chains / 2**30),
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import F32, F64, HELLINGER, GrampleError, check, lib
+from ._lib import F32, F64, HELLINGER, TABLE, GrampleError, check, lib
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -123,6 +123,19 @@ class Model:
         coff = np.zeros(nc.value + 1, dtype=np.int32)
         check(lib().gb_model_schedule(self.h, None, None, _ptr(order, _i32p), _ptr(coff, _i32p)))
         return order, coff
+
+    def table_mode(self):
+        """(applies?, number of tabulated configurations) for precision=TABLE"""
+        ok, n = C.c_int32(), C.c_int64()
+        check(lib().gb_model_table_mode(self.h, C.byref(ok), C.byref(n)))
+        return bool(ok.value), n.value
+
+    def thresholds(self, var):
+        n = C.c_int32()
+        check(lib().gb_model_thresholds(self.h, int(var), C.byref(n), None))
+        out = np.zeros(n.value, dtype=np.uint32)
+        check(lib().gb_model_thresholds(self.h, int(var), None, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
 
     def collapse(self, var=-1, seed=0):
         """(*GibbsCollapsed).Collapse as a pure function: (new Model, collapsed var, its local marginal)."""

@@ -67,6 +67,8 @@ struct gb_model {
     std::vector<void*> allocs;
     gb::DevModel dev{};
     int32_t* d_order = nullptr;
+    gb::DevTab tab{};
+    bool tab_built = false;
 
     ~gb_model() {
         if (device >= 0) {
@@ -100,6 +102,24 @@ struct gb_model {
         dev.tab32 = up(tab32);
         dev.entry_var = up(entry_var);
         d_order = up(h.order);
+    }
+    // table mode: evaluate every (variable, neighbour configuration) conditional once on the device
+    void ensure_tab() {
+        if (tab_built) return;
+        if (device < 0) throw gb::Err("table mode needs a device-resident model (there is no CPU fallback)");
+        if (!h.tab_ok) throw gb::Err("table mode does not apply to this model: " + h.tab_why);
+        require_device(device);
+        tab.tp_off = up(h.tp_off);
+        tab.tprog = up(h.tprog);
+        uint32_t* thr = nullptr;
+        CUDA_CHECK(cudaMalloc(&thr, (size_t)std::max<int64_t>(h.n_thresholds, 1) * sizeof(uint32_t)));
+        allocs.push_back(thr);
+        tab.thr = thr;
+        const int n = (int)h.order.size();
+        gb::k_build_thresholds<<<std::max(1, std::min((n + 127) / 128, 148 * 16)), 128>>>(dev, tab, d_order, n);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaDeviceSynchronize());
+        tab_built = true;
     }
 };
 
@@ -160,7 +180,8 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     if (!model) throw gb::Err("No model supplied");
     if (model->device != c->device) throw gb::Err("model lives on a different device than the chains");
     if (n_chains < 1) throw gb::Err("a chain group needs at least 1 chain");
-    if (first_chain % 4) throw gb::Err("first_chain_id must be a multiple of 4 (Philox quads)");
+    if (first_chain % 8) throw gb::Err("first_chain_id must be a multiple of 8 (chains share Philox calls in blocks of 8)");
+    if (c->precision == GB_TABLE) model->ensure_tab();
     if (!c->groups.empty() && (model->h.n_vars != c->base().n_vars || model->h.card != c->base().card))
         throw gb::Err("Cannot merge chain with different variables");
     if (model->h.order.empty()) throw gb::Err("No Variables to select");
@@ -168,7 +189,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     g.model = model;
     g.owns_model = owns;
     g.n_chains = n_chains;
-    g.n_pad = (n_chains + 3) / 4 * 4;
+    g.n_pad = (n_chains + 7) / 8 * 8;
     g.first_chain = first_chain;
     const gb::HostModel& h = model->h;
     CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
@@ -211,7 +232,20 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         const int32_t* dv = g.model->d_order + h.colour_off[col];
         const int32_t n = h.colour_off[col + 1] - h.colour_off[col];
         if (n == 0) continue;
-        if (c->precision == GB_F32) {
+        if (c->precision == GB_TABLE) {
+            constexpr int VB = 16;
+            const int64_t tiles = (int64_t)((g.n_pad / 8 + 255) / 256) * ((n + VB - 1) / VB);
+            static int resident = 0;  // CTAs that fit the device at once (persistent grid-stride loop)
+            if (!resident) {
+                int per_sm = 0, sms = 0;
+                CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB>, 256, 0));
+                CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+                resident = std::max(1, per_sm * sms);
+            }
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
+            gb::k_sweep_tab<VB><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, dv, n, g.sweep, record, hist_half);
+            c->launches++;
+        } else if (c->precision == GB_F32) {
             if (mc <= 2) launch_colour<float, 2, 4>(c, g, dv, n, record, hist_half);
             else if (mc <= 4) launch_colour<float, 4, 4>(c, g, dv, n, record, hist_half);
             else if (mc <= 8) launch_colour<float, 8, 4>(c, g, dv, n, record, hist_half);
@@ -535,6 +569,24 @@ int gb_model_schedule(const gb_model* m, int32_t* n_order, int32_t* n_colours, i
     if (colour_off) std::copy(m->h.colour_off.begin(), m->h.colour_off.end(), colour_off);
     GB_END
 }
+int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out) {
+    GB_TRY
+    if (ok_out) *ok_out = m->h.tab_ok ? 1 : 0;
+    if (n_thresholds_out) *n_thresholds_out = m->h.n_thresholds;
+    GB_END
+}
+int gb_model_thresholds(gb_model* m, int32_t var, int32_t* n_out, uint32_t* out) {
+    GB_TRY
+    if (var < 0 || var >= m->h.n_vars) throw gb::Err("Invalid variable index");
+    m->ensure_tab();
+    if (m->h.tp_off[var] < 0) throw gb::Err("variable is not sampled");
+    const int32_t* tp = m->h.tprog.data() + m->h.tp_off[var];
+    int n = 1;
+    for (int i = 0; i < tp[0]; i++) n *= m->h.card[tp[2 + 2 * i]];
+    if (n_out) *n_out = n;
+    if (out) CUDA_CHECK(cudaMemcpy(out, m->tab.thr + tp[1], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    GB_END
+}
 int gb_model_collapse(const gb_model* src, int32_t var, uint64_t seed, int32_t* collapsed_var_out,
                       double* marginal_out, gb_model** out) {
     if (collapsed_var_out) *collapsed_var_out = -1;
@@ -581,7 +633,7 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
                      gb_chains** out) {
     GB_TRY
     if (n_groups < 1) throw gb::Err("at least one chain group is required");
-    if (precision != GB_F64 && precision != GB_F32) throw gb::Err("unknown precision");
+    if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE) throw gb::Err("unknown precision");
     require_device(device);
     auto c = std::make_unique<gb_chains>();
     c->device = device;
@@ -592,7 +644,7 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
     uint64_t first = first_chain_id;
     for (int g = 0; g < n_groups; g++) {
         add_group(c.get(), models[g], chains_per_model[g], first, false);
-        first += (uint64_t)((chains_per_model[g] + 3) / 4 * 4);
+        first += (uint64_t)((chains_per_model[g] + 7) / 8 * 8);
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = c.release();
@@ -753,7 +805,7 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
             delete nm;
             throw;
         }
-        first += (uint64_t)((chains_per_new_model + 3) / 4 * 4);
+        first += (uint64_t)((chains_per_new_model + 7) / 8 * 8);
         // adaptive.go:145: NewChain(..., burnIn=2) — two single-variable steps; one un-recorded
         // sweep (>= 2 updates) is the sweep-granular equivalent
         sweep_group(c, c->groups.back(), 0, -1);

@@ -54,6 +54,11 @@ struct HostModel {
     std::vector<int32_t> colour;                   // per var, -1 if never sampled
     std::vector<int32_t> order, colour_off;        // colour-sorted sweep schedule
     std::vector<int32_t> prog_off, prog;           // per-variable update program (see kernels.cuh)
+    // ---- tabulated-conditional fast path (binary sampled variables, <= 256 neighbour configurations)
+    bool tab_ok = false;
+    std::string tab_why;                           // why the fast path does not apply
+    std::vector<int32_t> tp_off, tprog;            // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
+    int64_t n_thresholds = 0;
 
     bool sampled(int v) const { return fixed[v] < 0 && !collapsed[v]; }
 
@@ -113,6 +118,51 @@ struct HostModel {
         }
         build_colouring();
         build_programs();
+        build_tab_programs();
+    }
+
+    // Tabulated conditionals: for a sampled binary variable whose distinct free neighbours span
+    // C <= 256 joint configurations, the whole conditional (gibbs-simple.go:171-258) depends only
+    // on that configuration, so it is evaluated once per configuration (k_build_thresholds) and the
+    // sweep becomes: gather neighbour bytes -> configuration index -> threshold -> compare.
+    // Fixed neighbours are folded into the table (their value never changes).
+    void build_tab_programs() {
+        tab_ok = true;
+        tab_why.clear();
+        tp_off.assign(n_vars, -1);
+        tprog.clear();
+        n_thresholds = 0;
+        for (int v : order) {
+            if (card[v] != 2) {
+                tab_ok = false;
+                tab_why = "variable " + std::to_string(v) + " has cardinality " + std::to_string(card[v]) + " (table mode needs binary sampled variables)";
+                break;
+            }
+            int64_t cfgs = 1;
+            std::vector<int32_t> words;
+            for (int32_t u : nbrs[v]) {
+                if (u == v || fixed[u] >= 0) continue;
+                words.push_back(u);
+                words.push_back((int32_t)cfgs);
+                cfgs *= card[u];
+                if (cfgs > 256) break;
+            }
+            if (cfgs > 256) {
+                tab_ok = false;
+                tab_why = "variable " + std::to_string(v) + " has more than 256 neighbour configurations";
+                break;
+            }
+            tp_off[v] = (int32_t)tprog.size();
+            tprog.push_back((int32_t)words.size() / 2);
+            tprog.push_back((int32_t)n_thresholds);
+            tprog.insert(tprog.end(), words.begin(), words.end());
+            n_thresholds += cfgs;
+        }
+        if (!tab_ok) {
+            tp_off.assign(n_vars, -1);
+            tprog.clear();
+            n_thresholds = 0;
+        }
     }
 
     // Greedy colouring over the sampled variables in id order; fixed / collapsed neighbours

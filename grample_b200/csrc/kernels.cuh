@@ -164,7 +164,7 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
             const Philox4 b = philox4x32_10((uint32_t)v, sweep, (chain0 >> 1) + 1u, kTagDraw53, g.seed_lo, g.seed_hi);
             u[0] = u53(a.x, a.y); u[1] = u53(a.z, a.w); u[2] = u53(b.x, b.y); u[3] = u53(b.z, b.w);
         } else {
-            const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 2, kTagDraw32, g.seed_lo, g.seed_hi);
+            const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 2, kTagDraw24, g.seed_lo, g.seed_hi);
             u[0] = (float)(a.x >> 8) * (1.0f / 16777216.0f);
             u[1] = (float)(a.y >> 8) * (1.0f / 16777216.0f);
             u[2] = (float)(a.z >> 8) * (1.0f / 16777216.0f);
@@ -238,6 +238,162 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
                     }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------ K1-table
+// Tabulated-conditional sweep for models whose sampled variables are binary with <= 256
+// neighbour configurations (host_model.hpp::build_tab_programs).  The conditional of
+// gibbs-simple.go:171-258 is evaluated in float64 once per (variable, neighbour configuration)
+// by k_build_thresholds and stored as the largest 32-bit draw that still selects value 0 under
+// the reference's inverse-CDF rule (sampler.go:115-123: r = U*tot, r <= e0).  The sweep itself is
+// integer work: gather neighbour bytes -> configuration index -> threshold -> compare.
+struct DevTab {
+    const int32_t* tp_off;  // [n_vars]
+    const int32_t* tprog;   // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
+    uint32_t* thr;          // [n_thresholds]
+};
+
+__global__ void __launch_bounds__(128)
+k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__ order, const int32_t n_order) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_order; j += gridDim.x * blockDim.x) {
+        const int v = order[j];
+        const int32_t* tp = t.tprog + t.tp_off[v];
+        const int nn = tp[0], thr_off = tp[1];
+        int n_cfg = 1;
+        for (int i = 0; i < nn; i++) n_cfg *= m.card[tp[2 + 2 * i]];
+        const int32_t* prog = m.prog + m.prog_off[v];
+        const int nf = prog[0];
+        for (int cfg = 0; cfg < n_cfg; cfg++) {
+            double w[2] = {0.0, 0.0};
+            const int32_t* p = prog + 1;
+            for (int f = 0; f < nf; f++) {
+                const int tab_off = p[0], sv = p[1], no = p[2];
+                p += 3;
+                int b = tab_off;
+                for (int o = 0; o < no; o++, p += 2) {
+                    const int ov = p[0];
+                    int sv_o = m.fixed[ov];
+                    if (sv_o < 0) {
+                        for (int i = 0; i < nn; i++)
+                            if (tp[2 + 2 * i] == ov) sv_o = (cfg / tp[3 + 2 * i]) % m.card[ov];
+                    }
+                    b += sv_o * p[1];
+                }
+                w[0] += m.tab64[b];
+                w[1] += m.tab64[b + sv];
+            }
+            stabilise_exp_floor<double, 2>(w, 2);
+            const double tot = w[0] + w[1];  // WeightedSample re-sums (sampler.go:107-113)
+            // largest t with (t * 2^-32) * tot <= e0 — the reference predicate evaluated exactly
+            auto pred = [&](uint32_t tt) { return ((double)tt * (1.0 / 4294967296.0)) * tot <= w[0]; };
+            double c = (w[0] / tot) * 4294967296.0;
+            uint32_t tt = c >= 4294967295.0 ? 4294967295u : (uint32_t)c;
+            while (tt < 4294967295u && pred(tt + 1u)) tt++;
+            while (tt > 0u && !pred(tt)) tt--;
+            t.thr[thr_off + cfg] = tt;
+        }
+    }
+}
+
+// CTA tile = (chunk of 2048 consecutive chains) x (VB consecutive variables of the colour); every
+// thread keeps the same 8 chains (one 64-bit state word per variable) for the whole tile, so the
+// wave front of concurrently processed tiles stays L2-resident and shared neighbours of
+// consecutive variables hit L1.  One Philox call yields the 16-bit high halves of 8 draws; the low
+// halves are generated only when a high half ties with its threshold (probability 2^-16).
+template <int VB>
+__global__ void __launch_bounds__(256)
+k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ vars,
+            const int32_t n_vars_c, const uint32_t sweep, const int record, const int hist_half) {
+    __shared__ unsigned int s_ones[VB];
+    const int units = g.n_pad >> 3;
+    const int chunks = (units + 255) >> 8;
+    const int n_vb = (n_vars_c + VB - 1) / VB;
+    const int64_t n_tiles = (int64_t)chunks * n_vb;
+    const int lane = threadIdx.x & 31;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int chunk = (int)(tile / n_vb);
+        const int vb = (int)(tile - (int64_t)chunk * n_vb);
+        const int unit = chunk * 256 + threadIdx.x;
+        const bool active = unit < units;
+        const int nvalid = active ? max(0, min(8, g.n_chains - 8 * unit)) : 0;
+        const uint32_t vmask = (nvalid >= 8) ? 0xffu : ((1u << nvalid) - 1u);
+        const uint32_t chain_blk = (uint32_t)((g.first_chain >> 3) + (uint64_t)unit);
+        if (threadIdx.x < VB) s_ones[threadIdx.x] = 0;
+        __syncthreads();
+        const int j_end = min(n_vars_c, (vb + 1) * VB);
+        for (int j = vb * VB; j < j_end; j++) {
+            const int v = __ldg(vars + j);
+            unsigned ones = 0;
+            if (active) {
+                const int32_t* __restrict__ tp = t.tprog + __ldg(t.tp_off + v);
+                const int nn = __ldg(tp);
+                const uint32_t* __restrict__ thr = t.thr + __ldg(tp + 1);
+                uint32_t cfg_lo = 0, cfg_hi = 0;
+                for (int i = 0; i < nn; i++) {
+                    const int ov = __ldg(tp + 2 + 2 * i);
+                    const uint32_t st = (uint32_t)__ldg(tp + 3 + 2 * i);
+                    const uint2 s8 = *reinterpret_cast<const uint2*>(g.state + (size_t)ov * g.n_pad + 8 * (size_t)unit);
+                    cfg_lo += s8.x * st;  // packed bytes: no carries because every configuration index < 256
+                    cfg_hi += s8.y * st;
+                }
+                const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
+                const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+                uint32_t T[8];
+                uint32_t xbits = 0, amb = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+                    T[i] = __ldg(thr + idx);
+                    const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                    const uint32_t th = T[i] >> 16;
+                    xbits |= (hi > th ? 1u : 0u) << i;
+                    amb |= (hi == th ? 1u : 0u) << i;
+                }
+                if (amb) {
+                    const Philox4 b = philox4x32_10((uint32_t)v, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
+                    const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (amb & (1u << i)) {
+                            const uint32_t lo = (wb[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                            if (lo > (T[i] & 0xffffu)) xbits |= 1u << i;
+                        }
+                }
+                // spread the 8 decision bits into 8 state bytes
+                uint2 outw;
+                outw.x = (xbits & 1u) | ((xbits & 2u) << 7) | ((xbits & 4u) << 14) | ((xbits & 8u) << 21);
+                outw.y = ((xbits >> 4) & 1u) | ((xbits & 32u) << 3) | ((xbits & 64u) << 10) | ((xbits & 128u) << 17);
+                *reinterpret_cast<uint2*>(g.state + (size_t)v * g.n_pad + 8 * (size_t)unit) = outw;
+                ones = __popc(xbits & vmask);
+                if (record && hist_half >= 0 && g.hist) {
+                    const int32_t coff = __ldg(m.card_off + v);
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (i < nvalid) {
+                            uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + ((xbits >> i) & 1u)) * g.n_pad + 8 * (size_t)unit + i;
+                            *h = (uint16_t)(*h + 1);
+                        }
+                }
+            }
+            if (record) {  // chain.go:231-236, aggregated warp -> CTA (shared) -> one global atomic per variable per tile
+                const unsigned s = __reduce_add_sync(0xffffffffu, ones);
+                if (lane == 0 && s) atomicAdd(&s_ones[j - vb * VB], s);
+            }
+        }
+        __syncthreads();
+        if (record && threadIdx.x < VB) {
+            const int j = vb * VB + threadIdx.x;
+            if (j < n_vars_c) {
+                const int v = __ldg(vars + j);
+                const int32_t coff = __ldg(m.card_off + v);
+                const unsigned o = s_ones[threadIdx.x];
+                const int valid = max(0, min(2048, g.n_chains - chunk * 2048));
+                if (o) atomicAdd(g.counts + coff + 1, (unsigned long long)o);
+                if (valid - (int)o) atomicAdd(g.counts + coff, (unsigned long long)(valid - (int)o));
+            }
+        }
+        __syncthreads();
     }
 }
 

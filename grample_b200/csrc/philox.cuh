@@ -4,7 +4,12 @@
 // Stream definition (the oracle restates it in oracle/sweep.hpp — keep in sync):
 //   key     = (seed_lo, seed_hi)
 //   counter = (var, sweep, chain_block, tag)
-//   tag kTagDraw32: chain_block = chain >> 2, the 4 output words serve chains 4b .. 4b+3
+//   tag kTagDraw24: chain_block = chain >> 2, the 4 output words serve chains 4b .. 4b+3,
+//                   U = (word >> 8) * 2^-24 (float32 sweeps; statistical parity only)
+//   tag kTagDraw16Hi / kTagDraw16Lo: chain_block = chain >> 3; chain 8b+i takes the 16-bit field
+//                   (word[i >> 1] >> 16*(i & 1)) & 0xffff of each call; the 32-bit draw is
+//                   word32 = (hi16 << 16) | lo16, U = word32 * 2^-32.  The table-mode sweep only
+//                   evaluates the Lo call when hi16 alone does not decide the comparison.
 //   tag kTagDraw53: chain_block = chain >> 1, words (0,1) -> chain 2b, (2,3) -> chain 2b+1,
 //                   x = ((w_a << 32) | w_b) >> 11, U = x * 2^-53   (same range as Go's Float64)
 //   tag kTagInit  : chain_block = chain >> 2, value = (word * card) >> 32
@@ -14,7 +19,7 @@
 
 namespace gb {
 
-enum : uint32_t { kTagDraw32 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagCollapse = 5 };
+enum : uint32_t { kTagDraw24 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagCollapse = 5, kTagDraw16Hi = 6, kTagDraw16Lo = 7 };
 
 struct Philox4 {
     uint32_t x, y, z, w;

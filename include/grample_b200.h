@@ -40,8 +40,14 @@ typedef struct gb_chains gb_chains; /* a population of chains (grouped by model)
 
 /* model.Measure implementations (model/error.go:81-249) */
 enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 };
-/* arithmetic type of the sweep kernels */
-enum gb_precision { GB_F64 = 0, GB_F32 = 1 };
+/* arithmetic of the sweep kernels.
+ *   GB_F64   float64 log-sum-exp per update, 53-bit draws — follows the reference literally
+ *   GB_F32   float32 log-sum-exp per update, 24-bit draws
+ *   GB_TABLE conditionals evaluated in float64 ONCE per (variable, neighbour configuration) and
+ *            stored as 32-bit inverse-CDF thresholds; the sweep is integer work (gather, index,
+ *            compare) with 32-bit draws.  Applies when every sampled variable is binary with at
+ *            most 256 joint configurations of its free neighbours (gb_model_table_mode). */
+enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2 };
 /* gb_chains_create flags */
 #define GB_CHAINS_HISTORY 1u /* keep per-chain half-window histograms (needed by gb_chains_convergence*) */
 
@@ -81,6 +87,13 @@ int gb_model_function_count(const gb_model* m, int32_t var, int32_t* out);
  * colour_off[n_colours+1].  Pass NULL outputs to query sizes only. */
 int gb_model_schedule(const gb_model* m, int32_t* n_order, int32_t* n_colours, int32_t* order, int32_t* colour_off);
 
+/* whether GB_TABLE applies to this model, and the total number of tabulated configurations */
+int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out);
+/* the tabulated thresholds of one sampled variable (builds the tables on first use): value 0 is
+ * drawn iff the 32-bit draw <= threshold[configuration]; configuration = sum(state[nbr_i] * stride_i)
+ * over the variable's free neighbours in ascending id order.  Pass out = NULL to query n. */
+int gb_model_thresholds(gb_model* m, int32_t var, int32_t* n_out, uint32_t* out);
+
 /* (*GibbsCollapsed).Collapse (sampler/gibbs-collapsed.go:98-314) as a pure function: returns a NEW
  * model in which `var` is summed out of its blanket (K3 collapse_marginalise on the device).
  * var < 0: pick uniformly among free, un-collapsed variables with blanket <= GB_NEIGHBOR_VAR_MAX,
@@ -104,7 +117,7 @@ int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int
  * collapsed variant; `simple` uses a single group).  Chain ids are global:
  * first_chain_id + local index; the Philox stream is keyed by (seed, global chain id) so
  * results do not depend on how chains are sharded across devices (shard sizes must be
- * multiples of 4).  Initial state: FixedVal or a uniform draw (gibbs-simple.go:103-111). */
+ * multiples of 8).  Initial state: FixedVal or a uniform draw (gibbs-simple.go:103-111). */
 int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* chains_per_model,
                      uint64_t seed, uint64_t first_chain_id, int precision, uint32_t flags, int device,
                      gb_chains** out);

@@ -18,7 +18,7 @@
 namespace oracle {
 
 // Stream tags — MUST match grample_b200/csrc/philox.cuh
-enum : uint32_t { kTagDraw32 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4 };
+enum : uint32_t { kTagDraw24 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagDraw16Hi = 6, kTagDraw16Lo = 7 };
 
 inline double philox_uniform(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t var, int bits) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -30,9 +30,15 @@ inline double philox_uniform(uint64_t seed, uint32_t chain, uint32_t sweep, uint
         uint64_t x = (((uint64_t)out[a] << 32) | out[a + 1]) >> 11;
         return (double)x * (1.0 / 9007199254740992.0);
     }
-    uint32_t ctr[4] = {var, sweep, chain >> 2, kTagDraw32};
-    Philox4x32::gen(ctr, key, out);
-    return (double)out[chain & 3] * (1.0 / 4294967296.0);
+    // 32-bit draw of the table-mode sweep: hi and lo halves come from two calls shared by 8 chains
+    uint32_t hi[4], lo[4];
+    uint32_t ch[4] = {var, sweep, chain >> 3, kTagDraw16Hi}, cl[4] = {var, sweep, chain >> 3, kTagDraw16Lo};
+    Philox4x32::gen(ch, key, hi);
+    Philox4x32::gen(cl, key, lo);
+    const uint32_t i = chain & 7, sh = 16 * (i & 1);
+    const uint32_t word = (((hi[i >> 1] >> sh) & 0xffffu) << 16) | ((lo[i >> 1] >> sh) & 0xffffu);
+    (void)out;
+    return (double)word * (1.0 / 4294967296.0);
 }
 
 inline int philox_init_value(uint64_t seed, uint32_t chain, uint32_t var, int card) {

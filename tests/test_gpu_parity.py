@@ -105,7 +105,7 @@ def test_init_state(res, name, evid):
 def test_sweep_bitexact_f64(res, name, evid, n_chains, n_sweeps):
     dm, om = load_pair(res, name, evid)
     order, coff = dm.schedule()
-    seed, first = 4242, 12
+    seed, first = 4242, 16
     ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0)
     st0 = ch.get_state(0, n_chains)
     ch.burnin(2)
@@ -123,6 +123,99 @@ def test_sweep_bitexact_f64(res, name, evid, n_chains, n_sweeps):
     per_var = np.add.reduceat(counts, np.concatenate([[0], np.cumsum(dm.cards)[:-1]]))
     exp = np.where(dm.fixed < 0, n_sweeps * n_chains, 0)
     assert np.array_equal(per_var, exp)
+
+
+# ------------------------------------------------------------------ table mode (K1-table)
+def expected_threshold(e):
+    """largest 32-bit draw t with (t * 2^-32) * tot <= e0 (sampler.go:115-123 evaluated in float64)"""
+    tot = float(e[0]) + float(e[1])
+    t = min(int(e[0] / tot * 4294967296.0), 4294967295)
+    while t < 4294967295 and ((t + 1) * (1.0 / 4294967296.0)) * tot <= e[0]:
+        t += 1
+    while t > 0 and not ((t * (1.0 / 4294967296.0)) * tot <= e[0]):
+        t -= 1
+    return t
+
+
+@pytest.mark.parametrize("name,evid", [("Grids_11.uai", False), ("one.uai", False), ("deterministic.uai", False)])
+def test_table_thresholds_match_oracle_conditionals(res, name, evid):
+    dm, om = load_pair(res, name, evid)
+    ok, n_thr = dm.table_mode()
+    assert ok
+    samp = oracle.Sampler(oracle.Generator(3), om, collapsed=True)
+    cards = dm.cards
+    total = 0
+    for v in range(dm.n_vars):
+        thr = dm.thresholds(v)
+        nb = [u for u in samp.neighbors(v) if u != v and dm.fixed[u] < 0]
+        assert len(thr) == int(np.prod([cards[u] for u in nb])) if nb else len(thr) == 1
+        total += len(thr)
+        for cfg in range(len(thr)):
+            st = np.zeros(dm.n_vars, dtype=np.int32)
+            rem = cfg
+            for u in nb:
+                st[u] = rem % cards[u]
+                rem //= cards[u]
+            assert abs(int(thr[cfg]) - expected_threshold(samp.conditional(v, st))) <= 1, (v, cfg)
+    assert total == n_thr
+
+
+@pytest.mark.parametrize("n_chains,first", [(13, 16), (64, 0), (2100, 8)])
+def test_table_sweep_bitexact_grids(res, n_chains, first):
+    dm, om = load_pair(res, "Grids_11.uai", False)
+    order, _ = dm.schedule()
+    seed, n_sweeps = 777, 8 if n_chains < 1000 else 2
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.TABLE, device=0)
+    st0 = ch.get_state(0, n_chains)
+    ch.burnin(1)
+    ch.sweep(n_sweeps)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, _ = samp.sweep_run(order, seed, first, st0, 0, 1, bits=32, record=False)
+    ost, ocounts = samp.sweep_run(order, seed, first, ost, 1, n_sweeps, bits=32, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+    assert ch.total_samples == n_sweeps * 100 * n_chains
+
+
+def test_table_sweep_bitexact_ising_and_evidence():
+    arrays = list(gb.ising_torus(6, 8, wmax=4.9, seed=5))
+    arrays[1] = arrays[1].copy()
+    arrays[1][[3, 17, 40]] = [1, 0, 1]  # evidence folds into the tables
+    dm = gb.Model.from_arrays(*arrays, device=0)
+    om = oracle.Model.create(*arrays)
+    order, coff = dm.schedule()
+    assert len(order) == 45
+    n_chains, seed = 24, 99
+    ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.TABLE, history=True, device=0)
+    st0 = ch.get_state(0, n_chains)
+    ch.advance(10)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, ocounts = samp.sweep_run(order, seed, 0, st0, 0, 11, bits=32, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+    hist = ch.group_history(0, n_chains)
+    assert np.all(hist.reshape(2, -1, 2, n_chains).sum(2)[:, order] == 5)
+    conv = ch.convergence(gb.HELLINGER)
+    assert np.all(conv[[3, 17, 40]] == 1.0) and np.all(np.isfinite(conv))
+
+
+def test_table_mode_rejects_unsuitable_models(res):
+    dm, _ = load_pair(res, "ObjectDetection_11.uai", False)
+    assert dm.table_mode()[0] is False
+    with pytest.raises(gb.GrampleError, match="table mode"):
+        gb.Chains(dm, 8, precision=gb.TABLE, device=0)
+
+
+def test_table_mode_statistics_match_f64(res):
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    out = []
+    for prec in (gb.F64, gb.TABLE):
+        ch = gb.Chains(dm, 2048, seed=5, precision=prec, device=0)
+        ch.burnin(100)
+        ch.sweep(100)
+        m, _ = ch.merged_marginals()
+        out.append(m.reshape(-1, 2) / m.reshape(-1, 2).sum(1, keepdims=True))
+    assert np.abs(out[0] - out[1]).max() < 0.05
 
 
 def test_sweep_independent_of_sharding(res):
@@ -399,7 +492,7 @@ def test_ising_large_properties():
     order, coff = dm.schedule()
     assert len(coff) - 1 == 2 and len(order) == H * W  # checkerboard
     n_chains, n_sweeps = 4096, 3
-    ch = gb.Chains(dm, n_chains, seed=3, precision=gb.F32, device=0)
+    ch = gb.Chains(dm, n_chains, seed=3, precision=gb.TABLE, device=0)
     ch.sweep(n_sweeps)
     counts = ch.group_counts(0).reshape(-1, 2)
     assert np.all(counts.sum(1) == n_chains * n_sweeps)
