@@ -111,6 +111,9 @@ struct gb_model {
         require_device(device);
         tab.tp_off = up(h.tp_off);
         tab.tprog = up(h.tprog);
+        tab.trec = up(h.trec);
+        tab.n_order = (int32_t)h.order.size();
+        tab.n_thr = (int32_t)h.n_thresholds;
         uint32_t* thr = nullptr;
         CUDA_CHECK(cudaMalloc(&thr, (size_t)std::max<int64_t>(h.n_thresholds, 1) * sizeof(uint32_t)));
         allocs.push_back(thr);
@@ -235,15 +238,22 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         if (c->precision == GB_TABLE) {
             constexpr int VB = 16;
             const int64_t tiles = (int64_t)((g.n_pad / 8 + 255) / 256) * ((n + VB - 1) / VB);
-            static int resident = 0;  // CTAs that fit the device at once (persistent grid-stride loop)
-            if (!resident) {
+            static int resident4 = 0, resident8 = 0;  // CTAs that fit the device at once (persistent tile loop)
+            if (!resident4) {
                 int per_sm = 0, sms = 0;
-                CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB>, 256, 0));
                 CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-                resident = std::max(1, per_sm * sms);
+                CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB, 4>, 256, 0));
+                resident4 = std::max(1, per_sm * sms);
+                CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB, 8>, 256, 0));
+                resident8 = std::max(1, per_sm * sms);
             }
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
-            gb::k_sweep_tab<VB><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, dv, n, g.sweep, record, hist_half);
+            if (h.tab_max_nbr <= 4) {
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident4));
+                gb::k_sweep_tab<VB, 4><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, h.colour_off[col], n, g.sweep, record, hist_half);
+            } else {
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident8));
+                gb::k_sweep_tab<VB, 8><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, h.colour_off[col], n, g.sweep, record, hist_half);
+            }
             c->launches++;
         } else if (c->precision == GB_F32) {
             if (mc <= 2) launch_colour<float, 2, 4>(c, g, dv, n, record, hist_half);

@@ -58,7 +58,9 @@ struct HostModel {
     bool tab_ok = false;
     std::string tab_why;                           // why the fast path does not apply
     std::vector<int32_t> tp_off, tprog;            // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
+    std::vector<int32_t> trec;                     // per sweep position: kTabRec words (see kernels.cuh)
     int64_t n_thresholds = 0;
+    int tab_max_nbr = 0;                           // largest n_nbr over the sampled variables
 
     bool sampled(int v) const { return fixed[v] < 0 && !collapsed[v]; }
 
@@ -141,7 +143,7 @@ struct HostModel {
             int64_t cfgs = 1;
             std::vector<int32_t> words;
             for (int32_t u : nbrs[v]) {
-                if (u == v || fixed[u] >= 0) continue;
+                if (u == v || fixed[u] >= 0 || card[u] == 1) continue;  // constant neighbours fold into the table
                 words.push_back(u);
                 words.push_back((int32_t)cfgs);
                 cfgs *= card[u];
@@ -162,6 +164,25 @@ struct HostModel {
             tp_off.assign(n_vars, -1);
             tprog.clear();
             n_thresholds = 0;
+            return;
+        }
+        // fixed-size record per sweep position: {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
+        // (2^n_nbr <= 256 configurations => n_nbr <= 8)
+        tab_max_nbr = 0;
+        trec.assign(order.size() * 20, 0);
+        for (size_t j = 0; j < order.size(); j++) {
+            const int v = order[j];
+            const int32_t* tp = tprog.data() + tp_off[v];
+            int32_t* r = trec.data() + j * 20;
+            r[0] = v;
+            r[1] = tp[1];
+            r[2] = tp[0];
+            tab_max_nbr = std::max(tab_max_nbr, (int)tp[0]);
+            r[3] = card_off[v];
+            for (int i = 0; i < 8; i++) {
+                r[4 + i] = i < tp[0] ? tp[2 + 2 * i] : v;
+                r[12 + i] = i < tp[0] ? tp[3 + 2 * i] : 0;
+            }
         }
     }
 

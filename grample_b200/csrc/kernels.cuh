@@ -252,6 +252,8 @@ struct DevTab {
     const int32_t* tp_off;  // [n_vars]
     const int32_t* tprog;   // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
     uint32_t* thr;          // [n_thresholds]
+    const int32_t* trec;    // [n_order][kTabRec] fixed-size record per sweep position
+    int32_t n_order, n_thr;
 };
 
 __global__ void __launch_bounds__(128)
@@ -296,21 +298,114 @@ k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__
     }
 }
 
-// CTA tile = (chunk of 2048 consecutive chains) x (VB consecutive variables of the colour); every
-// thread keeps the same 8 chains (one 64-bit state word per variable) for the whole tile, so the
-// wave front of concurrently processed tiles stays L2-resident and shared neighbours of
-// consecutive variables hit L1.  One Philox call yields the 16-bit high halves of 8 draws; the low
-// halves are generated only when a high half ties with its threshold (probability 2^-16).
-template <int VB>
+// CTA tile = (chunk of 2048 consecutive chains) x (VB consecutive sweep positions of the colour);
+// every thread keeps the same 8 chains (one 64-bit state word per variable) for the whole tile, so
+// the wave front of concurrently processed tiles stays L2-resident and shared neighbours of
+// consecutive variables hit L1.  Per tile the position records and the 16-bit high halves of the
+// thresholds are staged in shared memory.  One Philox call yields the high halves of 8 draws; the
+// low halves are generated only when a high half ties with its threshold (probability 2^-16).
+constexpr int kTabRec = 20;  // {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
+
+__device__ __forceinline__ Philox4 philox_wide(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// NN = neighbour slots read per variable (4 or 8); records pad unused slots with the variable
+// itself at stride 0, so the loads are unconditional and branch-free.
+template <int NN>
+__device__ __forceinline__ void tab_load_nbrs(const int4* rec, const uint64_t my, const uint32_t n_pad, uint2 (&w)[NN]) {
+    const int4 na = rec[1];
+    w[0] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.x * n_pad);
+    w[1] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.y * n_pad);
+    w[2] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.z * n_pad);
+    w[3] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.w * n_pad);
+    if constexpr (NN == 8) {
+        const int4 nb = rec[2];
+        w[4] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.x * n_pad);
+        w[5] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.y * n_pad);
+        w[6] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.z * n_pad);
+        w[7] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.w * n_pad);
+    }
+}
+
+// One variable x 8 chains: configuration indices from the neighbour words, thresholds from
+// shared memory, one Philox call, compare, store.  Returns the number of ones among valid chains.
+template <int NN>
+__device__ __forceinline__ unsigned tab_update(const DevModel& m, const DevTab& t, const DevGroup& g, const int4* rec,
+                                               const uint2 (&w)[NN], const uint16_t* s_thr, const int thr_a,
+                                               const uint64_t my, const uint32_t chain_blk, const uint32_t sweep,
+                                               const uint32_t vmask, const int nvalid, const int unit, const int record,
+                                               const int hist_half) {
+    const int4 hd = rec[0];  // v, thr_off, n_nbr, card_off
+    const int4 sa = rec[3];
+    uint32_t cfg_lo = w[0].x * (uint32_t)sa.x + w[1].x * (uint32_t)sa.y + w[2].x * (uint32_t)sa.z + w[3].x * (uint32_t)sa.w;
+    uint32_t cfg_hi = w[0].y * (uint32_t)sa.x + w[1].y * (uint32_t)sa.y + w[2].y * (uint32_t)sa.z + w[3].y * (uint32_t)sa.w;
+    if constexpr (NN == 8) {
+        const int4 sb = rec[4];
+        cfg_lo += w[4].x * (uint32_t)sb.x + w[5].x * (uint32_t)sb.y + w[6].x * (uint32_t)sb.z + w[7].x * (uint32_t)sb.w;
+        cfg_hi += w[4].y * (uint32_t)sb.x + w[5].y * (uint32_t)sb.y + w[6].y * (uint32_t)sb.z + w[7].y * (uint32_t)sb.w;
+    }
+    const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+    const char* const tb = reinterpret_cast<const char*>(s_thr + (hd.y - thr_a));
+    uint32_t xbits = 0, tie = 1;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        const uint32_t idx = __byte_perm(i < 4 ? cfg_lo : cfg_hi, 0, 0x4440 + (i & 3));
+        const uint32_t th = *reinterpret_cast<const uint16_t*>(tb + idx + idx);
+        const uint32_t hi = (i & 1) ? (wa[i >> 1] >> 16) : __byte_perm(wa[i >> 1], 0, 0x4410);
+        const uint32_t d = th - hi;            // sign bit set <=> hi > th  (both < 2^16)
+        xbits = __funnelshift_l(d, xbits, 1);  // xbits = (xbits << 1) | (hi > th)
+        tie *= d;                              // zero if any high half ties (rare false positives are harmless)
+    }
+    if (tie == 0) {  // resolve ties with the low halves: draw > threshold <=> lo16 > (T & 0xffff)
+        const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
+        const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+            const uint32_t T = __ldg(t.thr + hd.y + idx);
+            const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            const uint32_t lo = (wb[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            if (hi == (T >> 16) && lo > (T & 0xffffu)) xbits |= 1u << i;
+        }
+    }
+    uint2 outw;  // spread decision bits into state bytes: bit i -> byte i
+    outw.x = ((xbits & 0xfu) * 0x00204081u) & 0x01010101u;
+    outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+    *reinterpret_cast<uint2*>(my + (uint64_t)(uint32_t)hd.x * (uint32_t)g.n_pad) = outw;
+    if (record && hist_half >= 0 && g.hist) {  // chain.go:237 as per-chain half-window histograms
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < nvalid) {
+                uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + hd.w + ((xbits >> i) & 1u)) * g.n_pad + 8 * (size_t)unit + i;
+                *h = (uint16_t)(*h + 1);
+            }
+    }
+    return __popc(xbits & vmask);
+}
+
+template <int VB, int NN>
 __global__ void __launch_bounds__(256)
-k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ vars,
-            const int32_t n_vars_c, const uint32_t sweep, const int record, const int hist_half) {
+k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_begin, const int32_t n_vars_c,
+            const uint32_t sweep, const int record, const int hist_half) {
+    __shared__ int4 s_rec[VB * (kTabRec / 4)];
     __shared__ unsigned int s_ones[VB];
+    __shared__ uint16_t s_thr[VB * 256];
     const int units = g.n_pad >> 3;
     const int chunks = (units + 255) >> 8;
     const int n_vb = (n_vars_c + VB - 1) / VB;
     const int64_t n_tiles = (int64_t)chunks * n_vb;
     const int lane = threadIdx.x & 31;
+    const uint32_t n_pad = (uint32_t)g.n_pad;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int chunk = (int)(tile / n_vb);
         const int vb = (int)(tile - (int64_t)chunk * n_vb);
@@ -319,79 +414,51 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t* _
         const int nvalid = active ? max(0, min(8, g.n_chains - 8 * unit)) : 0;
         const uint32_t vmask = (nvalid >= 8) ? 0xffu : ((1u << nvalid) - 1u);
         const uint32_t chain_blk = (uint32_t)((g.first_chain >> 3) + (uint64_t)unit);
-        if (threadIdx.x < VB) s_ones[threadIdx.x] = 0;
+        const int nv = min(VB, n_vars_c - vb * VB);
+        const int j0 = j_begin + vb * VB;
+        {  // stage the tile's records and threshold high halves
+            const int32_t* src = t.trec + (size_t)j0 * kTabRec;
+            int32_t* dst = reinterpret_cast<int32_t*>(s_rec);
+            for (int i = threadIdx.x; i < nv * kTabRec; i += 256) dst[i] = __ldg(src + i);
+            const int ta = __ldg(src + 1);
+            const int tb = (j0 + nv < t.n_order) ? __ldg(t.trec + (size_t)(j0 + nv) * kTabRec + 1) : t.n_thr;
+            for (int i = threadIdx.x; i < tb - ta; i += 256) s_thr[i] = (uint16_t)(__ldg(t.thr + ta + i) >> 16);
+            if (threadIdx.x < VB) s_ones[threadIdx.x] = 0;
+        }
         __syncthreads();
-        const int j_end = min(n_vars_c, (vb + 1) * VB);
-        for (int j = vb * VB; j < j_end; j++) {
-            const int v = __ldg(vars + j);
-            unsigned ones = 0;
+        const int thr_a = s_rec[0].y;
+        const uint64_t my = reinterpret_cast<uint64_t>(g.state) + 8ull * (uint64_t)unit;
+        // software pipeline: the next variable's neighbour words are in flight while this one computes
+        // (variables of one colour are never neighbours, so the early loads cannot see this tile's writes)
+        uint2 wA[NN], wB[NN];
+        if (active) tab_load_nbrs<NN>(s_rec, my, n_pad, wA);
+        for (int jj = 0; jj < nv; jj += 2) {
+            unsigned o0 = 0, o1 = 0;
+            const bool has1 = jj + 1 < nv;
             if (active) {
-                const int32_t* __restrict__ tp = t.tprog + __ldg(t.tp_off + v);
-                const int nn = __ldg(tp);
-                const uint32_t* __restrict__ thr = t.thr + __ldg(tp + 1);
-                uint32_t cfg_lo = 0, cfg_hi = 0;
-                for (int i = 0; i < nn; i++) {
-                    const int ov = __ldg(tp + 2 + 2 * i);
-                    const uint32_t st = (uint32_t)__ldg(tp + 3 + 2 * i);
-                    const uint2 s8 = *reinterpret_cast<const uint2*>(g.state + (size_t)ov * g.n_pad + 8 * (size_t)unit);
-                    cfg_lo += s8.x * st;  // packed bytes: no carries because every configuration index < 256
-                    cfg_hi += s8.y * st;
-                }
-                const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
-                const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
-                uint32_t T[8];
-                uint32_t xbits = 0, amb = 0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
-                    T[i] = __ldg(thr + idx);
-                    const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-                    const uint32_t th = T[i] >> 16;
-                    xbits |= (hi > th ? 1u : 0u) << i;
-                    amb |= (hi == th ? 1u : 0u) << i;
-                }
-                if (amb) {
-                    const Philox4 b = philox4x32_10((uint32_t)v, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
-                    const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (amb & (1u << i)) {
-                            const uint32_t lo = (wb[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-                            if (lo > (T[i] & 0xffffu)) xbits |= 1u << i;
-                        }
-                }
-                // spread the 8 decision bits into 8 state bytes
-                uint2 outw;
-                outw.x = (xbits & 1u) | ((xbits & 2u) << 7) | ((xbits & 4u) << 14) | ((xbits & 8u) << 21);
-                outw.y = ((xbits >> 4) & 1u) | ((xbits & 32u) << 3) | ((xbits & 64u) << 10) | ((xbits & 128u) << 17);
-                *reinterpret_cast<uint2*>(g.state + (size_t)v * g.n_pad + 8 * (size_t)unit) = outw;
-                ones = __popc(xbits & vmask);
-                if (record && hist_half >= 0 && g.hist) {
-                    const int32_t coff = __ldg(m.card_off + v);
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (i < nvalid) {
-                            uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + ((xbits >> i) & 1u)) * g.n_pad + 8 * (size_t)unit + i;
-                            *h = (uint16_t)(*h + 1);
-                        }
+                if (has1) tab_load_nbrs<NN>(s_rec + (jj + 1) * 5, my, n_pad, wB);
+                o0 = tab_update<NN>(m, t, g, s_rec + jj * 5, wA, s_thr, thr_a, my, chain_blk, sweep, vmask, nvalid, unit, record, hist_half);
+                if (has1) {
+                    if (jj + 2 < nv) tab_load_nbrs<NN>(s_rec + (jj + 2) * 5, my, n_pad, wA);
+                    o1 = tab_update<NN>(m, t, g, s_rec + (jj + 1) * 5, wB, s_thr, thr_a, my, chain_blk, sweep, vmask, nvalid, unit, record, hist_half);
                 }
             }
             if (record) {  // chain.go:231-236, aggregated warp -> CTA (shared) -> one global atomic per variable per tile
-                const unsigned s = __reduce_add_sync(0xffffffffu, ones);
-                if (lane == 0 && s) atomicAdd(&s_ones[j - vb * VB], s);
+                const unsigned s0 = __reduce_add_sync(0xffffffffu, o0);
+                const unsigned s1 = __reduce_add_sync(0xffffffffu, o1);
+                if (lane == 0) {
+                    if (s0) atomicAdd(&s_ones[jj], s0);
+                    if (s1) atomicAdd(&s_ones[jj + 1], s1);
+                }
             }
         }
         __syncthreads();
-        if (record && threadIdx.x < VB) {
-            const int j = vb * VB + threadIdx.x;
-            if (j < n_vars_c) {
-                const int v = __ldg(vars + j);
-                const int32_t coff = __ldg(m.card_off + v);
-                const unsigned o = s_ones[threadIdx.x];
-                const int valid = max(0, min(2048, g.n_chains - chunk * 2048));
-                if (o) atomicAdd(g.counts + coff + 1, (unsigned long long)o);
-                if (valid - (int)o) atomicAdd(g.counts + coff, (unsigned long long)(valid - (int)o));
-            }
+        if (record && threadIdx.x < nv) {
+            const int32_t coff = s_rec[threadIdx.x * 5].w;
+            const unsigned o = s_ones[threadIdx.x];
+            const int valid = max(0, min(2048, g.n_chains - chunk * 2048));
+            if (o) atomicAdd(g.counts + coff + 1, (unsigned long long)o);
+            if (valid - (int)o) atomicAdd(g.counts + coff, (unsigned long long)(valid - (int)o));
         }
         __syncthreads();
     }
