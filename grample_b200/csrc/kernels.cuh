@@ -393,8 +393,8 @@ __device__ __forceinline__ unsigned tab_update(const DevModel& m, const DevTab& 
     return __popc(xbits & vmask);
 }
 
-template <int VB, int NN>
-__global__ void __launch_bounds__(256)
+template <int VB, int NN, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_begin, const int32_t n_vars_c,
             const uint32_t sweep, const int record, const int hist_half) {
     __shared__ int4 s_rec[VB * (kTabRec / 4)];
