@@ -144,6 +144,7 @@ def run_reference(args):
 def run_native(args):
     import torch
     import grample_b200 as gb
+    from grample_b200 import distributed as gbd
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -208,16 +209,7 @@ def run_native(args):
     e0 = time.time()
     for _ in range(args.steps):
         chains.sweep(1, record=True)
-        if dist is not None:
-            ptr, n = chains.merge_partial_dev()
-            # all-reduce of the marginal counts over NVLink at the monitor interval
-            buf = torch.empty(0)
-            arr = _DevArray(ptr, n)
-            tens = torch.as_tensor(arr, device=f"cuda:{dev}")
-            dist.all_reduce(tens)
-            merged, _ = chains.merge_finalize()
-        else:
-            merged, _ = chains.merged_marginals()
+        merged, _ = gbd.merged_marginals(chains, dist)  # all-reduce over NVLink when world > 1
         _ = chains.total_samples
     barrier()
     e_ms = (time.time() - e0) * 1e3
@@ -275,14 +267,6 @@ def run_native(args):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
-
-
-class _DevArray:
-    """__cuda_array_interface__ view of a device float64 buffer owned by the library, so
-    torch.distributed can all-reduce it in place."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
 def main():

@@ -64,6 +64,9 @@ _SIGS = {
     "gb_chains_burnin": (C.c_int, [_vp, C.c_int64]),
     "gb_chains_advance": (C.c_int, [_vp, C.c_int32]),
     "gb_chains_total_samples": (C.c_int, [_vp, _i64p]),
+    "gb_chains_group_sweep": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int]),
+    "gb_chains_group_advance": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "gb_chains_group_info": (C.c_int, [_vp, C.c_int32, _i32p, _i64p, C.POINTER(_vp)]),
     "gb_chains_synchronize": (C.c_int, [_vp]),
     "gb_chains_merged_marginals": (C.c_int, [_vp, _f64p, _i32p]),
     "gb_chains_merge_partial_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),

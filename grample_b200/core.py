@@ -215,6 +215,18 @@ class Chains:
     def advance(self, cw):
         check(lib().gb_chains_advance(self.h, int(cw)))
 
+    def group_sweep(self, group, n_sweeps, record=True):
+        check(lib().gb_chains_group_sweep(self.h, group, int(n_sweeps), int(record)))
+
+    def group_advance(self, group, cw):
+        check(lib().gb_chains_group_advance(self.h, group, int(cw)))
+
+    def group_info(self, group):
+        """(chains in the group, the group's TotalSampleCount)"""
+        n, t = C.c_int32(), C.c_int64()
+        check(lib().gb_chains_group_info(self.h, group, C.byref(n), C.byref(t), None))
+        return n.value, t.value
+
     def synchronize(self):
         check(lib().gb_chains_synchronize(self.h))
 
@@ -258,11 +270,7 @@ class Chains:
         return p.value, n.value
 
     def convergence_finalize(self, wb, cw, total_chains, collapsed):
-        wb, collapsed = _f64(wb), _i32(collapsed)
-        out = np.zeros(self.base.n_vars)
-        check(lib().gb_convergence_finalize(self.h, _ptr(wb, _f64p), int(cw), int(total_chains), _ptr(collapsed, _i32p),
-                                            _ptr(out, _f64p)))
-        return out
+        return convergence_finalize(self.base, wb, cw, total_chains, collapsed)
 
     def adapt(self, base_model, new_chain_count, chains_per_new_model, cw, first_chain_id, measure=HELLINGER,
               max_groups=128):
@@ -294,6 +302,15 @@ class Chains:
         out = np.zeros((2, self.base.total_card, n_chains), dtype=np.uint16)
         check(lib().gb_chains_group_history(self.h, group, out.ctypes.data_as(C.POINTER(C.c_uint16))))
         return out
+
+
+def convergence_finalize(base_model, wb, cw, total_chains, collapsed):
+    """chain.go:46-59, 69-88 applied to all-reduced per-variable sums of within/between distances"""
+    wb, collapsed = _f64(wb), _i32(collapsed)
+    out = np.zeros(base_model.n_vars)
+    check(lib().gb_convergence_finalize(base_model.h, _ptr(wb, _f64p), int(cw), int(total_chains),
+                                        _ptr(collapsed, _i32p), _ptr(out, _f64p)))
+    return out
 
 
 def error_suite(cards, marg1, marg2, fixed1=None, fixed2=None):

@@ -135,6 +135,7 @@ struct Group {
     int32_t n_chains = 0, n_pad = 0;
     uint64_t first_chain = 0;
     uint32_t sweep = 0;  // next Philox sweep index
+    int64_t total_samples = 0;  // Chain.TotalSampleCount summed over the group's chains
     uint8_t* d_state = nullptr;
     unsigned long long* d_counts = nullptr;
     uint16_t* d_hist = nullptr;
@@ -292,7 +293,10 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         }
     }
     g.sweep++;
-    if (record) c->total_samples += (int64_t)h.order.size() * g.n_chains;
+    if (record) {
+        c->total_samples += (int64_t)h.order.size() * g.n_chains;
+        g.total_samples += (int64_t)h.order.size() * g.n_chains;
+    }
 }
 
 void sweeps(gb_chains* c, int64_t n, int record, int hist_half) {
@@ -737,6 +741,48 @@ int gb_chains_advance(gb_chains* c, int32_t cw) {
     GB_END
 }
 int gb_chains_total_samples(const gb_chains* c, int64_t* out) { *out = c->total_samples; return 0; }
+
+// ---- per-group forms: one reference Chain maps to one group of replica chains
+static Group& group_at(gb_chains* c, int32_t group) {
+    if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
+    return c->groups[group];
+}
+int gb_chains_group_sweep(gb_chains* c, int32_t group, int64_t n_sweeps, int record) {
+    GB_TRY
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Group& g = group_at(c, group);
+    for (int64_t s = 0; s < n_sweeps; s++) sweep_group(c, g, record, -1);
+    CUDA_CHECK(cudaGetLastError());
+    GB_END
+}
+int gb_chains_group_advance(gb_chains* c, int32_t group, int32_t cw) {
+    GB_TRY
+    if (cw < 0) throw gb::Err("Invalid convergence window");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Group& g = group_at(c, group);
+    c->last_cw = cw;
+    const int32_t half = cw / 2;
+    if (c->flags & GB_CHAINS_HISTORY) {
+        if (half > 65535) throw gb::Err("convergence window too large for 16-bit half-window histograms");
+        CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, (size_t)2 * g.model->h.total_card * g.n_pad * sizeof(uint16_t), c->stream));
+        for (int64_t s = 0; s < (int64_t)cw + 1 - 2 * half; s++) sweep_group(c, g, 1, -1);
+        for (int32_t s = 0; s < half; s++) sweep_group(c, g, 1, 0);
+        for (int32_t s = 0; s < half; s++) sweep_group(c, g, 1, 1);
+    } else {
+        for (int64_t s = 0; s < (int64_t)cw + 1; s++) sweep_group(c, g, 1, -1);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    GB_END
+}
+int gb_chains_group_info(gb_chains* c, int32_t group, int32_t* n_chains_out, int64_t* total_samples_out,
+                         gb_model** model_out) {
+    GB_TRY
+    Group& g = group_at(c, group);
+    if (n_chains_out) *n_chains_out = g.n_chains;
+    if (total_samples_out) *total_samples_out = g.total_samples;
+    if (model_out) *model_out = g.model;
+    GB_END
+}
 int gb_chains_synchronize(gb_chains* c) {
     GB_TRY
     CUDA_CHECK(cudaSetDevice(c->device));
@@ -784,10 +830,10 @@ int gb_chains_convergence_partial_dev(gb_chains* c, int measure, const double* m
     *n_out = (int64_t)2 * c->base().n_vars;
     GB_END
 }
-int gb_convergence_finalize(const gb_chains* c, const double* wb, int32_t cw, int64_t total_chains,
+int gb_convergence_finalize(const gb_model* base, const double* wb, int32_t cw, int64_t total_chains,
                             const int32_t* collapsed, double* out) {
     GB_TRY
-    const gb::HostModel& h = c->base();
+    const gb::HostModel& h = base->h;
     std::vector<uint8_t> col(h.n_vars, 0);
     for (int v = 0; v < h.n_vars; v++) col[v] = collapsed ? (collapsed[v] != 0) : 0;
     convergence_finalize(h, wb, cw, total_chains, col.data(), out);

@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: one process per GPU, chains sharded by GLOBAL chain id (the Philox stream
+is keyed by it, so a run does not depend on the number of GPUs), and the only exchange is the
+sum all-reduce of two small buffers at the monitor interval (cmd/root.go:498-539):
+the MergeChains contribution (sum(card) float64) and the per-variable within/between sums
+(2*n_vars float64).  torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is the
+transport; the buffers themselves are produced and consumed by the C ABI.
+"""
+import numpy as np
+
+from . import core
+
+CHAIN_BLOCK = 8  # chains share Philox calls in blocks of 8: shards start on multiples of 8
+
+
+def shard(total_chains, world, rank):
+    """(first_chain_id, n_chains) of `rank`: contiguous, block-aligned, covering [0, total)."""
+    blocks = (total_chains + CHAIN_BLOCK - 1) // CHAIN_BLOCK
+    per = (blocks + world - 1) // world
+    first = min(rank * per, blocks) * CHAIN_BLOCK
+    last = min((rank + 1) * per, blocks) * CHAIN_BLOCK
+    return first, max(0, min(last, total_chains) - first)
+
+
+class DeviceBuffer:
+    """__cuda_array_interface__ view of a float64 device buffer owned by the library."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def all_reduce_numpy(dist, arr):
+    """sum all-reduce of a host float64 array (gloo / CPU tests)"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64).copy())
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def all_reduce_device(dist, ptr, n, device):
+    """in-place sum all-reduce of a library-owned device buffer (NCCL)"""
+    import torch
+    t = torch.as_tensor(DeviceBuffer(ptr, n), device=f"cuda:{device}")
+    dist.all_reduce(t)
+    torch.cuda.synchronize(device)
+
+
+def merged_marginals(chains, dist=None):
+    """sampler.MergeChains over the chains of every rank"""
+    if dist is None or dist.get_world_size() == 1:
+        return chains.merged_marginals()
+    ptr, n = chains.merge_partial_dev()
+    all_reduce_device(dist, ptr, n, chains.device)
+    return chains.merge_finalize()
+
+
+def convergence(chains, measure, merged, collapsed, cw, dist=None):
+    """sampler.ChainConvergence over the chains of every rank"""
+    if dist is None or dist.get_world_size() == 1:
+        return chains.convergence(measure, merged)
+    import torch
+    ptr, n = chains.convergence_partial_dev(measure, merged)
+    all_reduce_device(dist, ptr, n, chains.device)
+    wb = torch.as_tensor(DeviceBuffer(ptr, n), device=f"cuda:{chains.device}").cpu().numpy()
+    total = torch.tensor([chains.n_chains], dtype=torch.int64, device=f"cuda:{chains.device}")
+    dist.all_reduce(total)
+    return core.convergence_finalize(chains.base, wb, cw, int(total.item()), collapsed)
+
+
+def total_samples(chains, dist=None):
+    if dist is None or dist.get_world_size() == 1:
+        return chains.total_samples
+    import torch
+    t = torch.tensor([chains.total_samples], dtype=torch.int64, device=f"cuda:{chains.device}")
+    dist.all_reduce(t)
+    return int(t.item())

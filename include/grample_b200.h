@@ -145,6 +145,16 @@ int gb_chains_burnin(gb_chains* c, int64_t n_sweeps);
 int gb_chains_advance(gb_chains* c, int32_t cw);
 /* sum of Chain.TotalSampleCount over this device's chains (cmd/root.go:488-491) */
 int gb_chains_total_samples(const gb_chains* c, int64_t* out);
+/* Per-group forms.  A drop-in shim maps ONE reference *Chain to ONE group of replica chains:
+ * NewChain's burn-in (chain.go:167-172) -> gb_chains_group_sweep(record = 0); (*Chain).AdvanceChain
+ * -> gb_chains_group_advance, which only ENQUEUES the work on the handle's stream (like the
+ * goroutine the reference spawns, chain.go:197-215); the caller's wg.Wait() is
+ * gb_chains_synchronize.  gb_chains_group_info returns the group's chain count, its
+ * TotalSampleCount and its (borrowed) model. */
+int gb_chains_group_sweep(gb_chains* c, int32_t group, int64_t n_sweeps, int record);
+int gb_chains_group_advance(gb_chains* c, int32_t group, int32_t cw);
+int gb_chains_group_info(gb_chains* c, int32_t group, int32_t* n_chains_out, int64_t* total_samples_out,
+                         gb_model** model_out);
 int gb_chains_synchronize(gb_chains* c);
 
 /* sampler.MergeChains (sampler/chain.go:96-148) over this device's chains: for every variable
@@ -166,7 +176,7 @@ int gb_chains_convergence(gb_chains* c, int measure, const double* merged, doubl
  * chain count. */
 int gb_chains_convergence_partial_dev(gb_chains* c, int measure, const double* merged, double** dev_ptr_out,
                                       int64_t* n_out);
-int gb_convergence_finalize(const gb_chains* c, const double* wb /*[2*n_vars] host*/, int32_t cw,
+int gb_convergence_finalize(const gb_model* base, const double* wb /*[2*n_vars] host*/, int32_t cw,
                             int64_t total_chains, const int32_t* collapsed /*[n_vars]*/, double* out);
 
 /* (*ConvergenceSampler).Adapt (sampler/adaptive.go:57-157): choose up to new_chain_count

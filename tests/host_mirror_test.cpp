@@ -1,0 +1,215 @@
+// C++ host-mirror tests: the reference's sampler tests, re-stated against grample_b200/host/grample.hpp
+// (which sits above the C ABI).  Each test names the Go test it follows.  Needs a CUDA device.
+//   usage: host_mirror_test <dir with the .uai fixtures>
+#include <cstdio>
+#include <functional>
+#include <iostream>
+
+#include "../grample_b200/host/grample.hpp"
+
+using namespace grample;
+static std::string RES;
+static int failures = 0;
+#define EXPECT(cond)                                                                  \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);           \
+            failures++;                                                               \
+        }                                                                             \
+    } while (0)
+template <typename F>
+static bool throws(F f) {
+    try { f(); } catch (const Error&) { return true; }
+    return false;
+}
+static bool in_epsilon(double exp, double act, double eps) { return std::fabs(exp - act) <= eps * std::fabs(exp); }
+
+// sampler/gibbs-simple_test.go:13-38
+static void TestWorkingGibbsSimple() {
+    sampler::ResetPool();
+    options().replicas = 64;
+    auto mod = model::NewModelFromFile(RES + "/one.uai", false);
+    auto gen = rnd::NewGenerator(42);
+    auto samp = sampler::NewGibbsSimple(gen, mod);
+    auto ch = sampler::NewChain(mod, samp, 16, 0);
+    sampler::WaitGroup wg;
+    ch->AdvanceChain(wg);
+    wg.Wait();
+    ch->Refresh();
+    EXPECT(ch->TotalSampleCount == 64 * 17);
+    EXPECT(ch->LastSample.size() == 1 && (ch->LastSample[0] == 0 || ch->LastSample[0] == 1));
+    const auto& m = mod->Vars[0].Marginal;
+    EXPECT(m[0] > 32.0 && m[1] > 32.0);  // both values were drawn (counts on top of the 64 * 1/2 prior)
+    EXPECT(in_epsilon(0.75, m[1] / (m[0] + m[1]), 0.1));
+    EXPECT(throws([&] { sampler::NewGibbsSimple(gen, nullptr); }));
+}
+
+// sampler/gibbs-collapsed_test.go:14-48
+static void TestWorkingGibbsCollapsed() {
+    auto mod = model::NewModelFromFile(RES + "/deterministic.uai", false);
+    auto gen = rnd::NewGenerator(42);
+    auto samp = sampler::NewGibbsCollapsed(gen, mod->Clone());
+    for (auto& v : samp->pgm->Vars) EXPECT(!v.Collapsed);
+    for (size_t i = 0; i < mod->Vars.size(); i++) {
+        auto samp2 = sampler::NewGibbsCollapsed(gen, mod->Clone());
+        model::Variable* v = samp2->Collapse((int)i);
+        EXPECT(v->ID == (int)i);
+        for (size_t j = 0; j < samp2->pgm->Vars.size(); j++) EXPECT(samp2->pgm->Vars[j].Collapsed == (j == i));
+        EXPECT(in_epsilon(0.50, v->Marginal[0], 1e-5));
+        EXPECT(in_epsilon(0.50, v->Marginal[1], 1e-5));
+    }
+    for (auto& v : mod->Vars) EXPECT(!v.Collapsed);  // the caller's model was cloned, not touched
+}
+
+// sampler/gibbs-collapsed_test.go:51-111
+static void TestFullGibbsCollapsed() {
+    auto mod = model::NewModelFromFile(RES + "/sample.uai", false);
+    auto gen = rnd::NewGenerator(42);
+    auto samp = sampler::NewGibbsCollapsed(gen, mod->Clone());
+    EXPECT(!samp->pgm->Vars[0].Collapsed && !samp->pgm->Vars[1].Collapsed);
+    model::Variable* v = samp->Collapse(0);
+    EXPECT(v->Collapsed && samp->pgm->Vars[0].Collapsed && !samp->pgm->Vars[1].Collapsed);
+    v = samp->Collapse(1);
+    EXPECT(v->Collapsed && samp->pgm->Vars[0].Collapsed && samp->pgm->Vars[1].Collapsed);
+
+    samp = sampler::NewGibbsCollapsed(gen, mod);
+    auto coll_count = [&] {
+        int c = 0;
+        for (auto& x : samp->pgm->Vars) c += x.Collapsed;
+        return c;
+    };
+    EXPECT(coll_count() == 0);
+    v = samp->Collapse(-1);
+    EXPECT(v->Collapsed && coll_count() == 1);
+    v = samp->Collapse(-1);
+    EXPECT(v->Collapsed && coll_count() == 2);
+    EXPECT(throws([&] { samp->Collapse(-1); }));  // at least one variable must remain uncollapsed
+    EXPECT(coll_count() == 2);
+    EXPECT(samp->BlanketSize(mod->Vars[0]) >= 0 && sampler::NeighborVarMax == 12);
+}
+
+// sampler/chain_test.go:11-80 (the reference builds chains around hand-made variables; here
+// they are real device chains, so expected values are computed from the chains themselves)
+static void TestMergeChains() {
+    sampler::ResetPool();
+    options().replicas = 8;
+    EXPECT(throws([] { sampler::MergeChains({}); }));
+    auto mod = model::NewModelFromFile(RES + "/sample.uai", false);
+    auto gen = rnd::NewGenerator(7);
+    auto m1 = mod->Clone();
+    auto ch1 = sampler::NewChain(m1, sampler::NewGibbsSimple(gen, m1), 10, 30);
+    auto m2 = mod->Clone();
+    auto s2 = sampler::NewGibbsCollapsed(gen, m2);
+    model::Variable* cv = s2->Collapse(0);
+    std::vector<double> exact = cv->Marginal;
+    auto ch2 = sampler::NewChain(m2, s2, 10, 30);
+    sampler::WaitGroup wg;
+    ch1->AdvanceChain(wg);
+    ch2->AdvanceChain(wg);
+    wg.Wait();
+    auto one = sampler::MergeChains({ch1});  // 1 chain: its own variables
+    for (size_t i = 0; i < one.size(); i++) EXPECT(one[i].Marginal == ch1->Target->Vars[i].Marginal);
+    for (auto order : {std::vector<std::shared_ptr<sampler::Chain>>{ch1, ch2}, {ch2, ch1}}) {
+        auto vars = sampler::MergeChains(order);
+        EXPECT(vars[0].Collapsed && vars[0].Marginal == exact);  // collapsed in any chain wins, no summation
+        for (int i = 1; i < 3; i++)
+            for (int k = 0; k < vars[i].Card; k++)
+                EXPECT(std::fabs(vars[i].Marginal[k] - (ch1->Target->Vars[i].Marginal[k] + ch2->Target->Vars[i].Marginal[k])) < 1e-9);
+    }
+    double tot = 0;
+    for (double x : ch1->Target->Vars[1].Marginal) tot += x;
+    EXPECT(std::fabs(tot - (8.0 + 8.0 * 11)) < 1e-9);  // 8 replicas: uniform start mass + (cw+1) recorded draws each
+    EXPECT(ch1->TotalSampleCount == 8 * 11 * 3 && ch2->TotalSampleCount == 8 * 11 * 2);
+}
+
+// cmd/root.go:381-430, 475-561, 640-652: the main loop with the simple sampler, then the four
+// final ChainConvergence calls
+static void TestMainLoopSimple() {
+    sampler::ResetPool();
+    options().replicas = 32;
+    auto mod = model::NewModelFromFile(RES + "/Grids_11.uai", false);
+    auto sol = model::NewSolutionFromFile(RES + "/Grids_11.uai.MAR");
+    auto start = sol.Error(mod->Vars);
+    auto gen = rnd::NewGenerator(1);
+    std::vector<std::shared_ptr<sampler::Chain>> chains;
+    for (int idx = 0; idx < 4; idx++) {
+        auto copy = mod->Clone();
+        chains.push_back(sampler::NewChain(copy, sampler::NewGibbsSimple(gen, copy), 50, 2000 * 100 / 100));
+    }
+    auto adapt = sampler::NewIdentitySampler();
+    sampler::WaitGroup wg;
+    int64_t sample_count = 0;
+    for (int round = 0; round < 4; round++) {
+        for (auto& ch : chains) ch->AdvanceChain(wg);
+        wg.Wait();
+        sample_count = 0;
+        for (auto& ch : chains) { ch->Refresh(); sample_count += ch->TotalSampleCount; }
+        chains = adapt->Adapt(chains, 1);
+    }
+    EXPECT(sample_count == 4LL * 32 * 51 * 100 * 4);
+    auto merged = sampler::MergeChains(chains);
+    auto score = sol.Error(merged);
+    EXPECT(score.MeanHellinger < start.MeanHellinger && score.MeanHellinger > 0);
+    for (auto measure : {sampler::HellingerDiff, sampler::JSDivergence, sampler::MaxAbsDiff, sampler::MeanAbsDiff}) {
+        auto conv = sampler::ChainConvergence(chains, measure, merged);
+        EXPECT(conv.size() == 100);
+        for (double c : conv) EXPECT(std::isfinite(c) && c > 0);
+    }
+    EXPECT(throws([&] { sampler::ChainConvergence({chains[0]}, sampler::HellingerDiff, {}); }));
+}
+
+// cmd/root.go with --sampler adaptive + sampler/adaptive.go:57-157
+static void TestMainLoopAdaptive() {
+    sampler::ResetPool();
+    options().replicas = 16;
+    auto mod = model::NewModelFromFile(RES + "/Pedigree_11.uai", true);
+    auto gen = rnd::NewGenerator(3);
+    std::vector<std::shared_ptr<sampler::Chain>> chains;
+    for (int idx = 0; idx < 2; idx++) {
+        auto copy = mod->Clone();
+        chains.push_back(sampler::NewChain(copy, sampler::NewGibbsCollapsed(gen, copy), 20, 2000));
+    }
+    auto adapt = sampler::NewConvergenceSampler(gen, mod->Clone());
+    EXPECT(adapt->MaxChains == 128 && adapt->DistFunc == sampler::HellingerDiff);
+    EXPECT(throws([&] { sampler::NewConvergenceSampler(gen, nullptr); }));
+    EXPECT(throws([&] { adapt->Adapt({chains[0]}, 4); }));
+    sampler::WaitGroup wg;
+    for (int round = 0; round < 3; round++) {
+        for (auto& ch : chains) ch->AdvanceChain(wg);
+        wg.Wait();
+        size_t pre = chains.size();
+        chains = adapt->Adapt(chains, 4);
+        EXPECT(chains.size() == pre + 4);
+    }
+    auto merged = sampler::MergeChains(chains);
+    int col = 0;
+    for (auto& v : merged) col += v.Collapsed;
+    EXPECT(col == 12);
+    for (size_t i = 2; i < chains.size(); i++) {
+        int c = 0;
+        for (auto& v : chains[i]->Target->Vars) c += v.Collapsed;
+        EXPECT(c == 1);  // adaptive.go:130-154: one new chain per chosen variable
+    }
+    adapt->MaxChains = (int)chains.size();
+    EXPECT(adapt->Adapt(chains, 4).size() == chains.size());  // adaptive.go:62-64
+}
+
+int main(int argc, char** argv) {
+    RES = argc > 1 ? argv[1] : "tests/golden/res";
+    struct { const char* name; std::function<void()> fn; } tests[] = {
+        {"TestWorkingGibbsSimple", TestWorkingGibbsSimple}, {"TestWorkingGibbsCollapsed", TestWorkingGibbsCollapsed},
+        {"TestFullGibbsCollapsed", TestFullGibbsCollapsed}, {"TestMergeChains", TestMergeChains},
+        {"TestMainLoopSimple", TestMainLoopSimple},         {"TestMainLoopAdaptive", TestMainLoopAdaptive}};
+    for (auto& t : tests) {
+        int before = failures;
+        try {
+            t.fn();
+        } catch (const std::exception& e) {
+            std::printf("  EXCEPTION in %s: %s\n", t.name, e.what());
+            failures++;
+        }
+        std::printf("%s %s\n", failures == before ? "PASS" : "FAIL", t.name);
+    }
+    sampler::ResetPool();
+    return failures ? 1 : 0;
+}
