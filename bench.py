@@ -164,7 +164,7 @@ def run_native(args):
         torch.cuda.synchronize()
 
     prec = {"table": gb.TABLE, "f32": gb.F32, "f64": gb.F64}[args.precision]
-    kernel = {"table": "k_sweep_tab<16>", "f32": "k_sweep_colour<float,2,4>", "f64": "k_sweep_colour<double,2,4>"}[args.precision]
+    kernel = {"table": "k_sweep_tab<32,4,1>", "f32": "k_sweep_colour<float,2,4>", "f64": "k_sweep_colour<double,2,4>"}[args.precision]
     dtype = {"table": "u32", "f32": "f32", "f64": "f64"}[args.precision]
     t_setup = time.time()
     arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)

@@ -320,19 +320,26 @@ __device__ __forceinline__ Philox4 philox_wide(uint32_t c0, uint32_t c1, uint32_
 
 // NN = neighbour slots read per variable (4 or 8); records pad unused slots with the variable
 // itself at stride 0, so the loads are unconditional and branch-free.
+// Neighbour rows belong to other colours, so they are read-only for the whole launch: the
+// non-coherent global path is safe and keeps the loads out of the generic address space.
+__device__ __forceinline__ uint2 ld_state8(const uint64_t addr) { return __ldg(reinterpret_cast<const uint2*>(addr)); }
+__device__ __forceinline__ void st_state8(const uint64_t addr, const uint2 v) {
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
 template <int NN>
 __device__ __forceinline__ void tab_load_nbrs(const int4* rec, const uint64_t my, const uint32_t n_pad, uint2 (&w)[NN]) {
     const int4 na = rec[1];
-    w[0] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.x * n_pad);
-    w[1] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.y * n_pad);
-    w[2] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.z * n_pad);
-    w[3] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)na.w * n_pad);
+    w[0] = ld_state8(my + (uint64_t)(uint32_t)na.x * n_pad);
+    w[1] = ld_state8(my + (uint64_t)(uint32_t)na.y * n_pad);
+    w[2] = ld_state8(my + (uint64_t)(uint32_t)na.z * n_pad);
+    w[3] = ld_state8(my + (uint64_t)(uint32_t)na.w * n_pad);
     if constexpr (NN == 8) {
         const int4 nb = rec[2];
-        w[4] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.x * n_pad);
-        w[5] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.y * n_pad);
-        w[6] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.z * n_pad);
-        w[7] = *reinterpret_cast<const uint2*>(my + (uint64_t)(uint32_t)nb.w * n_pad);
+        w[4] = ld_state8(my + (uint64_t)(uint32_t)nb.x * n_pad);
+        w[5] = ld_state8(my + (uint64_t)(uint32_t)nb.y * n_pad);
+        w[6] = ld_state8(my + (uint64_t)(uint32_t)nb.z * n_pad);
+        w[7] = ld_state8(my + (uint64_t)(uint32_t)nb.w * n_pad);
     }
 }
 
@@ -381,7 +388,7 @@ __device__ __forceinline__ unsigned tab_update(const DevModel& m, const DevTab& 
     uint2 outw;  // spread decision bits into state bytes: bit i -> byte i
     outw.x = ((xbits & 0xfu) * 0x00204081u) & 0x01010101u;
     outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-    *reinterpret_cast<uint2*>(my + (uint64_t)(uint32_t)hd.x * (uint32_t)g.n_pad) = outw;
+    st_state8(my + (uint64_t)(uint32_t)hd.x * (uint32_t)g.n_pad, outw);
     if (record && hist_half >= 0 && g.hist) {  // chain.go:237 as per-chain half-window histograms
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -393,12 +400,12 @@ __device__ __forceinline__ unsigned tab_update(const DevModel& m, const DevTab& 
     return __popc(xbits & vmask);
 }
 
-template <int VB, int NN, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int VB, int NN, int DEPTH>
+__global__ void __launch_bounds__(256)
 k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_begin, const int32_t n_vars_c,
             const uint32_t sweep, const int record, const int hist_half) {
     __shared__ int4 s_rec[VB * (kTabRec / 4)];
-    __shared__ unsigned int s_ones[VB];
+    __shared__ unsigned int s_ones[VB + 4];
     __shared__ uint16_t s_thr[VB * 256];
     const int units = g.n_pad >> 3;
     const int chunks = (units + 255) >> 8;
@@ -428,27 +435,32 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
         __syncthreads();
         const int thr_a = s_rec[0].y;
         const uint64_t my = reinterpret_cast<uint64_t>(g.state) + 8ull * (uint64_t)unit;
-        // software pipeline: the next variable's neighbour words are in flight while this one computes
-        // (variables of one colour are never neighbours, so the early loads cannot see this tile's writes)
-        uint2 wA[NN], wB[NN];
-        if (active) tab_load_nbrs<NN>(s_rec, my, n_pad, wA);
-        for (int jj = 0; jj < nv; jj += 2) {
-            unsigned o0 = 0, o1 = 0;
-            const bool has1 = jj + 1 < nv;
-            if (active) {
-                if (has1) tab_load_nbrs<NN>(s_rec + (jj + 1) * 5, my, n_pad, wB);
-                o0 = tab_update<NN>(m, t, g, s_rec + jj * 5, wA, s_thr, thr_a, my, chain_blk, sweep, vmask, nvalid, unit, record, hist_half);
-                if (has1) {
-                    if (jj + 2 < nv) tab_load_nbrs<NN>(s_rec + (jj + 2) * 5, my, n_pad, wA);
-                    o1 = tab_update<NN>(m, t, g, s_rec + (jj + 1) * 5, wB, s_thr, thr_a, my, chain_blk, sweep, vmask, nvalid, unit, record, hist_half);
+        // software pipeline, DEPTH variables deep: the neighbour words of the next DEPTH-1 variables
+        // are in flight while this one computes (variables of one colour are never neighbours, so
+        // the early loads cannot see this tile's writes)
+        uint2 w[DEPTH][NN];
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < DEPTH - 1; d++)
+                if (d < nv) tab_load_nbrs<NN>(s_rec + d * 5, my, n_pad, w[d]);
+        }
+        for (int jj = 0; jj < nv; jj += DEPTH) {
+            unsigned o[DEPTH];
+#pragma unroll
+            for (int d = 0; d < DEPTH; d++) {
+                o[d] = 0;
+                if (active && jj + d < nv) {
+                    if (jj + d + DEPTH - 1 < nv)
+                        tab_load_nbrs<NN>(s_rec + (jj + d + DEPTH - 1) * 5, my, n_pad, w[(d + DEPTH - 1) % DEPTH]);
+                    o[d] = tab_update<NN>(m, t, g, s_rec + (jj + d) * 5, w[d], s_thr, thr_a, my, chain_blk, sweep, vmask,
+                                          nvalid, unit, record, hist_half);
                 }
             }
             if (record) {  // chain.go:231-236, aggregated warp -> CTA (shared) -> one global atomic per variable per tile
-                const unsigned s0 = __reduce_add_sync(0xffffffffu, o0);
-                const unsigned s1 = __reduce_add_sync(0xffffffffu, o1);
-                if (lane == 0) {
-                    if (s0) atomicAdd(&s_ones[jj], s0);
-                    if (s1) atomicAdd(&s_ones[jj + 1], s1);
+#pragma unroll
+                for (int d = 0; d < DEPTH; d++) {
+                    const unsigned sd = __reduce_add_sync(0xffffffffu, o[d]);
+                    if (lane == 0 && sd) atomicAdd(&s_ones[jj + d], sd);
                 }
             }
         }
