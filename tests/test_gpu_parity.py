@@ -504,3 +504,30 @@ def test_ising_large_properties():
     h_pos = tables[0:2 * H * W:2] > tables[1:2 * H * W:2]  # e^h > e^-h -> value 0 favoured
     p0 = counts[:, 0] / counts.sum(1)
     assert p0[h_pos].mean() > 0.55 and p0[~h_pos].mean() < 0.45
+
+
+def test_ising_full_baseline_size():
+    """BASELINE configs[4] at full size (1024x1024 variables x 65536 chains = 64 GiB of state):
+    size-independent invariants of one recorded sweep, and the shard-independence of the stream."""
+    import torch  # only to skip when the device is too small
+    if torch.cuda.get_device_properties(0).total_memory < 100 * 2**30:
+        pytest.skip("needs a 180 GB device")
+    H = W = 1024
+    dm = gb.Model.from_arrays(*gb.ising_torus(H, W, wmax=4.9), device=0)
+    order, coff = dm.schedule()
+    assert coff.tolist() == [0, H * W // 2, H * W]
+    n_chains = 65536
+    ch = gb.Chains(dm, n_chains, seed=20260101, precision=gb.TABLE, device=0)
+    ch.sweep(2)
+    counts = ch.group_counts(0).reshape(-1, 2)
+    assert np.all(counts.sum(1) == 2 * n_chains)          # every variable recorded once per sweep per chain
+    assert ch.total_samples == 2 * H * W * n_chains
+    merged, col = ch.merged_marginals()
+    assert not col.any() and np.allclose(merged.reshape(-1, 2).sum(1), 3 * n_chains)
+    # a 16-chain shard starting at global chain 4096 reproduces those chains' states exactly
+    del ch
+    big = gb.Chains(dm, 8192, seed=5, precision=gb.TABLE, device=0)
+    small = gb.Chains(dm, 16, seed=5, first_chain_id=4096, precision=gb.TABLE, device=0)
+    big.sweep(2)
+    small.sweep(2)
+    assert np.array_equal(big.get_state(0, 8192)[4096:4112], small.get_state(0, 16))
