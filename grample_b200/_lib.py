@@ -61,6 +61,7 @@ _SIGS = {
     "gb_chains_sweep": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "gb_chains_sweep_timed": (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "gb_chains_launch_count": (C.c_int, [_vp, _i64p]),
+    "gb_chains_scan": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "gb_chains_burnin": (C.c_int, [_vp, C.c_int64]),
     "gb_chains_advance": (C.c_int, [_vp, C.c_int32]),
     "gb_chains_total_samples": (C.c_int, [_vp, _i64p]),

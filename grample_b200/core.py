@@ -209,6 +209,10 @@ class Chains:
         check(lib().gb_chains_launch_count(self.h, C.byref(v)))
         return v.value
 
+    def scan(self, n_steps, record=True):
+        """reference schedule: n_steps random-scan single-variable updates per chain"""
+        check(lib().gb_chains_scan(self.h, int(n_steps), int(record)))
+
     def burnin(self, n_sweeps):
         check(lib().gb_chains_burnin(self.h, int(n_sweeps)))
 

@@ -136,6 +136,7 @@ struct Group {
     uint64_t first_chain = 0;
     uint32_t sweep = 0;  // next Philox sweep index
     int64_t total_samples = 0;  // Chain.TotalSampleCount summed over the group's chains
+    uint64_t scan_step = 0;     // next random-scan step index
     uint8_t* d_state = nullptr;
     unsigned long long* d_counts = nullptr;
     uint16_t* d_hist = nullptr;
@@ -716,6 +717,29 @@ int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_
     GB_END
 }
 int gb_chains_launch_count(const gb_chains* c, int64_t* out) { *out = c->launches; return 0; }
+int gb_chains_scan(gb_chains* c, int64_t n_steps, int record) {
+    GB_TRY
+    if (n_steps < 0) throw gb::Err("Invalid step count");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    for (auto& g : c->groups) {
+        const gb::HostModel& h = g.model->h;
+        const int blocks = (g.n_chains + 127) / 128;
+        const int32_t n_order = (int32_t)h.order.size();
+        const int mc = h.max_card;
+        if (mc <= 2) gb::k_random_scan<2><<<blocks, 128, 0, c->stream>>>(g.model->dev, g.dev, g.model->d_order, n_order, g.scan_step, n_steps, record);
+        else if (mc <= 4) gb::k_random_scan<4><<<blocks, 128, 0, c->stream>>>(g.model->dev, g.dev, g.model->d_order, n_order, g.scan_step, n_steps, record);
+        else if (mc <= 16) gb::k_random_scan<16><<<blocks, 128, 0, c->stream>>>(g.model->dev, g.dev, g.model->d_order, n_order, g.scan_step, n_steps, record);
+        else gb::k_random_scan<64><<<blocks, 128, 0, c->stream>>>(g.model->dev, g.dev, g.model->d_order, n_order, g.scan_step, n_steps, record);
+        c->launches++;
+        g.scan_step += (uint64_t)n_steps;
+        if (record) {
+            g.total_samples += n_steps * g.n_chains;
+            c->total_samples += n_steps * g.n_chains;
+        }
+    }
+    CUDA_CHECK(cudaGetLastError());
+    GB_END
+}
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps) {
     GB_TRY sweeps(c, n_sweeps, 0, -1);
     GB_END

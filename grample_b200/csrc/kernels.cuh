@@ -499,6 +499,46 @@ __global__ void __launch_bounds__(256) k_init_state(const DevModel m, const DevG
     }
 }
 
+// ------------------------------------------------------------------ K1-scan (parity mode)
+// The reference's own schedule: every step each chain picks ONE variable uniformly among the
+// free, un-collapsed ones (sampler.go:135-174) and updates it (gibbs-simple.go:163-271).  One
+// thread per chain, float64, one Philox call per (chain, step): words (x) -> variable index by
+// multiply-shift (the reference uses Int31n's rejection sampling; the bias here is < n/2^32),
+// words (z, w) -> the 53-bit uniform of the value draw.  Slow by design (divergent gathers): it
+// exists so that small-model parity runs can use the reference's schedule.
+template <int MAXC>
+__global__ void __launch_bounds__(128)
+k_random_scan(const DevModel m, const DevGroup g, const int32_t* __restrict__ order, const int32_t n_order,
+              const uint64_t step0, const int64_t n_steps, const int record) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= g.n_chains) return;
+    const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)ch);
+    for (int64_t s = 0; s < n_steps; s++) {
+        const uint64_t step = step0 + (uint64_t)s;
+        const Philox4 r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), chain, kTagScan, g.seed_lo, g.seed_hi);
+        const int v = order[__umulhi(r.x, (uint32_t)n_order)];
+        const int card = m.card[v];
+        double w[MAXC];
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) w[k] = 0.0;
+        const int32_t* p = m.prog + m.prog_off[v];
+        const int nf = *p++;
+        for (int f = 0; f < nf; f++) {
+            const int tab_off = p[0], sv = p[1], no = p[2];
+            p += 3;
+            int b = tab_off;
+            for (int o = 0; o < no; o++, p += 2) b += (int)g.state[(size_t)p[0] * g.n_pad + ch] * p[1];
+#pragma unroll
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) w[k] += m.tab64[b + k * sv];
+        }
+        stabilise_exp_floor<double, MAXC>(w, card);
+        const int x = inverse_cdf<double, MAXC>(w, card, u53(r.z, r.w));
+        g.state[(size_t)v * g.n_pad + ch] = (uint8_t)x;
+        if (record) atomicAdd(g.counts + m.card_off[v] + x, 1ull);
+    }
+}
+
 // ------------------------------------------------------------------ K5
 // states: int32 [n_states][n_vars]; out: double [n_states][kOutStride] floored weights e[k]
 constexpr int kProbeStride = 64;

@@ -136,6 +136,12 @@ int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record);
 int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_out);
 /* number of kernels launched on behalf of this handle so far */
 int gb_chains_launch_count(const gb_chains* c, int64_t* out);
+/* Parity mode with the reference's OWN schedule: n_steps single-variable updates per chain, each
+ * on a variable drawn uniformly among the free, un-collapsed ones ((*GibbsSimple).Sample /
+ * (*GibbsCollapsed).Sample + UniformSampler.VarSample, sampler/sampler.go:135-174), float64
+ * arithmetic.  One thread per chain: meant for small-model parity runs, not for throughput.
+ * No window histograms are kept in this mode. */
+int gb_chains_scan(gb_chains* c, int64_t n_steps, int record);
 /* burn-in (chain.go:167-172): un-recorded.  The reference counts single-variable steps;
  * callers convert with ceil(steps / n_free). */
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps);

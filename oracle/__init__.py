@@ -456,6 +456,21 @@ class Sampler:
         return st, counts
 
 
+def _scan_run(self, order, seed, chain0, states, step0, n_steps, record=True, counts=None):
+    """Device random-scan parity mode (oracle/sweep.hpp::scan_chain)."""
+    order = _ia(order)
+    st = _ia(states).copy()
+    if counts is None:
+        counts = np.zeros(int(self.model.cards.sum()))
+    counts = _da(counts).copy()
+    _chk(lib().orc_scan_run(self.h, _p(order, C.c_int), len(order), C.c_ulonglong(seed), C.c_uint(chain0), st.shape[0],
+                            C.c_ulonglong(step0), C.c_longlong(n_steps), int(record), _p(st, C.c_int), _p(counts, C.c_double)))
+    return st, counts
+
+
+Sampler.scan_run = _scan_run
+
+
 class Chain:
     def __init__(self, model=None, sampler=None, cw=0, burn_in=0, _handle=None):
         self.model, self.sampler = model, sampler

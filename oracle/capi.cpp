@@ -596,4 +596,17 @@ int orc_sweep_run(void* sampler, const int* order, int n_order, unsigned long lo
     ORC_END
 }
 
+int orc_scan_run(void* sampler, const int* order, int n_order, unsigned long long seed, unsigned chain0, int n_chains,
+                 unsigned long long step0, long long n_steps, int record, int* states, double* counts) {
+    ORC_TRY
+    auto* h = (SamplerH*)sampler;
+    std::vector<int> ord(order, order + n_order), off;
+    int acc = 0;
+    for (auto& v : h->model->vars) { off.push_back(acc); acc += v.card; }
+    size_t nv = h->model->vars.size();
+    for (int c = 0; c < n_chains; c++)
+        scan_chain(*h->simple, ord, seed, chain0 + (unsigned)c, step0, n_steps, record != 0, states + (size_t)c * nv, off, counts);
+    ORC_END
+}
+
 }  // extern "C"

@@ -79,4 +79,32 @@ inline void sweep_chain(GibbsSimple& gs, const std::vector<int>& order, uint64_t
     }
 }
 
+// Random-scan parity mode of the device (k_random_scan): the reference's schedule with the
+// device's Philox stream — one call per (chain, step): word 0 picks the variable by
+// multiply-shift, words 2..3 form the 53-bit uniform of the value draw.
+inline void scan_chain(GibbsSimple& gs, const std::vector<int>& order, uint64_t seed, uint32_t chain, uint64_t step0,
+                       int64_t n_steps, bool record, int* state, const std::vector<int>& count_off, double* counts) {
+    FixedUniform fu;
+    UniformSampler us(&fu, 1);
+    std::vector<double> w;
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int64_t s = 0; s < n_steps; s++) {
+        const uint64_t step = step0 + (uint64_t)s;
+        uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), chain, kTagScan}, out[4];
+        Philox4x32::gen(ctr, key, out);
+        const int v = order[(size_t)(((uint64_t)out[0] * (uint64_t)order.size()) >> 32)];
+        gs.conditional(v, state, w);
+        const uint64_t x = (((uint64_t)out[2] << 32) | out[3]) >> 11;
+        fu.next = (double)x * (1.0 / 9007199254740992.0);
+        int k;
+        try {
+            k = us.weighted_sample((int64_t)w.size(), w.data(), w.size());
+        } catch (const Error&) {
+            k = (int)w.size() - 1;
+        }
+        state[v] = k;
+        if (record && !gs.pgm->vars[v].collapsed) counts[count_off[v] + k] += 1.0;
+    }
+}
+
 }  // namespace oracle

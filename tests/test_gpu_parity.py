@@ -218,6 +218,45 @@ def test_table_mode_statistics_match_f64(res):
     assert np.abs(out[0] - out[1]).max() < 0.05
 
 
+# ------------------------------------------------------------------ random-scan parity mode (the reference's schedule)
+@pytest.mark.parametrize("name,evid,n_chains,n_steps", [
+    ("one.uai", False, 5, 40), ("sample.uai", False, 7, 300), ("Grids_11.uai", False, 9, 1500),
+    ("Pedigree_11.uai", True, 6, 1200), ("ObjectDetection_11.uai", False, 5, 400)])
+def test_random_scan_bitexact(res, name, evid, n_chains, n_steps):
+    dm, om = load_pair(res, name, evid)
+    order, _ = dm.schedule()
+    seed, first = 2718, 8
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0)
+    st0 = ch.get_state(0, n_chains)
+    ch.scan(100, record=False)  # burn-in counts single-variable steps (chain.go:167-172)
+    ch.scan(n_steps, record=True)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, _ = samp.scan_run(order, seed, first, st0, 0, 100, record=False)
+    ost, ocounts = samp.scan_run(order, seed, first, ost, 100, n_steps, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+    assert ch.total_samples == n_steps * n_chains
+    assert ocounts.sum() == n_steps * n_chains
+
+
+def test_random_scan_collapsed_and_statistics(res):
+    dm, om = load_pair(res, "sample.uai", False)
+    nm, v, marg = dm.collapse(1)
+    order, _ = nm.schedule()
+    ch = gb.Chains(nm, 256, seed=3, precision=gb.F64, device=0)
+    ch.scan(200, record=False)
+    ch.scan(4000, record=True)
+    counts = ch.group_counts(0).astype(float)
+    assert counts[2:4].sum() == 0  # the collapsed variable is never selected (gibbs-collapsed.go:326)
+    # random scan and colour sweep leave the same stationary marginals
+    sw = gb.Chains(nm, 256, seed=4, precision=gb.F64, device=0)
+    sw.burnin(100)
+    sw.sweep(2000)
+    c2 = sw.group_counts(0).astype(float)
+    for a, b in ((0, 2), (4, 7)):
+        assert np.abs(counts[a:b] / counts[a:b].sum() - c2[a:b] / c2[a:b].sum()).max() < 0.01
+
+
 def test_sweep_independent_of_sharding(res):
     """Philox is keyed by the global chain id: chains 8..15 of a 16-chain run == an 8-chain shard."""
     dm, _ = load_pair(res, "Grids_11.uai", False)
@@ -524,10 +563,40 @@ def test_ising_full_baseline_size():
     assert ch.total_samples == 2 * H * W * n_chains
     merged, col = ch.merged_marginals()
     assert not col.any() and np.allclose(merged.reshape(-1, 2).sum(1), 3 * n_chains)
-    # a 16-chain shard starting at global chain 4096 reproduces those chains' states exactly
+    # a 16-chain shard starting at global chain 4096 reproduces those chains' states exactly (chains 4064..4127 vs 4096..4111)
     del ch
-    big = gb.Chains(dm, 8192, seed=5, precision=gb.TABLE, device=0)
+    big = gb.Chains(dm, 64, seed=5, first_chain_id=4064, precision=gb.TABLE, device=0)
     small = gb.Chains(dm, 16, seed=5, first_chain_id=4096, precision=gb.TABLE, device=0)
     big.sweep(2)
     small.sweep(2)
-    assert np.array_equal(big.get_state(0, 8192)[4096:4112], small.get_state(0, 16))
+    assert np.array_equal(big.get_state(0, 64)[32:48], small.get_state(0, 16))
+
+
+# ------------------------------------------------------------------ CLI (cmd/root.go flags and report format)
+def test_cli_sample_adaptive(res, tmp_path):
+    import io
+
+    from grample_b200 import cli
+    trace = tmp_path / "trace.txt"
+    args = cli.build_parser().parse_args(["sample", "-m", res("Pedigree_11.uai"), "-d", "-o", "-s", "adaptive", "-a", "4",
+                                          "-b", "2000", "-w", "20", "-c", "2", "-i", "3000000", "-e", "5", "--replicas", "16",
+                                          "-p", "-t", str(trace)])
+    out = io.StringIO()
+    final, col = cli.sample(args, out)
+    text = out.getvalue()
+    assert "Model has 385 vars and 385 functions" in text and "Main Sampling Start" in text and "DONE" in text
+    assert "ADAPT:" in text and "FINAL ... M:mean(neg log), X:max(neg log)" in text and "HEL=>" in text
+    assert col.sum() >= 4 and np.allclose(np.add.reduceat(final, np.concatenate([[0], np.cumsum(gb.Model.from_uai(res("Pedigree_11.uai"), device=-1).cards)[:-1]])), 1.0)
+    lines = trace.read_text().splitlines()
+    assert lines[1] == "RunSecs, MaxHell, NegLogMaxHell, MaxJS, NegLogMaxJS, CollapseCount"
+    assert len(lines[2].split(",")) == 6  # the row format script/trace_file_process.py parses
+
+
+def test_cli_errors(res):
+    from grample_b200 import cli
+    args = cli.build_parser().parse_args(["sample", "-m", res("one.uai"), "-s", "simple", "-a", "3"])
+    with pytest.raises(gb.GrampleError, match="ChainAdds"):  # cmd/root.go:440-442
+        cli.sample(args)
+    args = cli.build_parser().parse_args(["sample", "-m", res("one.uai"), "-p"])
+    with pytest.raises(gb.GrampleError, match="trace file"):  # cmd/root.go:313-316
+        cli.sample(args)
