@@ -159,6 +159,12 @@ struct gb_chains {
     double* d_merged_in = nullptr;
     int32_t last_cw = -1;       // ConvergenceWindow of the last gb_chains_advance
     int64_t launches = 0;       // kernels launched on behalf of this handle
+    // merge path caches (rebuilt when a group is added)
+    std::vector<uint8_t> col_any;      // collapsed in any group
+    std::vector<int> col_first_group;  // first group (list order) in which a variable is collapsed
+    std::vector<int> col_vars;         // indices of the collapsed-in-any variables
+    bool skip_uploaded = false;
+    double* h_merge = nullptr;         // pinned staging buffer for the device -> host copy
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     ~gb_chains() {
@@ -173,6 +179,7 @@ struct gb_chains {
         cudaFree(d_wb);
         cudaFree(d_skip);
         cudaFree(d_merged_in);
+        if (h_merge) cudaFreeHost(h_merge);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -219,6 +226,8 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     c->launches++;
     CUDA_CHECK(cudaGetLastError());
     c->groups.push_back(g);
+    c->col_any.clear();  // invalidate the merge caches
+    c->skip_uploaded = false;
 }
 
 template <typename Real, int MAXC, int CW>
@@ -327,32 +336,42 @@ void ensure_scratch(gb_chains* c) {
     if (!c->d_skip) CUDA_CHECK(cudaMalloc(&c->d_skip, (size_t)h.n_vars));
 }
 
+void refresh_collapsed_cache(gb_chains* c) {
+    if (!c->col_any.empty()) return;
+    c->col_any = collapsed_any(c, &c->col_first_group);
+    c->col_vars.clear();
+    for (int v = 0; v < (int)c->col_any.size(); v++)
+        if (c->col_any[v]) c->col_vars.push_back(v);
+}
+
 void merge_partial(gb_chains* c) {
     CUDA_CHECK(cudaSetDevice(c->device));
     ensure_scratch(c);
     const gb::HostModel& h = c->base();
-    std::vector<uint8_t> col = collapsed_any(c);
-    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, col.data(), col.size(), cudaMemcpyHostToDevice, c->stream));
+    refresh_collapsed_cache(c);
+    // d_skip is shared with the convergence path (which also marks fixed variables): re-upload
+    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, c->col_any.data(), c->col_any.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->d_merge, 0, (size_t)h.total_card * sizeof(double), c->stream));
     for (auto& g : c->groups)
         gb::k_merge_partial<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(g.model->dev, g.d_counts,
                                                                               (double)g.n_chains, c->d_skip, c->d_merge);
     c->launches += (int64_t)c->groups.size();
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // col goes out of scope
 }
 
 void merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const gb::HostModel& h = c->base();
-    CUDA_CHECK(cudaMemcpyAsync(out, c->d_merge, (size_t)h.total_card * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    const size_t bytes = (size_t)h.total_card * sizeof(double);
+    if (!c->h_merge) CUDA_CHECK(cudaMallocHost(&c->h_merge, bytes));
+    CUDA_CHECK(cudaMemcpyAsync(c->h_merge, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    std::vector<int> first;
-    std::vector<uint8_t> col = collapsed_any(c, &first);
-    for (int v = 0; v < h.n_vars; v++) {
-        if (collapsed_out) collapsed_out[v] = col[v];
-        if (!col[v]) continue;
-        const auto& m = c->groups[first[v]].model->h.coll_marg[v];  // chain.go:113-129: first chain found
+    std::memcpy(out, c->h_merge, bytes);
+    refresh_collapsed_cache(c);
+    if (collapsed_out)
+        for (int v = 0; v < h.n_vars; v++) collapsed_out[v] = c->col_any[v];
+    for (int v : c->col_vars) {
+        const auto& m = c->groups[c->col_first_group[v]].model->h.coll_marg[v];  // chain.go:113-129: first chain found
         for (int k = 0; k < h.card[v]; k++) out[h.card_off[v] + k] = m[k];
     }
 }
@@ -821,6 +840,7 @@ int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out
 int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out) {
     GB_TRY
     merge_partial(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the caller all-reduces the buffer on ITS stream
     *dev_ptr_out = c->d_merge;
     *n_out = c->base().total_card;
     GB_END
