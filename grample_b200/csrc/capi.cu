@@ -238,38 +238,31 @@ void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int
     c->launches++;
 }
 
-template <int VB, int NN, int DEPTH>
+template <int VB, int NN, bool HIST>
 void launch_tab_variant(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
     static int resident = 0;  // CTAs that fit the device at once (persistent tile loop)
     if (!resident) {
         int per_sm = 0, sms = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB, NN, DEPTH>, 256, 0));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB, NN, HIST>, 256, 0));
         resident = std::max(1, per_sm * sms);
     }
     const gb::HostModel& h = g.model->h;
     const int64_t tiles = (int64_t)((g.n_pad / 8 + 255) / 256) * ((n + VB - 1) / VB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
-    gb::k_sweep_tab<VB, NN, DEPTH><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, h.colour_off[col], n,
+    gb::k_sweep_tab<VB, NN, HIST><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, h.colour_off[col], n,
                                                               g.sweep, record, hist_half);
     c->launches++;
 }
 
 void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
-    // tuning knob GB_TAB_VARIANT = prefetch depth of the neighbour loads (2, 3 or 4 variables)
-    static int variant = -1;
-    if (variant < 0) {
-        const char* e = std::getenv("GB_TAB_VARIANT");
-        variant = e ? std::atoi(e) : 2;
-    }
+    const bool hist = g.d_hist != nullptr && hist_half >= 0;
     if (g.model->h.tab_max_nbr > 4) {
-        launch_tab_variant<32, 8, 2>(c, g, col, n, record, hist_half);
-        return;
-    }
-    switch (variant) {
-        case 3: launch_tab_variant<32, 4, 3>(c, g, col, n, record, hist_half); break;
-        case 4: launch_tab_variant<32, 4, 4>(c, g, col, n, record, hist_half); break;
-        default: launch_tab_variant<32, 4, 2>(c, g, col, n, record, hist_half); break;
+        if (hist) launch_tab_variant<32, 8, true>(c, g, col, n, record, hist_half);
+        else launch_tab_variant<32, 8, false>(c, g, col, n, record, hist_half);
+    } else {
+        if (hist) launch_tab_variant<32, 4, true>(c, g, col, n, record, hist_half);
+        else launch_tab_variant<32, 4, false>(c, g, col, n, record, hist_half);
     }
 }
 

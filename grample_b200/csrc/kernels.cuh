@@ -327,80 +327,11 @@ __device__ __forceinline__ void st_state8(const uint64_t addr, const uint2 v) {
     asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
-template <int NN>
-__device__ __forceinline__ void tab_load_nbrs(const int4* rec, const uint64_t my, const uint32_t n_pad, uint2 (&w)[NN]) {
-    const int4 na = rec[1];
-    w[0] = ld_state8(my + (uint64_t)(uint32_t)na.x * n_pad);
-    w[1] = ld_state8(my + (uint64_t)(uint32_t)na.y * n_pad);
-    w[2] = ld_state8(my + (uint64_t)(uint32_t)na.z * n_pad);
-    w[3] = ld_state8(my + (uint64_t)(uint32_t)na.w * n_pad);
-    if constexpr (NN == 8) {
-        const int4 nb = rec[2];
-        w[4] = ld_state8(my + (uint64_t)(uint32_t)nb.x * n_pad);
-        w[5] = ld_state8(my + (uint64_t)(uint32_t)nb.y * n_pad);
-        w[6] = ld_state8(my + (uint64_t)(uint32_t)nb.z * n_pad);
-        w[7] = ld_state8(my + (uint64_t)(uint32_t)nb.w * n_pad);
-    }
-}
-
-// One variable x 8 chains: configuration indices from the neighbour words, thresholds from
-// shared memory, one Philox call, compare, store.  Returns the number of ones among valid chains.
-template <int NN>
-__device__ __forceinline__ unsigned tab_update(const DevModel& m, const DevTab& t, const DevGroup& g, const int4* rec,
-                                               const uint2 (&w)[NN], const uint16_t* s_thr, const int thr_a,
-                                               const uint64_t my, const uint32_t chain_blk, const uint32_t sweep,
-                                               const uint32_t vmask, const int nvalid, const int unit, const int record,
-                                               const int hist_half) {
-    const int4 hd = rec[0];  // v, thr_off, n_nbr, card_off
-    const int4 sa = rec[3];
-    uint32_t cfg_lo = w[0].x * (uint32_t)sa.x + w[1].x * (uint32_t)sa.y + w[2].x * (uint32_t)sa.z + w[3].x * (uint32_t)sa.w;
-    uint32_t cfg_hi = w[0].y * (uint32_t)sa.x + w[1].y * (uint32_t)sa.y + w[2].y * (uint32_t)sa.z + w[3].y * (uint32_t)sa.w;
-    if constexpr (NN == 8) {
-        const int4 sb = rec[4];
-        cfg_lo += w[4].x * (uint32_t)sb.x + w[5].x * (uint32_t)sb.y + w[6].x * (uint32_t)sb.z + w[7].x * (uint32_t)sb.w;
-        cfg_hi += w[4].y * (uint32_t)sb.x + w[5].y * (uint32_t)sb.y + w[6].y * (uint32_t)sb.z + w[7].y * (uint32_t)sb.w;
-    }
-    const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
-    const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
-    const char* const tb = reinterpret_cast<const char*>(s_thr + (hd.y - thr_a));
-    uint32_t xbits = 0, tie = 1;
-#pragma unroll
-    for (int i = 7; i >= 0; i--) {
-        const uint32_t idx = __byte_perm(i < 4 ? cfg_lo : cfg_hi, 0, 0x4440 + (i & 3));
-        const uint32_t th = *reinterpret_cast<const uint16_t*>(tb + idx + idx);
-        const uint32_t hi = (i & 1) ? (wa[i >> 1] >> 16) : __byte_perm(wa[i >> 1], 0, 0x4410);
-        const uint32_t d = th - hi;            // sign bit set <=> hi > th  (both < 2^16)
-        xbits = __funnelshift_l(d, xbits, 1);  // xbits = (xbits << 1) | (hi > th)
-        tie *= d;                              // zero if any high half ties (rare false positives are harmless)
-    }
-    if (tie == 0) {  // resolve ties with the low halves: draw > threshold <=> lo16 > (T & 0xffff)
-        const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
-        const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
-            const uint32_t T = __ldg(t.thr + hd.y + idx);
-            const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-            const uint32_t lo = (wb[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-            if (hi == (T >> 16) && lo > (T & 0xffffu)) xbits |= 1u << i;
-        }
-    }
-    uint2 outw;  // spread decision bits into state bytes: bit i -> byte i
-    outw.x = ((xbits & 0xfu) * 0x00204081u) & 0x01010101u;
-    outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-    st_state8(my + (uint64_t)(uint32_t)hd.x * (uint32_t)g.n_pad, outw);
-    if (record && hist_half >= 0 && g.hist) {  // chain.go:237 as per-chain half-window histograms
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (i < nvalid) {
-                uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + hd.w + ((xbits >> i) & 1u)) * g.n_pad + 8 * (size_t)unit + i;
-                *h = (uint16_t)(*h + 1);
-            }
-    }
-    return __popc(xbits & vmask);
-}
-
-template <int VB, int NN, int DEPTH>
+// NN = neighbour slots read per variable (4 or 8); records pad unused slots with the variable
+// itself at stride 0, so the loads are unconditional and branch-free.  HIST = keep the per-chain
+// half-window histograms (chain.go:237).  All shared-memory accesses go through the array symbols
+// (not through generic pointers) so they compile to LDS with immediate bases.
+template <int VB, int NN, bool HIST>
 __global__ void __launch_bounds__(256)
 k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_begin, const int32_t n_vars_c,
             const uint32_t sweep, const int record, const int hist_half) {
@@ -411,8 +342,8 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
     const int chunks = (units + 255) >> 8;
     const int n_vb = (n_vars_c + VB - 1) / VB;
     const int64_t n_tiles = (int64_t)chunks * n_vb;
-    const int lane = threadIdx.x & 31;
     const uint32_t n_pad = (uint32_t)g.n_pad;
+    const uint32_t seed_lo = g.seed_lo, seed_hi = g.seed_hi;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int chunk = (int)(tile / n_vb);
         const int vb = (int)(tile - (int64_t)chunk * n_vb);
@@ -433,34 +364,93 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
             if (threadIdx.x < VB) s_ones[threadIdx.x] = 0;
         }
         __syncthreads();
-        const int thr_a = s_rec[0].y;
-        const uint64_t my = reinterpret_cast<uint64_t>(g.state) + 8ull * (uint64_t)unit;
-        // software pipeline, DEPTH variables deep: the neighbour words of the next DEPTH-1 variables
-        // are in flight while this one computes (variables of one colour are never neighbours, so
-        // the early loads cannot see this tile's writes)
-        uint2 w[DEPTH][NN];
         if (active) {
-#pragma unroll
-            for (int d = 0; d < DEPTH - 1; d++)
-                if (d < nv) tab_load_nbrs<NN>(s_rec + d * 5, my, n_pad, w[d]);
-        }
-        for (int jj = 0; jj < nv; jj += DEPTH) {
-            unsigned o[DEPTH];
-#pragma unroll
-            for (int d = 0; d < DEPTH; d++) {
-                o[d] = 0;
-                if (active && jj + d < nv) {
-                    if (jj + d + DEPTH - 1 < nv)
-                        tab_load_nbrs<NN>(s_rec + (jj + d + DEPTH - 1) * 5, my, n_pad, w[(d + DEPTH - 1) % DEPTH]);
-                    o[d] = tab_update<NN>(m, t, g, s_rec + (jj + d) * 5, w[d], s_thr, thr_a, my, chain_blk, sweep, vmask,
-                                          nvalid, unit, record, hist_half);
+            const int thr_a = s_rec[0].y;
+            const uint64_t my = reinterpret_cast<uint64_t>(g.state) + 8ull * (uint64_t)unit;
+            const unsigned amask = __activemask();  // the lanes of this warp that own chains (all, except in a ragged last chunk)
+            const bool leader = (threadIdx.x & 31) == (__ffs(amask) - 1);
+
+            auto load_nbrs = [&](const int j, uint2(&w)[NN]) {
+                const int4 na = s_rec[j * 5 + 1];
+                w[0] = ld_state8(my + (uint64_t)(uint32_t)na.x * n_pad);
+                w[1] = ld_state8(my + (uint64_t)(uint32_t)na.y * n_pad);
+                w[2] = ld_state8(my + (uint64_t)(uint32_t)na.z * n_pad);
+                w[3] = ld_state8(my + (uint64_t)(uint32_t)na.w * n_pad);
+                if constexpr (NN == 8) {
+                    const int4 nb = s_rec[j * 5 + 2];
+                    w[4] = ld_state8(my + (uint64_t)(uint32_t)nb.x * n_pad);
+                    w[5] = ld_state8(my + (uint64_t)(uint32_t)nb.y * n_pad);
+                    w[6] = ld_state8(my + (uint64_t)(uint32_t)nb.z * n_pad);
+                    w[7] = ld_state8(my + (uint64_t)(uint32_t)nb.w * n_pad);
                 }
-            }
-            if (record) {  // chain.go:231-236, aggregated warp -> CTA (shared) -> one global atomic per variable per tile
+            };
+            // one variable x 8 chains: configuration indices, one Philox call, threshold compare, store
+            auto update = [&](const int j, const uint2(&w)[NN]) {
+                const int4 hd = s_rec[j * 5];  // v, thr_off, n_nbr, card_off
+                const int4 sa = s_rec[j * 5 + 3];
+                uint32_t cfg_lo = w[0].x * (uint32_t)sa.x + w[1].x * (uint32_t)sa.y + w[2].x * (uint32_t)sa.z + w[3].x * (uint32_t)sa.w;
+                uint32_t cfg_hi = w[0].y * (uint32_t)sa.x + w[1].y * (uint32_t)sa.y + w[2].y * (uint32_t)sa.z + w[3].y * (uint32_t)sa.w;
+                if constexpr (NN == 8) {
+                    const int4 sb = s_rec[j * 5 + 4];
+                    cfg_lo += w[4].x * (uint32_t)sb.x + w[5].x * (uint32_t)sb.y + w[6].x * (uint32_t)sb.z + w[7].x * (uint32_t)sb.w;
+                    cfg_hi += w[4].y * (uint32_t)sb.x + w[5].y * (uint32_t)sb.y + w[6].y * (uint32_t)sb.z + w[7].y * (uint32_t)sb.w;
+                }
+                const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, seed_lo, seed_hi);
+                const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+                const int toff = hd.y - thr_a;
+                uint32_t xbits = 0, tie = 1;
 #pragma unroll
-                for (int d = 0; d < DEPTH; d++) {
-                    const unsigned sd = __reduce_add_sync(0xffffffffu, o[d]);
-                    if (lane == 0 && sd) atomicAdd(&s_ones[jj + d], sd);
+                for (int i = 7; i >= 0; i--) {
+                    const uint32_t idx = __byte_perm(i < 4 ? cfg_lo : cfg_hi, 0, 0x4440 + (i & 3));
+                    const uint32_t th = s_thr[toff + idx];
+                    const uint32_t hi = (i & 1) ? (wa[i >> 1] >> 16) : __byte_perm(wa[i >> 1], 0, 0x4410);
+                    const uint32_t d = th - hi;            // sign bit set <=> hi > th  (both < 2^16)
+                    xbits = __funnelshift_l(d, xbits, 1);  // xbits = (xbits << 1) | (hi > th)
+                    tie *= d;                              // zero if any high half ties (rare false positives are harmless)
+                }
+                if (tie == 0) {  // resolve ties with the low halves: draw > threshold <=> lo16 > (T & 0xffff)
+                    const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, seed_lo, seed_hi);
+                    const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+                        const uint32_t T = __ldg(t.thr + hd.y + idx);
+                        const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                        const uint32_t lo = (wb[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                        if (hi == (T >> 16) && lo > (T & 0xffffu)) xbits |= 1u << i;
+                    }
+                }
+                uint2 outw;  // spread decision bits into state bytes: bit i -> byte i
+                outw.x = ((xbits & 0xfu) * 0x00204081u) & 0x01010101u;
+                outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+                st_state8(my + (uint64_t)(uint32_t)hd.x * n_pad, outw);
+                if constexpr (HIST) {
+                    if (record && hist_half >= 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (i < nvalid) {
+                                uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + hd.w + ((xbits >> i) & 1u)) * g.n_pad + 8 * (size_t)unit + i;
+                                *h = (uint16_t)(*h + 1);
+                            }
+                    }
+                }
+                if (record) {  // chain.go:231-236: warp -> CTA (shared) -> one global atomic per variable per tile
+                    const unsigned s = __reduce_add_sync(amask, __popc(xbits & vmask));
+                    if (leader && s) atomicAdd(&s_ones[j], s);
+                }
+            };
+
+            // software pipeline: the next variable's neighbour words are in flight while this one
+            // computes (variables of one colour are never neighbours, so the early loads cannot see
+            // this tile's writes)
+            uint2 wA[NN], wB[NN];
+            load_nbrs(0, wA);
+            for (int jj = 0; jj < nv; jj += 2) {
+                if (jj + 1 < nv) load_nbrs(jj + 1, wB);
+                update(jj, wA);
+                if (jj + 1 < nv) {
+                    if (jj + 2 < nv) load_nbrs(jj + 2, wA);
+                    update(jj + 1, wB);
                 }
             }
         }
