@@ -68,6 +68,7 @@ struct gb_model {
     std::vector<void*> allocs;
     gb::DevModel dev{};
     int32_t* d_order = nullptr;
+    int32_t* d_colour_off = nullptr;
     gb::DevTab tab{};
     bool tab_built = false;
 
@@ -103,6 +104,7 @@ struct gb_model {
         dev.tab32 = up(tab32);
         dev.entry_var = up(entry_var);
         d_order = up(h.order);
+        d_colour_off = up(h.colour_off);
     }
     // table mode: evaluate every (variable, neighbour configuration) conditional once on the device
     void ensure_tab() {
@@ -300,11 +302,101 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
     }
 }
 
-void sweeps(gb_chains* c, int64_t n, int record, int hist_half) {
+// Shared-memory-resident path for small models: all sweeps of one group in ONE launch.
+template <typename Real, int MAXC, int CW>
+void launch_resident(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
+    // block size >= work items of the largest colour of one CTA (one item per thread keeps the
+    // per-colour critical path at a single update), capped at 256
+    const gb::HostModel& hm = g.model->h;
+    int max_col = 1;
+    for (size_t i = 0; i + 1 < hm.colour_off.size(); i++) max_col = std::max(max_col, hm.colour_off[i + 1] - hm.colour_off[i]);
+    const int64_t items = (int64_t)max_col * (CW == 0 ? ch : ch / 4);
+    int threads = 32;
+    while (threads < 256 && threads < items) threads *= 2;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const gb::HostModel& h = g.model->h;
+    gb::k_sweep_resident<Real, MAXC, CW><<<g.n_pad / ch, threads, smem, c->stream>>>(
+        g.model->dev, g.dev, g.model->d_order, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, ch, g.sweep, n_sweeps,
+        record, n_pre, n_half);
+    c->launches++;
+}
+
+// chains per CTA for the resident path, or 0 when the model does not qualify
+int resident_chains_per_cta(const gb_chains* c, const Group& g, size_t* smem_out) {
+    static int disabled = -1;
+    if (disabled < 0) disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
+    if (disabled || c->precision == GB_TABLE) return 0;
+    const gb::HostModel& h = g.model->h;
+    if (h.n_vars > 4096) return 0;
+    // few chains per CTA = many CTAs = better SM fill and latency hiding for these small models;
+    // grow the CTA's chain count only when that would exceed ~16 CTAs per SM
+    for (int ch : {8, 16, 32}) {
+        if (g.n_pad % ch) continue;
+        if (ch < 32 && g.n_pad / ch > 148 * 16) continue;
+        const size_t smem = (((size_t)h.n_vars * ch + 15) & ~(size_t)15) + (size_t)h.total_card * 4;
+        if (smem > 100 * 1024) continue;
+        *smem_out = smem;
+        return ch;
+    }
+    return 0;
+}
+
+// n_sweeps sweeps of one group with the AdvanceChain window schedule (n_half < 0: no histograms)
+void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
+    if (n_sweeps <= 0) return;
+    if (!(c->flags & GB_CHAINS_HISTORY)) n_half = -1;
+    size_t smem = 0;
+    const int ch = resident_chains_per_cta(c, g, &smem);
+    const gb::HostModel& h = g.model->h;
+    if (ch && n_sweeps < (1ll << 30)) {
+        const int mc = h.max_card;
+        const int32_t ns = (int32_t)n_sweeps;
+        if (c->precision == GB_F32) {
+            if (mc <= 2) launch_resident<float, 2, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 4) launch_resident<float, 4, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 8) launch_resident<float, 8, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 16) launch_resident<float, 16, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 32) launch_resident<float, 32, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else launch_resident<float, 64, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+        } else {
+            if (mc <= 2) launch_resident<double, 2, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 4) launch_resident<double, 4, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 8) launch_resident<double, 8, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 16) launch_resident<double, 16, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else if (mc <= 32) launch_resident<double, 32, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            else launch_resident<double, 64, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+        }
+        g.sweep += (uint32_t)n_sweeps;
+        if (record) {
+            c->total_samples += n_sweeps * (int64_t)h.order.size() * g.n_chains;
+            g.total_samples += n_sweeps * (int64_t)h.order.size() * g.n_chains;
+        }
+        return;
+    }
+    for (int64_t s = 0; s < n_sweeps; s++) {
+        const int hist_half = (n_half < 0 || s < n_pre) ? -1 : (s < (int64_t)n_pre + n_half ? 0 : 1);
+        sweep_group(c, g, record, hist_half);
+    }
+}
+
+void sweeps(gb_chains* c, int64_t n, int record) {
     CUDA_CHECK(cudaSetDevice(c->device));
-    for (int64_t s = 0; s < n; s++)
-        for (auto& g : c->groups) sweep_group(c, g, record, hist_half);
+    for (auto& g : c->groups) run_group(c, g, n, record, 0, -1);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// (*Chain).AdvanceChain for one group: cw + 1 recorded sweeps, the last 2 * (cw / 2) into the window
+void advance_group(gb_chains* c, Group& g, int32_t cw) {
+    const int32_t half = cw / 2;
+    if (c->flags & GB_CHAINS_HISTORY) {
+        if (half > 65535) throw gb::Err("convergence window too large for 16-bit half-window histograms");
+        CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, (size_t)2 * g.model->h.total_card * g.n_pad * sizeof(uint16_t), c->stream));
+    }
+    run_group(c, g, (int64_t)cw + 1, 1, cw + 1 - 2 * half, half);
 }
 
 // skip flags: bit0 = collapsed in any group, bit1 = fixed
@@ -711,7 +803,7 @@ int gb_chains_n_chains(const gb_chains* c, int64_t* out) {
 }
 
 int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record) {
-    GB_TRY sweeps(c, n_sweeps, record, -1);
+    GB_TRY sweeps(c, n_sweeps, record);
     GB_END
 }
 int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_out) {
@@ -722,7 +814,7 @@ int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_
         CUDA_CHECK(cudaEventCreate(&c->ev1));
     }
     CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
-    sweeps(c, n_sweeps, record, -1);
+    sweeps(c, n_sweeps, record);
     CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
     CUDA_CHECK(cudaEventSynchronize(c->ev1));
     CUDA_CHECK(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
@@ -753,7 +845,7 @@ int gb_chains_scan(gb_chains* c, int64_t n_steps, int record) {
     GB_END
 }
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps) {
-    GB_TRY sweeps(c, n_sweeps, 0, -1);
+    GB_TRY sweeps(c, n_sweeps, 0);
     GB_END
 }
 int gb_chains_advance(gb_chains* c, int32_t cw) {
@@ -761,17 +853,8 @@ int gb_chains_advance(gb_chains* c, int32_t cw) {
     if (cw < 0) throw gb::Err("Invalid convergence window");
     CUDA_CHECK(cudaSetDevice(c->device));
     c->last_cw = cw;
-    const int32_t half = cw / 2;
-    if (c->flags & GB_CHAINS_HISTORY) {
-        for (auto& g : c->groups)
-            CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, (size_t)2 * g.model->h.total_card * g.n_pad * sizeof(uint16_t), c->stream));
-        if (half > 65535) throw gb::Err("convergence window too large for 16-bit half-window histograms");
-        sweeps(c, (int64_t)cw + 1 - 2 * half, 1, -1);
-        sweeps(c, half, 1, 0);
-        sweeps(c, half, 1, 1);
-    } else {
-        sweeps(c, (int64_t)cw + 1, 1, -1);
-    }
+    for (auto& g : c->groups) advance_group(c, g, cw);
+    CUDA_CHECK(cudaGetLastError());
     GB_END
 }
 int gb_chains_total_samples(const gb_chains* c, int64_t* out) { *out = c->total_samples; return 0; }
@@ -784,8 +867,7 @@ static Group& group_at(gb_chains* c, int32_t group) {
 int gb_chains_group_sweep(gb_chains* c, int32_t group, int64_t n_sweeps, int record) {
     GB_TRY
     CUDA_CHECK(cudaSetDevice(c->device));
-    Group& g = group_at(c, group);
-    for (int64_t s = 0; s < n_sweeps; s++) sweep_group(c, g, record, -1);
+    run_group(c, group_at(c, group), n_sweeps, record, 0, -1);
     CUDA_CHECK(cudaGetLastError());
     GB_END
 }
@@ -793,18 +875,8 @@ int gb_chains_group_advance(gb_chains* c, int32_t group, int32_t cw) {
     GB_TRY
     if (cw < 0) throw gb::Err("Invalid convergence window");
     CUDA_CHECK(cudaSetDevice(c->device));
-    Group& g = group_at(c, group);
     c->last_cw = cw;
-    const int32_t half = cw / 2;
-    if (c->flags & GB_CHAINS_HISTORY) {
-        if (half > 65535) throw gb::Err("convergence window too large for 16-bit half-window histograms");
-        CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, (size_t)2 * g.model->h.total_card * g.n_pad * sizeof(uint16_t), c->stream));
-        for (int64_t s = 0; s < (int64_t)cw + 1 - 2 * half; s++) sweep_group(c, g, 1, -1);
-        for (int32_t s = 0; s < half; s++) sweep_group(c, g, 1, 0);
-        for (int32_t s = 0; s < half; s++) sweep_group(c, g, 1, 1);
-    } else {
-        for (int64_t s = 0; s < (int64_t)cw + 1; s++) sweep_group(c, g, 1, -1);
-    }
+    advance_group(c, group_at(c, group), cw);
     CUDA_CHECK(cudaGetLastError());
     GB_END
 }
@@ -919,7 +991,7 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
         first += (uint64_t)((chains_per_new_model + 7) / 8 * 8);
         // adaptive.go:145: NewChain(..., burnIn=2) — two single-variable steps; one un-recorded
         // sweep (>= 2 updates) is the sweep-granular equivalent
-        sweep_group(c, c->groups.back(), 0, -1);
+        run_group(c, c->groups.back(), 1, 0, 0, -1);
         if (chosen_out) chosen_out[n_done] = v;
         n_done++;
     }

@@ -133,9 +133,101 @@ __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real
 }
 
 // ------------------------------------------------------------------ K1/K2
+// One variable x 4 consecutive chains: gather the Markov-blanket factor rows, stabilise,
+// exponentiate, floor, inverse CDF.  `row` points at the first of the 4 chains in the row of
+// variable 0, `stride` is the row stride in bytes (global layout: n_pad; shared-memory-resident
+// layout: chains per CTA).  CW = chains whose weight vectors are held in registers at once.
+template <typename Real, int MAXC, int CW>
+__device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
+                                                const uint32_t stride, const int v, const int card, const uint32_t chain0,
+                                                const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
+                                                int (&x)[4]) {
+    const int32_t* __restrict__ prog = m.prog + __ldg(m.prog_off + v);
+    const int nf = __ldg(prog);
+    Real u[4];
+    if constexpr (std::is_same<Real, double>::value) {
+        const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 1, kTagDraw53, seed_lo, seed_hi);
+        const Philox4 b = philox4x32_10((uint32_t)v, sweep, (chain0 >> 1) + 1u, kTagDraw53, seed_lo, seed_hi);
+        u[0] = u53(a.x, a.y); u[1] = u53(a.z, a.w); u[2] = u53(b.x, b.y); u[3] = u53(b.z, b.w);
+    } else {
+        const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 2, kTagDraw24, seed_lo, seed_hi);
+        u[0] = (float)(a.x >> 8) * (1.0f / 16777216.0f);
+        u[1] = (float)(a.y >> 8) * (1.0f / 16777216.0f);
+        u[2] = (float)(a.z >> 8) * (1.0f / 16777216.0f);
+        u[3] = (float)(a.w >> 8) * (1.0f / 16777216.0f);
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; cb += CW) {
+        Real w[CW][MAXC];
+#pragma unroll
+        for (int ci = 0; ci < CW; ci++)
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) w[ci][k] = 0;
+        const int32_t* __restrict__ p = prog + 1;
+        for (int f = 0; f < nf; f++) {
+            const int tab_off = __ldg(p), sv = __ldg(p + 1), no = __ldg(p + 2);
+            p += 3;
+            int b[CW];
+#pragma unroll
+            for (int ci = 0; ci < CW; ci++) b[ci] = tab_off;
+            for (int o = 0; o < no; o++) {
+                const int ov = __ldg(p), os = __ldg(p + 1);
+                p += 2;
+                const uint32_t s4 = *reinterpret_cast<const uint32_t*>(row + (size_t)ov * stride);
+#pragma unroll
+                for (int ci = 0; ci < CW; ci++) b[ci] += (int)((s4 >> (8 * (cb + ci))) & 0xffu) * os;
+            }
+#pragma unroll
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) {
+#pragma unroll
+                    for (int ci = 0; ci < CW; ci++) w[ci][k] += __ldg(tab + b[ci] + k * sv);
+                }
+        }
+#pragma unroll
+        for (int ci = 0; ci < CW; ci++) {
+            stabilise_exp_floor<Real, MAXC>(w[ci], card);
+            x[cb + ci] = inverse_cdf<Real, MAXC>(w[ci], card, u[cb + ci]);
+        }
+    }
+}
+
+// One variable x ONE chain (same arithmetic and draws as lse_update_quad for that chain): used by the
+// resident kernel for high-cardinality models, where one thread per chain gives 4x the parallelism
+// and a quarter of the registers.  `cell` points at this chain's byte in the row of variable 0.
+template <typename Real, int MAXC>
+__device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
+                                              const uint32_t stride, const int v, const int card, const uint32_t chain,
+                                              const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+    const int32_t* __restrict__ p = m.prog + __ldg(m.prog_off + v);
+    const int nf = __ldg(p++);
+    Real u;
+    if constexpr (std::is_same<Real, double>::value) {
+        const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain >> 1, kTagDraw53, seed_lo, seed_hi);
+        u = (chain & 1u) ? u53(a.z, a.w) : u53(a.x, a.y);
+    } else {
+        const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain >> 2, kTagDraw24, seed_lo, seed_hi);
+        const uint32_t wsel = (chain & 2u) ? ((chain & 1u) ? a.w : a.z) : ((chain & 1u) ? a.y : a.x);
+        u = (float)(wsel >> 8) * (1.0f / 16777216.0f);
+    }
+    Real w[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) w[k] = 0;
+    for (int f = 0; f < nf; f++) {
+        const int tab_off = __ldg(p), sv = __ldg(p + 1), no = __ldg(p + 2);
+        p += 3;
+        int b = tab_off;
+        for (int o = 0; o < no; o++, p += 2) b += (int)cell[(size_t)__ldg(p) * stride] * __ldg(p + 1);
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < card) w[k] += __ldg(tab + b + k * sv);
+    }
+    stabilise_exp_floor<Real, MAXC>(w, card);
+    return inverse_cdf<Real, MAXC>(w, card, u);
+}
+
 // One launch = one colour of one group.  Work item = (variable of the colour, quad of 4 chains);
-// consecutive threads take consecutive quads of the same variable.  CW = chains whose weight
-// vectors are held in registers at once (4 for small cardinalities, 1 for wide ones).
+// consecutive threads take consecutive quads of the same variable.
 template <typename Real, int MAXC, int CW>
 __global__ void __launch_bounds__(256)
 k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ vars, const int32_t n_vars_c,
@@ -153,59 +245,10 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
         const int32_t q = (int32_t)(item - (int64_t)j * n_quads);
         const int32_t v = __ldg(vars + j);
         const int32_t card = __ldg(m.card + v);
-        const int32_t* __restrict__ prog = m.prog + __ldg(m.prog_off + v);
-        const int nf = __ldg(prog);
-
-        // uniforms for the 4 chains of the quad
         const uint32_t chain0 = (uint32_t)(g.first_chain + 4u * (uint32_t)q);
-        Real u[4];
-        if constexpr (std::is_same<Real, double>::value) {
-            const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 1, kTagDraw53, g.seed_lo, g.seed_hi);
-            const Philox4 b = philox4x32_10((uint32_t)v, sweep, (chain0 >> 1) + 1u, kTagDraw53, g.seed_lo, g.seed_hi);
-            u[0] = u53(a.x, a.y); u[1] = u53(a.z, a.w); u[2] = u53(b.x, b.y); u[3] = u53(b.z, b.w);
-        } else {
-            const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain0 >> 2, kTagDraw24, g.seed_lo, g.seed_hi);
-            u[0] = (float)(a.x >> 8) * (1.0f / 16777216.0f);
-            u[1] = (float)(a.y >> 8) * (1.0f / 16777216.0f);
-            u[2] = (float)(a.z >> 8) * (1.0f / 16777216.0f);
-            u[3] = (float)(a.w >> 8) * (1.0f / 16777216.0f);
-        }
-
         int x[4];
-#pragma unroll
-        for (int cb = 0; cb < 4; cb += CW) {
-            Real w[CW][MAXC];
-#pragma unroll
-            for (int ci = 0; ci < CW; ci++)
-#pragma unroll
-                for (int k = 0; k < MAXC; k++) w[ci][k] = 0;
-            const int32_t* __restrict__ p = prog + 1;
-            for (int f = 0; f < nf; f++) {
-                const int tab_off = __ldg(p), sv = __ldg(p + 1), no = __ldg(p + 2);
-                p += 3;
-                int b[CW];
-#pragma unroll
-                for (int ci = 0; ci < CW; ci++) b[ci] = tab_off;
-                for (int o = 0; o < no; o++) {
-                    const int ov = __ldg(p), os = __ldg(p + 1);
-                    p += 2;
-                    const uint32_t s4 = *reinterpret_cast<const uint32_t*>(g.state + (size_t)ov * g.n_pad + 4 * q);
-#pragma unroll
-                    for (int ci = 0; ci < CW; ci++) b[ci] += (int)((s4 >> (8 * (cb + ci))) & 0xffu) * os;
-                }
-#pragma unroll
-                for (int k = 0; k < MAXC; k++)
-                    if (k < card) {
-#pragma unroll
-                        for (int ci = 0; ci < CW; ci++) w[ci][k] += __ldg(tab + b[ci] + k * sv);
-                    }
-            }
-#pragma unroll
-            for (int ci = 0; ci < CW; ci++) {
-                stabilise_exp_floor<Real, MAXC>(w[ci], card);
-                x[cb + ci] = inverse_cdf<Real, MAXC>(w[ci], card, u[cb + ci]);
-            }
-        }
+        lse_update_quad<Real, MAXC, CW>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo,
+                                        g.seed_hi, x);
         const uint32_t packed = (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
         *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + 4 * q) = packed;
 
@@ -239,6 +282,102 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ K1/K2 resident
+// Small models (the bundled UAI problems): the whole state of CH chains fits in shared memory, so
+// ONE launch runs many sweeps — every colour of every sweep — with __syncthreads() between
+// colours instead of one launch per colour (which is launch- and latency-bound for 60..461
+// variables).  A CTA owns CH consecutive chains; marginal counts accumulate in shared memory and
+// are flushed once per launch.  Same arithmetic and Philox stream as k_sweep_colour: the two
+// paths produce identical trajectories.  Window schedule of (*Chain).AdvanceChain: sweeps
+// [0, n_pre) record only, then n_half sweeps into the first and n_half into the second
+// half-window histogram (n_half < 0: no histograms).
+template <typename Real, int MAXC, int CW>  // CW = 0: one thread per chain (lse_update_one)
+__global__ void __launch_bounds__(256)
+k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
+                 const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
+                 const int32_t n_half) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_state = smem;                                                                  // [n_vars][CH]
+    unsigned int* s_counts = reinterpret_cast<unsigned int*>(smem + (((size_t)m.n_vars * ch_per_cta + 15) & ~(size_t)15));  // [total_card]
+    const Real* __restrict__ tab = tables_of<Real>(m);
+    const int CH = ch_per_cta;
+    const int cta_chain = blockIdx.x * CH;  // local index of this CTA's first chain
+    const int n_quads = CH >> 2;
+    // load state (CH bytes per variable) and clear the counts
+    for (int i = threadIdx.x; i < m.n_vars * n_quads; i += blockDim.x) {
+        const int v = i / n_quads, q = i - v * n_quads;
+        *reinterpret_cast<uint32_t*>(s_state + (size_t)v * CH + 4 * q) =
+            *reinterpret_cast<const uint32_t*>(g.state + (size_t)v * g.n_pad + cta_chain + 4 * q);
+    }
+    for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
+    __syncthreads();
+    for (int s = 0; s < n_sweeps; s++) {
+        const uint32_t sweep = sweep0 + (uint32_t)s;
+        const int hist_half = (n_half < 0 || s < n_pre) ? -1 : (s < n_pre + n_half ? 0 : 1);
+        for (int col = 0; col < n_colours; col++) {
+            const int c0 = __ldg(colour_off + col), nvc = __ldg(colour_off + col + 1) - c0;
+            if constexpr (CW == 0) {
+                for (int item = threadIdx.x; item < nvc * CH; item += blockDim.x) {
+                    const int j = item / CH, cc = item - j * CH;
+                    const int v = __ldg(order + c0 + j);
+                    const int card = __ldg(m.card + v);
+                    const int lchain = cta_chain + cc;
+                    const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)lchain);
+                    const int x = lse_update_one<Real, MAXC>(m, tab, s_state + cc, (uint32_t)CH, v, card, chain, sweep, g.seed_lo, g.seed_hi);
+                    s_state[(size_t)v * CH + cc] = (uint8_t)x;
+                    if (record && lchain < g.n_chains) {
+                        const int32_t coff = __ldg(m.card_off + v);
+                        atomicAdd(&s_counts[coff + x], 1u);
+                        if (hist_half >= 0 && g.hist) {
+                            uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + x) * g.n_pad + lchain;
+                            *h = (uint16_t)(*h + 1);
+                        }
+                    }
+                }
+            } else {
+                for (int item = threadIdx.x; item < nvc * n_quads; item += blockDim.x) {
+                    const int j = item / n_quads, q = item - j * n_quads;
+                    const int v = __ldg(order + c0 + j);
+                    const int card = __ldg(m.card + v);
+                    const int lchain = cta_chain + 4 * q;  // local chain index of the quad
+                    const uint32_t chain0 = (uint32_t)(g.first_chain + (uint64_t)lchain);
+                    int x[4];
+                    lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW)>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep,
+                                                                    g.seed_lo, g.seed_hi, x);
+                    *reinterpret_cast<uint32_t*>(s_state + (size_t)v * CH + 4 * q) =
+                        (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
+                    if (record) {
+                        const int nvalid = max(0, min(4, g.n_chains - lchain));
+                        const int32_t coff = __ldg(m.card_off + v);
+#pragma unroll
+                        for (int ci = 0; ci < 4; ci++)
+                            if (ci < nvalid) atomicAdd(&s_counts[coff + x[ci]], 1u);
+                        if (hist_half >= 0 && g.hist) {
+#pragma unroll
+                            for (int ci = 0; ci < 4; ci++)
+                                if (ci < nvalid) {
+                                    uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + x[ci]) * g.n_pad + lchain + ci;
+                                    *h = (uint16_t)(*h + 1);
+                                }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // write the state back and flush the counts
+    for (int i = threadIdx.x; i < m.n_vars * n_quads; i += blockDim.x) {
+        const int v = i / n_quads, q = i - v * n_quads;
+        *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + cta_chain + 4 * q) =
+            *reinterpret_cast<const uint32_t*>(s_state + (size_t)v * CH + 4 * q);
+    }
+    if (record)
+        for (int i = threadIdx.x; i < m.total_card; i += blockDim.x)
+            if (s_counts[i]) atomicAdd(g.counts + i, (unsigned long long)s_counts[i]);
 }
 
 // ------------------------------------------------------------------ K1-table
