@@ -486,9 +486,13 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int chunk = (int)(tile / n_vb);
         const int vb = (int)(tile - (int64_t)chunk * n_vb);
-        const int unit = chunk * 256 + threadIdx.x;
-        const bool active = unit < units;
-        const int nvalid = active ? max(0, min(8, g.n_chains - 8 * unit)) : 0;
+        // A warp runs if ANY of its lanes owns chains; lanes past the end of a ragged last chunk redo the
+        // last unit's work with their store and counts masked off, so warp-wide shuffles always see 32 lanes.
+        const int unit_raw = chunk * 256 + threadIdx.x;
+        const bool lane_valid = unit_raw < units;
+        const bool active = chunk * 256 + (int)(threadIdx.x & ~31u) < units;
+        const int unit = min(unit_raw, units - 1);
+        const int nvalid = lane_valid ? max(0, min(8, g.n_chains - 8 * unit)) : 0;
         const uint32_t vmask = (nvalid >= 8) ? 0xffu : ((1u << nvalid) - 1u);
         const uint32_t chain_blk = (uint32_t)((g.first_chain >> 3) + (uint64_t)unit);
         const int nv = min(VB, n_vars_c - vb * VB);
@@ -506,8 +510,8 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
         if (active) {
             const int thr_a = s_rec[0].y;
             const uint64_t my = reinterpret_cast<uint64_t>(g.state) + 8ull * (uint64_t)unit;
-            const unsigned amask = __activemask();  // the lanes of this warp that own chains (all, except in a ragged last chunk)
-            const bool leader = (threadIdx.x & 31) == (__ffs(amask) - 1);
+            constexpr unsigned amask = 0xffffffffu;
+            const bool leader = (threadIdx.x & 31) == 0;
 
             auto load_nbrs = [&](const int j, uint2(&w)[NN]) {
                 const int4 na = s_rec[j * 5 + 1];
@@ -538,10 +542,16 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
                 const int toff = hd.y - thr_a;
                 uint32_t xbits = 0, tie = 1;
+                // NN == 4: at most 16 configurations, so the variable's thresholds live one per lane and
+                // are fetched with a warp shuffle (no address arithmetic); NN == 8: shared-memory lookup
+                uint32_t my_th = 0;
+                if constexpr (NN == 4) my_th = s_thr[toff + (threadIdx.x & 15)];
 #pragma unroll
                 for (int i = 7; i >= 0; i--) {
                     const uint32_t idx = __byte_perm(i < 4 ? cfg_lo : cfg_hi, 0, 0x4440 + (i & 3));
-                    const uint32_t th = s_thr[toff + idx];
+                    uint32_t th;
+                    if constexpr (NN == 4) th = __shfl_sync(amask, my_th, idx);
+                    else th = s_thr[toff + idx];
                     const uint32_t hi = (i & 1) ? (wa[i >> 1] >> 16) : __byte_perm(wa[i >> 1], 0, 0x4410);
                     const uint32_t d = th - hi;            // sign bit set <=> hi > th  (both < 2^16)
                     xbits = __funnelshift_l(d, xbits, 1);  // xbits = (xbits << 1) | (hi > th)
@@ -562,7 +572,7 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
                 uint2 outw;  // spread decision bits into state bytes: bit i -> byte i
                 outw.x = ((xbits & 0xfu) * 0x00204081u) & 0x01010101u;
                 outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-                st_state8(my + (uint64_t)(uint32_t)hd.x * n_pad, outw);
+                if (lane_valid) st_state8(my + (uint64_t)(uint32_t)hd.x * n_pad, outw);
                 if constexpr (HIST) {
                     if (record && hist_half >= 0) {
 #pragma unroll
