@@ -229,10 +229,14 @@ def run_native(args):
                 "traffic": None, "peak_source": peak_src, "kernel": kernel,
                 "algorithmic_bytes_per_update": GATHER_BYTES_PER_UPDATE, "updates_per_launch": updates_per_launch,
                 "launch_ms": launch_ms}
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
+    # bytes per update measured at the capture's chain count, scaled to this launch's update count)
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and args.precision == "table":
         try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            t = json.load(open(tr))
+            roofline["traffic"] = t["dram_bytes_per_update"] * updates_per_launch
+            roofline["traffic_source"] = t["source"]
         except Exception:
             pass
 

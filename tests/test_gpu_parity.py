@@ -600,3 +600,24 @@ def test_cli_errors(res):
     args = cli.build_parser().parse_args(["sample", "-m", res("one.uai"), "-p"])
     with pytest.raises(gb.GrampleError, match="trace file"):  # cmd/root.go:313-316
         cli.sample(args)
+
+
+def test_baseline_config_sizes_match_oracle_on_a_shard(res):
+    """BASELINE configs[1] / [2] chain counts (4096 / 8192 chains): because the Philox stream is keyed
+    by the global chain id, any 8 of those chains can be replayed by the oracle and must match bit
+    for bit — a full-size parity check at oracle cost O(8 chains)."""
+    for name, evid, n_chains, lo in (("Promedus_11.uai", True, 4096, 2048), ("Pedigree_11.uai", True, 8192, 8000)):
+        dm, om = load_pair(res, name, evid)
+        order, _ = dm.schedule()
+        seed = 99
+        ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.F64, device=0)
+        st0 = ch.get_state(0, n_chains)
+        ch.burnin(3)
+        ch.sweep(4)
+        st1 = ch.get_state(0, n_chains)
+        samp = oracle.Sampler(oracle.Generator(1), om)
+        ost, _ = samp.sweep_run(order, seed, lo, st0[lo:lo + 8], 0, 7, bits=53, record=False)
+        assert np.array_equal(ost, st1[lo:lo + 8]), name
+        counts = ch.group_counts(0)
+        per_var = np.add.reduceat(counts, np.concatenate([[0], np.cumsum(dm.cards)[:-1]]))
+        assert np.array_equal(per_var, np.where(dm.fixed < 0, 4 * n_chains, 0))
