@@ -240,9 +240,13 @@ class Chains:
         check(lib().gb_chains_total_samples(self.h, C.byref(v)))
         return v.value
 
-    def merged_marginals(self):
-        out = np.zeros(self.base.total_card)
-        col = np.zeros(self.base.n_vars, dtype=np.int32)
+    def _merge_buffers(self, out):
+        if out is not None:  # caller-owned (float64 [sum(card)], int32 [n_vars]) buffers, reused across intervals
+            return out
+        return np.empty(self.base.total_card), np.empty(self.base.n_vars, dtype=np.int32)
+
+    def merged_marginals(self, out=None):
+        out, col = self._merge_buffers(out)
         check(lib().gb_chains_merged_marginals(self.h, _ptr(out, _f64p), _ptr(col, _i32p)))
         return out, col
 
@@ -252,9 +256,8 @@ class Chains:
         check(lib().gb_chains_merge_partial_dev(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def merge_finalize(self):
-        out = np.zeros(self.base.total_card)
-        col = np.zeros(self.base.n_vars, dtype=np.int32)
+    def merge_finalize(self, out=None):
+        out, col = self._merge_buffers(out)
         check(lib().gb_chains_merge_finalize(self.h, _ptr(out, _f64p), _ptr(col, _i32p)))
         return out, col
 

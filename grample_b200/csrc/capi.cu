@@ -166,6 +166,8 @@ struct gb_chains {
     std::vector<int> col_first_group;  // first group (list order) in which a variable is collapsed
     std::vector<int> col_vars;         // indices of the collapsed-in-any variables
     bool skip_uploaded = false;
+    std::vector<uint8_t> skip_bits;    // host copy of d_skip
+    std::vector<int32_t> col_any32;    // col_any widened for the ABI's int32 output
     double* h_merge = nullptr;         // pinned staging buffer for the device -> host copy
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -240,31 +242,40 @@ void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int
     c->launches++;
 }
 
-template <int VB, int NN, bool HIST>
+template <int VB, int NN, bool HIST, int PF>
 void launch_tab_variant(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
     static int resident = 0;  // CTAs that fit the device at once (persistent tile loop)
+    constexpr size_t ring = (size_t)(PF > 0 ? (PF + 1) * NN * 256 * 8 : 0);  // cp.async prefetch ring
     if (!resident) {
         int per_sm = 0, sms = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB, NN, HIST>, 256, 0));
+        if (ring > 0)
+            CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_tab<VB, NN, HIST, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_tab<VB, NN, HIST, PF>, 256, ring));
         resident = std::max(1, per_sm * sms);
     }
     const gb::HostModel& h = g.model->h;
     const int64_t tiles = (int64_t)((g.n_pad / 8 + 255) / 256) * ((n + VB - 1) / VB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
-    gb::k_sweep_tab<VB, NN, HIST><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, h.colour_off[col], n,
-                                                              g.sweep, record, hist_half);
+    gb::k_sweep_tab<VB, NN, HIST, PF><<<grid, 256, ring, c->stream>>>(g.model->dev, g.model->tab, g.dev, h.colour_off[col], n,
+                                                                     g.sweep, record, hist_half);
     c->launches++;
 }
 
 void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
     const bool hist = g.d_hist != nullptr && hist_half >= 0;
+    // GB_TAB_PF=0 selects the register-prefetch variant (kept for A/B measurements; default: cp.async ring, depth 3)
+    static const bool reg_prefetch = std::getenv("GB_TAB_PF") && std::atoi(std::getenv("GB_TAB_PF")) == 0;
+    constexpr int VB = gb::kTabTile;
     if (g.model->h.tab_max_nbr > 4) {
-        if (hist) launch_tab_variant<32, 8, true>(c, g, col, n, record, hist_half);
-        else launch_tab_variant<32, 8, false>(c, g, col, n, record, hist_half);
+        if (hist) launch_tab_variant<32, 8, true, 3>(c, g, col, n, record, hist_half);
+        else launch_tab_variant<32, 8, false, 3>(c, g, col, n, record, hist_half);
+    } else if (hist) {
+        launch_tab_variant<VB, 4, true, 3>(c, g, col, n, record, hist_half);
+    } else if (reg_prefetch) {
+        launch_tab_variant<VB, 4, false, 0>(c, g, col, n, record, hist_half);
     } else {
-        if (hist) launch_tab_variant<32, 4, true>(c, g, col, n, record, hist_half);
-        else launch_tab_variant<32, 4, false>(c, g, col, n, record, hist_half);
+        launch_tab_variant<VB, 4, false, 3>(c, g, col, n, record, hist_half);
     }
 }
 
@@ -429,13 +440,26 @@ void refresh_collapsed_cache(gb_chains* c) {
         if (c->col_any[v]) c->col_vars.push_back(v);
 }
 
+// d_skip[v]: bit0 = collapsed in any group (skipped by the merge), bit1 = fixed (skipped, with
+// bit0, by the convergence pass); uploaded once per change of the group list
+void upload_skip(gb_chains* c) {
+    refresh_collapsed_cache(c);
+    if (c->skip_uploaded) return;
+    ensure_scratch(c);
+    const gb::HostModel& h = c->base();
+    c->skip_bits.resize(h.n_vars);
+    for (int v = 0; v < h.n_vars; v++) c->skip_bits[v] = (uint8_t)(c->col_any[v] | (h.fixed[v] >= 0 ? 2 : 0));
+    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, c->skip_bits.data(), c->skip_bits.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->col_any32.assign(c->col_any.begin(), c->col_any.end());
+    c->skip_uploaded = true;
+}
+
 void merge_partial(gb_chains* c) {
     CUDA_CHECK(cudaSetDevice(c->device));
     ensure_scratch(c);
     const gb::HostModel& h = c->base();
-    refresh_collapsed_cache(c);
-    // d_skip is shared with the convergence path (which also marks fixed variables): re-upload
-    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, c->col_any.data(), c->col_any.size(), cudaMemcpyHostToDevice, c->stream));
+    upload_skip(c);
     CUDA_CHECK(cudaMemsetAsync(c->d_merge, 0, (size_t)h.total_card * sizeof(double), c->stream));
     for (auto& g : c->groups)
         gb::k_merge_partial<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(g.model->dev, g.d_counts,
@@ -453,8 +477,10 @@ void merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     std::memcpy(out, c->h_merge, bytes);
     refresh_collapsed_cache(c);
-    if (collapsed_out)
-        for (int v = 0; v < h.n_vars; v++) collapsed_out[v] = c->col_any[v];
+    if (collapsed_out) {
+        upload_skip(c);
+        std::memcpy(collapsed_out, c->col_any32.data(), (size_t)h.n_vars * sizeof(int32_t));
+    }
     for (int v : c->col_vars) {
         const auto& m = c->groups[c->col_first_group[v]].model->h.coll_marg[v];  // chain.go:113-129: first chain found
         for (int k = 0; k < h.card[v]; k++) out[h.card_off[v] + k] = m[k];
@@ -474,11 +500,8 @@ void convergence_partial(gb_chains* c, int measure, const double* merged) {
         merge_finalize(c, tmp.data(), nullptr);
         merged = tmp.data();
     }
-    std::vector<uint8_t> skip = collapsed_any(c);
-    for (int v = 0; v < h.n_vars; v++)
-        if (h.fixed[v] >= 0) skip[v] = 1;
+    upload_skip(c);
     CUDA_CHECK(cudaMemcpyAsync(c->d_merged_in, merged, (size_t)h.total_card * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(c->d_skip, skip.data(), skip.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->d_wb, 0, (size_t)2 * h.n_vars * sizeof(double), c->stream));
     for (auto& g : c->groups) {
         const int64_t items = (int64_t)h.n_vars * g.n_chains;

@@ -466,17 +466,37 @@ __device__ __forceinline__ void st_state8(const uint64_t addr, const uint2 v) {
     asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// Asynchronous 8-byte global -> shared copies (LDGSTS): completion is tracked per thread by commit
+// groups, not by a register scoreboard, so several variables' neighbour words can be in flight at once.
+__device__ __forceinline__ void cp_async8(const uint32_t smem_addr, const uint64_t gaddr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gaddr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint2 lds_state8(const uint32_t smem_addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr) : "memory");
+    return v;
+}
+
 // NN = neighbour slots read per variable (4 or 8); records pad unused slots with the variable
 // itself at stride 0, so the loads are unconditional and branch-free.  HIST = keep the per-chain
 // half-window histograms (chain.go:237).  All shared-memory accesses go through the array symbols
 // (not through generic pointers) so they compile to LDS with immediate bases.
-template <int VB, int NN, bool HIST>
+// PF = prefetch depth in variables.  PF == 0: the next variable's words are loaded into a second
+// register set (LDG; ptxas tracks both sets on one scoreboard, so every second variable waits for
+// loads issued a few instructions earlier).  PF > 0: each thread copies the words of variable j + PF
+// into its own slots of a shared-memory ring of PF + 1 stages with cp.async while variable j
+// computes; the ring is private to the thread (no barrier), dynamic shared memory =
+// (PF + 1) * NN * 256 * 8 bytes.
+template <int VB, int NN, bool HIST, int PF>
 __global__ void __launch_bounds__(256)
 k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_begin, const int32_t n_vars_c,
             const uint32_t sweep, const int record, const int hist_half) {
     __shared__ int4 s_rec[VB * (kTabRec / 4)];
-    __shared__ unsigned int s_ones[VB + 4];
-    __shared__ uint16_t s_thr[VB * 256];
+    __shared__ unsigned int s_cnt[VB / 2];  // ones per variable: word 4*(j/8) + j%4 holds variables j (low 16 bits) and j+4 (high)
+    __shared__ uint16_t s_thr[VB * (NN == 4 ? 16 : 256)];  // <= 2^NN configurations per variable
     const int units = g.n_pad >> 3;
     const int chunks = (units + 255) >> 8;
     const int n_vb = (n_vars_c + VB - 1) / VB;
@@ -504,7 +524,7 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
             const int ta = __ldg(src + 1);
             const int tb = (j0 + nv < t.n_order) ? __ldg(t.trec + (size_t)(j0 + nv) * kTabRec + 1) : t.n_thr;
             for (int i = threadIdx.x; i < tb - ta; i += 256) s_thr[i] = (uint16_t)(__ldg(t.thr + ta + i) >> 16);
-            if (threadIdx.x < VB) s_ones[threadIdx.x] = 0;
+            if (threadIdx.x < VB / 2) s_cnt[threadIdx.x] = 0;
         }
         __syncthreads();
         if (active) {
@@ -514,21 +534,22 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
             const bool leader = (threadIdx.x & 31) == 0;
 
             auto load_nbrs = [&](const int j, uint2(&w)[NN]) {
+                const uint64_t base = my;
                 const int4 na = s_rec[j * 5 + 1];
-                w[0] = ld_state8(my + (uint64_t)(uint32_t)na.x * n_pad);
-                w[1] = ld_state8(my + (uint64_t)(uint32_t)na.y * n_pad);
-                w[2] = ld_state8(my + (uint64_t)(uint32_t)na.z * n_pad);
-                w[3] = ld_state8(my + (uint64_t)(uint32_t)na.w * n_pad);
+                w[0] = ld_state8(base + (uint64_t)(uint32_t)na.x * n_pad);
+                w[1] = ld_state8(base + (uint64_t)(uint32_t)na.y * n_pad);
+                w[2] = ld_state8(base + (uint64_t)(uint32_t)na.z * n_pad);
+                w[3] = ld_state8(base + (uint64_t)(uint32_t)na.w * n_pad);
                 if constexpr (NN == 8) {
                     const int4 nb = s_rec[j * 5 + 2];
-                    w[4] = ld_state8(my + (uint64_t)(uint32_t)nb.x * n_pad);
-                    w[5] = ld_state8(my + (uint64_t)(uint32_t)nb.y * n_pad);
-                    w[6] = ld_state8(my + (uint64_t)(uint32_t)nb.z * n_pad);
-                    w[7] = ld_state8(my + (uint64_t)(uint32_t)nb.w * n_pad);
+                    w[4] = ld_state8(base + (uint64_t)(uint32_t)nb.x * n_pad);
+                    w[5] = ld_state8(base + (uint64_t)(uint32_t)nb.y * n_pad);
+                    w[6] = ld_state8(base + (uint64_t)(uint32_t)nb.z * n_pad);
+                    w[7] = ld_state8(base + (uint64_t)(uint32_t)nb.w * n_pad);
                 }
             };
             // one variable x 8 chains: configuration indices, one Philox call, threshold compare, store
-            auto update = [&](const int j, const uint2(&w)[NN]) {
+            auto update = [&](const int j, const uint2(&w)[NN], uint32_t& acc, const int slot) {
                 const int4 hd = s_rec[j * 5];  // v, thr_off, n_nbr, card_off
                 const int4 sa = s_rec[j * 5 + 3];
                 uint32_t cfg_lo = w[0].x * (uint32_t)sa.x + w[1].x * (uint32_t)sa.y + w[2].x * (uint32_t)sa.z + w[3].x * (uint32_t)sa.w;
@@ -541,7 +562,7 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
                 const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, seed_lo, seed_hi);
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
                 const int toff = hd.y - thr_a;
-                uint32_t xbits = 0, tie = 1;
+                uint32_t xbits = 0, dd[8];
                 // NN == 4: at most 16 configurations, so the variable's thresholds live one per lane and
                 // are fetched with a warp shuffle (no address arithmetic); NN == 8: shared-memory lookup
                 uint32_t my_th = 0;
@@ -555,8 +576,10 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
                     const uint32_t hi = (i & 1) ? (wa[i >> 1] >> 16) : __byte_perm(wa[i >> 1], 0, 0x4410);
                     const uint32_t d = th - hi;            // sign bit set <=> hi > th  (both < 2^16)
                     xbits = __funnelshift_l(d, xbits, 1);  // xbits = (xbits << 1) | (hi > th)
-                    tie *= d;                              // zero if any high half ties (rare false positives are harmless)
+                    dd[i] = d;
                 }
+                // a high half ties with its threshold <=> some d is zero <=> the unsigned minimum is zero
+                const uint32_t tie = __vimin3_u32(__vimin3_u32(dd[0], dd[1], dd[2]), __vimin3_u32(dd[3], dd[4], dd[5]), min(dd[6], dd[7]));
                 if (tie == 0) {  // resolve ties with the low halves: draw > threshold <=> lo16 > (T & 0xffff)
                     const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, seed_lo, seed_hi);
                     const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
@@ -583,30 +606,89 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
                             }
                     }
                 }
-                if (record) {  // chain.go:231-236: warp -> CTA (shared) -> one global atomic per variable per tile
-                    const unsigned s = __reduce_add_sync(amask, __popc(xbits & vmask));
-                    if (leader && s) atomicAdd(&s_ones[j], s);
-                }
+                // chain.go:231-236: this thread's ones of the variable go into nibble `slot` of the group accumulator
+                acc += (uint32_t)__popc(xbits & vmask) << (4 * slot);
             };
 
             // software pipeline: the next variable's neighbour words are in flight while this one
             // computes (variables of one colour are never neighbours, so the early loads cannot see
             // this tile's writes)
-            uint2 wA[NN], wB[NN];
-            load_nbrs(0, wA);
-            for (int jj = 0; jj < nv; jj += 2) {
-                if (jj + 1 < nv) load_nbrs(jj + 1, wB);
-                update(jj, wA);
-                if (jj + 1 < nv) {
-                    if (jj + 2 < nv) load_nbrs(jj + 2, wA);
-                    update(jj + 1, wB);
+            // Variables are taken in groups of 8 so that the nibble slot is a compile-time constant;
+            // per group the 8 nibbles are reduced over the warp as four words of two 16-bit fields
+            // (<= 256 per field) and added to the CTA's shared counters by the warp leader.
+            [[maybe_unused]] uint2 wA[NN], wB[NN];
+            [[maybe_unused]] uint32_t pf_base = 0;
+            if constexpr (PF > 0) {
+                static_assert(8 % (PF + 1) == 0, "ring stages must divide the unroll factor");
+                extern __shared__ __align__(16) uint8_t s_ring[];  // [PF + 1][NN][256] uint2
+                pf_base = (uint32_t)__cvta_generic_to_shared(s_ring) + 8u * threadIdx.x;
+            }
+            [[maybe_unused]] auto issue = [&](const int j, const int stage) {
+                const int4 na = s_rec[j * 5 + 1];
+                cp_async8(pf_base + (stage * NN + 0) * 2048, my + (uint64_t)(uint32_t)na.x * n_pad);
+                cp_async8(pf_base + (stage * NN + 1) * 2048, my + (uint64_t)(uint32_t)na.y * n_pad);
+                cp_async8(pf_base + (stage * NN + 2) * 2048, my + (uint64_t)(uint32_t)na.z * n_pad);
+                cp_async8(pf_base + (stage * NN + 3) * 2048, my + (uint64_t)(uint32_t)na.w * n_pad);
+                if constexpr (NN == 8) {
+                    const int4 nb = s_rec[j * 5 + 2];
+                    cp_async8(pf_base + (stage * NN + 4) * 2048, my + (uint64_t)(uint32_t)nb.x * n_pad);
+                    cp_async8(pf_base + (stage * NN + 5) * 2048, my + (uint64_t)(uint32_t)nb.y * n_pad);
+                    cp_async8(pf_base + (stage * NN + 6) * 2048, my + (uint64_t)(uint32_t)nb.z * n_pad);
+                    cp_async8(pf_base + (stage * NN + 7) * 2048, my + (uint64_t)(uint32_t)nb.w * n_pad);
+                }
+            };
+            if constexpr (PF > 0) {
+#pragma unroll
+                for (int d = 0; d < PF; d++) {
+                    if (d < nv) issue(d, d);
+                    cp_async_commit();
+                }
+            } else {
+                load_nbrs(0, wA);
+            }
+            for (int jg = 0; jg < nv; jg += 8) {
+                uint32_t acc = 0;
+                if constexpr (PF > 0) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int j = jg + u;
+                        if (j < nv) {
+                            cp_async_wait<PF - 1>();  // variable j's words have landed (one group per variable)
+#pragma unroll
+                            for (int k = 0; k < NN; k++) wA[k] = lds_state8(pf_base + ((u % (PF + 1)) * NN + k) * 2048);
+                            // refill the stage consumed by the PREVIOUS variable (its words are in registers)
+                            if (j + PF < nv) issue(j + PF, (u + PF) % (PF + 1));
+                            cp_async_commit();
+                            update(j, wA, acc, u);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        const int jj = jg + u;
+                        if (jj < nv) {
+                            if (jj + 1 < nv) load_nbrs(jj + 1, wB);
+                            update(jj, wA, acc, u);
+                            if (jj + 1 < nv) {
+                                if (jj + 2 < nv) load_nbrs(jj + 2, wA);
+                                update(jj + 1, wB, acc, u + 1);
+                            }
+                        }
+                    }
+                }
+                if (record) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned s = __reduce_add_sync(amask, (acc >> (4 * k)) & 0x000f000fu);
+                        if (leader && s) atomicAdd(&s_cnt[(jg >> 1) + k], s);
+                    }
                 }
             }
         }
         __syncthreads();
         if (record && threadIdx.x < nv) {
             const int32_t coff = s_rec[threadIdx.x * 5].w;
-            const unsigned o = s_ones[threadIdx.x];
+            const unsigned o = (s_cnt[(threadIdx.x >> 3) * 4 + (threadIdx.x & 3)] >> (4 * (threadIdx.x & 4))) & 0xffffu;
             const int valid = max(0, min(2048, g.n_chains - chunk * 2048));
             if (o) atomicAdd(g.counts + coff + 1, (unsigned long long)o);
             if (valid - (int)o) atomicAdd(g.counts + coff, (unsigned long long)(valid - (int)o));
@@ -827,7 +909,7 @@ k_merge_partial(const DevModel m, const unsigned long long* __restrict__ counts,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.total_card) return;
     const int v = m.entry_var[i];
-    if (skip[v]) return;
+    if (skip[v] & 1) return;
     out[i] += n_chains * (1.0 / (double)m.card[v]) + (double)counts[i];
 }
 

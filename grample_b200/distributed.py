@@ -44,13 +44,14 @@ def all_reduce_device(dist, ptr, n, device):
     torch.cuda.synchronize(device)
 
 
-def merged_marginals(chains, dist=None):
-    """sampler.MergeChains over the chains of every rank"""
+def merged_marginals(chains, dist=None, out=None):
+    """sampler.MergeChains over the chains of every rank; `out` = optional caller-owned
+    (float64 [sum(card)], int32 [n_vars]) host buffers to fill instead of allocating"""
     if dist is None or dist.get_world_size() == 1:
-        return chains.merged_marginals()
+        return chains.merged_marginals(out)
     ptr, n = chains.merge_partial_dev()
     all_reduce_device(dist, ptr, n, chains.device)
-    return chains.merge_finalize()
+    return chains.merge_finalize(out)
 
 
 def convergence(chains, measure, merged, collapsed, cw, dist=None):
