@@ -91,7 +91,11 @@ struct gb_model {
         std::vector<int32_t> entry_var(h.total_card);
         for (int v = 0; v < h.n_vars; v++)
             for (int k = 0; k < h.card[v]; k++) entry_var[h.card_off[v] + k] = v;
-        std::vector<float> tab32(h.log_tab.begin(), h.log_tab.end());
+        // device copies of the tables are padded to a multiple of 4 entries (16-byte TMA bulk-copy granules)
+        std::vector<double> tab64(h.log_tab);
+        tab64.resize((tab64.size() + 3) & ~(size_t)3, 0.0);
+        std::vector<float> tab32(tab64.begin(), tab64.end());
+        dev.n_tab = (int32_t)tab64.size();
         dev.n_vars = h.n_vars;
         dev.total_card = h.total_card;
         dev.max_card = h.max_card;
@@ -100,7 +104,7 @@ struct gb_model {
         dev.fixed = up(h.fixed);
         dev.prog_off = up(h.prog_off);
         dev.prog = up(h.prog);
-        dev.tab64 = up(h.log_tab);
+        dev.tab64 = up(tab64);
         dev.tab32 = up(tab32);
         dev.entry_var = up(entry_var);
         d_order = up(h.order);
@@ -314,8 +318,8 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
 }
 
 // Shared-memory-resident path for small models: all sweeps of one group in ONE launch.
-template <typename Real, int MAXC, int CW>
-void launch_resident(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
+template <typename Real, int MAXC, int CW, bool TS>
+void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
     // block size >= work items of the largest colour of one CTA (one item per thread keeps the
     // per-colour critical path at a single update), capped at 256
     const gb::HostModel& hm = g.model->h;
@@ -326,60 +330,93 @@ void launch_resident(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_swee
     while (threads < 256 && threads < items) threads *= 2;
     static size_t configured = 0;
     if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const gb::HostModel& h = g.model->h;
-    gb::k_sweep_resident<Real, MAXC, CW><<<g.n_pad / ch, threads, smem, c->stream>>>(
+    gb::k_sweep_resident<Real, MAXC, CW, TS><<<g.n_pad / ch, threads, smem, c->stream>>>(
         g.model->dev, g.dev, g.model->d_order, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, ch, g.sweep, n_sweeps,
         record, n_pre, n_half);
     c->launches++;
 }
 
-// chains per CTA for the resident path, or 0 when the model does not qualify
-int resident_chains_per_cta(const gb_chains* c, const Group& g, size_t* smem_out) {
-    static int disabled = -1;
+// Resident-path launch plan: chains per CTA, dynamic shared memory, and whether the log-space tables are
+// staged in shared memory by TMA bulk copies (ts).  ch == 0: the model does not qualify.
+struct ResidentPlan {
+    int ch = 0;
+    size_t smem = 0;
+    bool ts = false;
+};
+
+ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
+    static int disabled = -1, no_ts = -1;
     if (disabled < 0) disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
-    if (disabled || c->precision == GB_TABLE) return 0;
+    if (no_ts < 0) no_ts = std::getenv("GB_NO_SMEM_TABLES") ? 1 : 0;  // A/B knob
+    ResidentPlan p;
+    if (disabled || c->precision == GB_TABLE) return p;
     const gb::HostModel& h = g.model->h;
-    if (h.n_vars > 4096) return 0;
-    // few chains per CTA = many CTAs = better SM fill and latency hiding for these small models;
-    // grow the CTA's chain count only when that would exceed ~16 CTAs per SM
+    if (h.n_vars > 4096) return p;
+    auto base = [&](int ch) { return (((size_t)h.n_vars * ch + 15) & ~(size_t)15) + (size_t)h.total_card * 4; };
+    const size_t real_bytes = c->precision == GB_F32 ? 4 : 8;
+    const size_t tab_bytes = 16 + (((size_t)h.log_tab.size() + 3) & ~(size_t)3) * real_bytes;
+    constexpr size_t kSmemPerSm = 220 * 1024, kSmemPerCta = 200 * 1024;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    // 1) tables staged in shared memory, if every CTA of the launch is still co-resident (these models
+    //    expose little parallelism per colour, so a second wave of CTAs costs more than LDS tables gain)
+    if (!no_ts)
+        for (int ch : {8, 16, 32, 64}) {
+            if (g.n_pad % ch) continue;
+            const size_t smem = base(ch) + tab_bytes;
+            if (smem > kSmemPerCta) break;
+            const int64_t per_sm = std::min<int64_t>(8, (int64_t)(kSmemPerSm / (smem + 1024)));
+            if (ch < 64 && (int64_t)(g.n_pad / ch) > per_sm * sms) continue;
+            if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
+            p.ch = ch; p.smem = smem; p.ts = true;
+            return p;
+        }
+    // 2) tables through L1: few chains per CTA = many CTAs = better SM fill and latency hiding; grow the
+    //    CTA's chain count only when that would exceed ~16 CTAs per SM
     for (int ch : {8, 16, 32}) {
         if (g.n_pad % ch) continue;
-        if (ch < 32 && g.n_pad / ch > 148 * 16) continue;
-        const size_t smem = (((size_t)h.n_vars * ch + 15) & ~(size_t)15) + (size_t)h.total_card * 4;
+        if (ch < 32 && g.n_pad / ch > sms * 16) continue;
+        const size_t smem = base(ch);
         if (smem > 100 * 1024) continue;
-        *smem_out = smem;
-        return ch;
+        p.ch = ch; p.smem = smem;
+        return p;
     }
-    return 0;
+    return p;
+}
+
+template <typename Real, int MAXC, int CW>
+void launch_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
+    if (p.ts) launch_resident_ts<Real, MAXC, CW, true>(c, g, p.ch, p.smem, n_sweeps, record, n_pre, n_half);
+    else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, p.smem, n_sweeps, record, n_pre, n_half);
 }
 
 // n_sweeps sweeps of one group with the AdvanceChain window schedule (n_half < 0: no histograms)
 void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
     if (n_sweeps <= 0) return;
     if (!(c->flags & GB_CHAINS_HISTORY)) n_half = -1;
-    size_t smem = 0;
-    const int ch = resident_chains_per_cta(c, g, &smem);
+    const ResidentPlan plan = resident_plan(c, g);
     const gb::HostModel& h = g.model->h;
-    if (ch && n_sweeps < (1ll << 30)) {
+    if (plan.ch && n_sweeps < (1ll << 30)) {
         const int mc = h.max_card;
         const int32_t ns = (int32_t)n_sweeps;
         if (c->precision == GB_F32) {
-            if (mc <= 2) launch_resident<float, 2, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 4) launch_resident<float, 4, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 8) launch_resident<float, 8, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 16) launch_resident<float, 16, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 32) launch_resident<float, 32, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else launch_resident<float, 64, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 4) launch_resident<float, 4, 4>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 8) launch_resident<float, 8, 0>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 16) launch_resident<float, 16, 0>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 32) launch_resident<float, 32, 0>(c, g, plan, ns, record, n_pre, n_half);
+            else launch_resident<float, 64, 0>(c, g, plan, ns, record, n_pre, n_half);
         } else {
-            if (mc <= 2) launch_resident<double, 2, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 4) launch_resident<double, 4, 4>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 8) launch_resident<double, 8, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 16) launch_resident<double, 16, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else if (mc <= 32) launch_resident<double, 32, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
-            else launch_resident<double, 64, 0>(c, g, ch, smem, ns, record, n_pre, n_half);
+            if (mc <= 2) launch_resident<double, 2, 4>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 4) launch_resident<double, 4, 4>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 8) launch_resident<double, 8, 0>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 16) launch_resident<double, 16, 0>(c, g, plan, ns, record, n_pre, n_half);
+            else if (mc <= 32) launch_resident<double, 32, 0>(c, g, plan, ns, record, n_pre, n_half);
+            else launch_resident<double, 64, 0>(c, g, plan, ns, record, n_pre, n_half);
         }
         g.sweep += (uint32_t)n_sweeps;
         if (record) {

@@ -35,6 +35,7 @@ struct DevModel {
     const int32_t* prog;        // update programs (host_model.hpp::build_programs)
     const double* tab64;        // log-space tables
     const float* tab32;
+    int32_t n_tab;              // table entries, padded to a multiple of 4 (16-byte bulk-copy granularity)
     const int32_t* entry_var;   // [total_card] variable of each marginal entry
 };
 
@@ -53,6 +54,14 @@ template <>
 __device__ __forceinline__ const double* tables_of<double>(const DevModel& m) { return m.tab64; }
 template <>
 __device__ __forceinline__ const float* tables_of<float>(const DevModel& m) { return m.tab32; }
+
+// Table reads: through the non-coherent global path (G = true) or plain loads when the tables have been
+// staged in shared memory (the compiler then emits LDS).
+template <bool G, typename Real>
+__device__ __forceinline__ Real ld_tab(const Real* p) {
+    if constexpr (G) return __ldg(p);
+    else return *p;
+}
 
 // gibbs-simple.go:227-258: log-weights -> floored un-normalised weights, in place.
 // float64 follows the reference literally (min-shift only when min < -8, sequential floor with
@@ -137,7 +146,7 @@ __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real
 // exponentiate, floor, inverse CDF.  `row` points at the first of the 4 chains in the row of
 // variable 0, `stride` is the row stride in bytes (global layout: n_pad; shared-memory-resident
 // layout: chains per CTA).  CW = chains whose weight vectors are held in registers at once.
-template <typename Real, int MAXC, int CW>
+template <typename Real, int MAXC, int CW, bool GT = true>
 __device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
                                                 const uint32_t stride, const int v, const int card, const uint32_t chain0,
                                                 const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
@@ -181,7 +190,7 @@ __device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* _
             for (int k = 0; k < MAXC; k++)
                 if (k < card) {
 #pragma unroll
-                    for (int ci = 0; ci < CW; ci++) w[ci][k] += __ldg(tab + b[ci] + k * sv);
+                    for (int ci = 0; ci < CW; ci++) w[ci][k] += ld_tab<GT>(tab + b[ci] + k * sv);
                 }
         }
 #pragma unroll
@@ -195,7 +204,7 @@ __device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* _
 // One variable x ONE chain (same arithmetic and draws as lse_update_quad for that chain): used by the
 // resident kernel for high-cardinality models, where one thread per chain gives 4x the parallelism
 // and a quarter of the registers.  `cell` points at this chain's byte in the row of variable 0.
-template <typename Real, int MAXC>
+template <typename Real, int MAXC, bool GT = true>
 __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                               const uint32_t stride, const int v, const int card, const uint32_t chain,
                                               const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
@@ -220,7 +229,7 @@ __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __r
         for (int o = 0; o < no; o++, p += 2) b += (int)cell[(size_t)__ldg(p) * stride] * __ldg(p + 1);
 #pragma unroll
         for (int k = 0; k < MAXC; k++)
-            if (k < card) w[k] += __ldg(tab + b + k * sv);
+            if (k < card) w[k] += ld_tab<GT>(tab + b + k * sv);
     }
     stabilise_exp_floor<Real, MAXC>(w, card);
     return inverse_cdf<Real, MAXC>(w, card, u);
@@ -293,16 +302,60 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
 // paths produce identical trajectories.  Window schedule of (*Chain).AdvanceChain: sweeps
 // [0, n_pre) record only, then n_half sweeps into the first and n_half into the second
 // half-window histogram (n_half < 0: no histograms).
-template <typename Real, int MAXC, int CW>  // CW = 0: one thread per chain (lse_update_one)
+// TS = the model's log-space tables are staged in shared memory for the whole launch (every sweep's
+// table gathers become LDS): one elected thread issues TMA bulk copies (cp.async.bulk, 16-byte
+// granules) that complete on an mbarrier while the CTA loads its chains' state.  TS = false reads the
+// tables through L1 (__ldg) — used when they do not fit next to the state.
+__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t bar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(const uint32_t dst, const void* src, const uint32_t bytes, const uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr uint32_t kBulkChunk = 32768;  // bytes per cp.async.bulk (multiple of 16)
+
+template <typename Real, int MAXC, int CW, bool TS>  // CW = 0: one thread per chain (lse_update_one)
 __global__ void __launch_bounds__(256)
 k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
                  const int32_t n_half) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar;
     uint8_t* s_state = smem;                                                                  // [n_vars][CH]
-    unsigned int* s_counts = reinterpret_cast<unsigned int*>(smem + (((size_t)m.n_vars * ch_per_cta + 15) & ~(size_t)15));  // [total_card]
+    const size_t counts_off = ((size_t)m.n_vars * ch_per_cta + 15) & ~(size_t)15;
+    unsigned int* s_counts = reinterpret_cast<unsigned int*>(smem + counts_off);              // [total_card]
     const Real* __restrict__ tab = tables_of<Real>(m);
+    if constexpr (TS) {
+        Real* s_tab = reinterpret_cast<Real*>(smem + ((counts_off + (size_t)m.total_card * 4 + 15) & ~(size_t)15));  // [n_tab]
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)m.n_tab * (uint32_t)sizeof(Real);
+            mbar_expect_tx(bar, bytes);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab);
+            for (uint32_t off = 0; off < bytes; off += kBulkChunk)
+                tma_bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(tab) + off, min(kBulkChunk, bytes - off), bar);
+        }
+        tab = s_tab;
+    }
     const int CH = ch_per_cta;
     const int cta_chain = blockIdx.x * CH;  // local index of this CTA's first chain
     const int n_quads = CH >> 2;
@@ -313,6 +366,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
             *reinterpret_cast<const uint32_t*>(g.state + (size_t)v * g.n_pad + cta_chain + 4 * q);
     }
     for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
+    if constexpr (TS) mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0);  // the tables have landed
     __syncthreads();
     for (int s = 0; s < n_sweeps; s++) {
         const uint32_t sweep = sweep0 + (uint32_t)s;
@@ -326,7 +380,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const int card = __ldg(m.card + v);
                     const int lchain = cta_chain + cc;
                     const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)lchain);
-                    const int x = lse_update_one<Real, MAXC>(m, tab, s_state + cc, (uint32_t)CH, v, card, chain, sweep, g.seed_lo, g.seed_hi);
+                    const int x = lse_update_one<Real, MAXC, !TS>(m, tab, s_state + cc, (uint32_t)CH, v, card, chain, sweep, g.seed_lo, g.seed_hi);
                     s_state[(size_t)v * CH + cc] = (uint8_t)x;
                     if (record && lchain < g.n_chains) {
                         const int32_t coff = __ldg(m.card_off + v);
@@ -345,7 +399,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const int lchain = cta_chain + 4 * q;  // local chain index of the quad
                     const uint32_t chain0 = (uint32_t)(g.first_chain + (uint64_t)lchain);
                     int x[4];
-                    lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW)>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep,
+                    lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep,
                                                                     g.seed_lo, g.seed_hi, x);
                     *reinterpret_cast<uint32_t*>(s_state + (size_t)v * CH + 4 * q) =
                         (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
