@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "grample_b200.h")
 F64, F32, TABLE = 0, 1, 2
 MAX_ABS, MEAN_ABS, HELLINGER, JS = 0, 1, 2, 3
 CHAINS_HISTORY = 1
+CHAINS_PER_COLOUR = 2
 NEIGHBOR_VAR_MAX = 12
 MAX_CARD = 64
 

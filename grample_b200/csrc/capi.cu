@@ -353,10 +353,22 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     if (disabled < 0) disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
     if (no_ts < 0) no_ts = std::getenv("GB_NO_SMEM_TABLES") ? 1 : 0;  // A/B knob
     ResidentPlan p;
-    if (disabled || c->precision == GB_TABLE) return p;
+    if (disabled || (c->flags & GB_CHAINS_PER_COLOUR)) return p;
     const gb::HostModel& h = g.model->h;
     if (h.n_vars > 4096) return p;
     auto base = [&](int ch) { return (((size_t)h.n_vars * ch + 15) & ~(size_t)15) + (size_t)h.total_card * 4; };
+    if (c->precision == GB_TABLE) {  // units of 8 chains; thresholds and records stay in L1
+        int sms_t = 148;
+        cudaDeviceGetAttribute(&sms_t, cudaDevAttrMultiProcessorCount, c->device);
+        for (int ch : {8, 16, 32, 64}) {
+            if (g.n_pad % ch) continue;
+            if (ch < 64 && g.n_pad / ch > sms_t * 16) continue;
+            if (base(ch) > 100 * 1024) break;
+            p.ch = ch; p.smem = base(ch);
+            return p;
+        }
+        return p;
+    }
     const size_t real_bytes = c->precision == GB_F32 ? 4 : 8;
     const size_t tab_bytes = 16 + (((size_t)h.log_tab.size() + 3) & ~(size_t)3) * real_bytes;
     constexpr size_t kSmemPerSm = 220 * 1024, kSmemPerCta = 200 * 1024;
@@ -394,6 +406,24 @@ void launch_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sw
     else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, p.smem, n_sweeps, record, n_pre, n_half);
 }
 
+void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
+    const gb::HostModel& h = g.model->h;
+    int max_col = 1;
+    for (size_t i = 0; i + 1 < h.colour_off.size(); i++) max_col = std::max(max_col, h.colour_off[i + 1] - h.colour_off[i]);
+    const int64_t items = (int64_t)max_col * (p.ch / 8);
+    int threads = 32;
+    while (threads < 256 && threads < items) threads *= 2;
+    static size_t configured = 0;
+    if (p.smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_tab_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        configured = p.smem;
+    }
+    gb::k_sweep_tab_resident<<<g.n_pad / p.ch, threads, p.smem, c->stream>>>(
+        g.model->dev, g.model->tab, g.dev, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, p.ch, g.sweep, n_sweeps, record,
+        n_pre, n_half);
+    c->launches++;
+}
+
 // n_sweeps sweeps of one group with the AdvanceChain window schedule (n_half < 0: no histograms)
 void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
     if (n_sweeps <= 0) return;
@@ -403,7 +433,9 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
     if (plan.ch && n_sweeps < (1ll << 30)) {
         const int mc = h.max_card;
         const int32_t ns = (int32_t)n_sweeps;
-        if (c->precision == GB_F32) {
+        if (c->precision == GB_TABLE) {
+            launch_tab_resident(c, g, plan, ns, record, n_pre, n_half);
+        } else if (c->precision == GB_F32) {
             if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, n_pre, n_half);
             else if (mc <= 4) launch_resident<float, 4, 4>(c, g, plan, ns, record, n_pre, n_half);
             else if (mc <= 8) launch_resident<float, 8, 0>(c, g, plan, ns, record, n_pre, n_half);

@@ -751,6 +751,116 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
     }
 }
 
+// ------------------------------------------------------------------ K1-table resident
+// Table mode for small models: like k_sweep_resident, a CTA keeps the state of CH (multiple of 8)
+// consecutive chains in shared memory and runs every colour of every sweep of a round in one launch.
+// Work item = (sweep position, unit of 8 chains); same records, thresholds, Philox stream and tie rule
+// as k_sweep_tab, so the two paths produce identical trajectories.  Records and thresholds are read
+// through L1 (they are a few KB and shared by every CTA).
+__global__ void __launch_bounds__(256)
+k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ colour_off,
+                     const int32_t n_colours, const int32_t ch_per_cta, const uint32_t sweep0, const int32_t n_sweeps,
+                     const int record, const int32_t n_pre, const int32_t n_half) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_state = smem;  // [n_vars][CH]
+    unsigned int* s_counts = reinterpret_cast<unsigned int*>(smem + (((size_t)m.n_vars * ch_per_cta + 15) & ~(size_t)15));  // [total_card]
+    const int CH = ch_per_cta;
+    const int cta_chain = blockIdx.x * CH;
+    const int units = CH >> 3;
+    for (int i = threadIdx.x; i < m.n_vars * units; i += blockDim.x) {
+        const int v = i / units, q = i - v * units;
+        *reinterpret_cast<uint2*>(s_state + (size_t)v * CH + 8 * q) =
+            *reinterpret_cast<const uint2*>(g.state + (size_t)v * g.n_pad + cta_chain + 8 * q);
+    }
+    for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
+    __syncthreads();
+    for (int s = 0; s < n_sweeps; s++) {
+        const uint32_t sweep = sweep0 + (uint32_t)s;
+        const int hist_half = (n_half < 0 || s < n_pre) ? -1 : (s < n_pre + n_half ? 0 : 1);
+        for (int col = 0; col < n_colours; col++) {
+            const int c0 = __ldg(colour_off + col), nvc = __ldg(colour_off + col + 1) - c0;
+            for (int item = threadIdx.x; item < nvc * units; item += blockDim.x) {
+                const int j = item / units, q = item - j * units;
+                const int4* r = reinterpret_cast<const int4*>(t.trec + (size_t)(c0 + j) * kTabRec);
+                const int4 hd = __ldg(r);  // v, thr_off, n_nbr, card_off
+                uint32_t cfg_lo = 0, cfg_hi = 0;
+                {
+                    const int4 na = __ldg(r + 1), sa = __ldg(r + 3);
+                    const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {  // slots past n_nbr hold the variable itself at stride 0
+                        const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)nb[i] * CH + 8 * q);
+                        cfg_lo += w.x * (uint32_t)sb[i];
+                        cfg_hi += w.y * (uint32_t)sb[i];
+                    }
+                }
+                if (hd.z > 4) {
+                    const int4 na = __ldg(r + 2), sa = __ldg(r + 4);
+                    const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)nb[i] * CH + 8 * q);
+                        cfg_lo += w.x * (uint32_t)sb[i];
+                        cfg_hi += w.y * (uint32_t)sb[i];
+                    }
+                }
+                const int lchain = cta_chain + 8 * q;
+                const uint32_t chain_blk = (uint32_t)((g.first_chain + (uint64_t)lchain) >> 3);
+                const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
+                const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+                uint32_t T[8], xbits = 0;
+                bool tie = false;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+                    T[i] = __ldg(t.thr + hd.y + idx);
+                    const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                    xbits |= (hi > (T[i] >> 16) ? 1u : 0u) << i;
+                    tie |= hi == (T[i] >> 16);
+                }
+                if (tie) {  // draw > threshold <=> high halves equal and lo16 > (T & 0xffff)
+                    const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
+                    const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                        const uint32_t lo = (wb[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                        if (hi == (T[i] >> 16) && lo > (T[i] & 0xffffu)) xbits |= 1u << i;
+                    }
+                }
+                uint2 outw;
+                outw.x = ((xbits & 0xfu) * 0x00204081u) & 0x01010101u;
+                outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+                *reinterpret_cast<uint2*>(s_state + (size_t)hd.x * CH + 8 * q) = outw;
+                if (record) {
+                    const int nvalid = max(0, min(8, g.n_chains - lchain));
+                    const uint32_t vmask = (nvalid >= 8) ? 0xffu : ((1u << nvalid) - 1u);
+                    const int ones = __popc(xbits & vmask);
+                    if (ones) atomicAdd(&s_counts[hd.w + 1], (unsigned)ones);
+                    if (nvalid - ones) atomicAdd(&s_counts[hd.w], (unsigned)(nvalid - ones));
+                    if (hist_half >= 0 && g.hist) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (i < nvalid) {
+                                uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + hd.w + ((xbits >> i) & 1u)) * g.n_pad + lchain + i;
+                                *h = (uint16_t)(*h + 1);
+                            }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < m.n_vars * units; i += blockDim.x) {
+        const int v = i / units, q = i - v * units;
+        *reinterpret_cast<uint2*>(g.state + (size_t)v * g.n_pad + cta_chain + 8 * q) =
+            *reinterpret_cast<const uint2*>(s_state + (size_t)v * CH + 8 * q);
+    }
+    if (record)
+        for (int i = threadIdx.x; i < m.total_card; i += blockDim.x)
+            if (s_counts[i]) atomicAdd(g.counts + i, (unsigned long long)s_counts[i]);
+}
+
 // ------------------------------------------------------------------ K6
 __global__ void __launch_bounds__(256) k_init_state(const DevModel m, const DevGroup g) {
     const int32_t n_quads = g.n_pad >> 2;

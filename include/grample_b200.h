@@ -50,6 +50,7 @@ enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 }
 enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2 };
 /* gb_chains_create flags */
 #define GB_CHAINS_HISTORY 1u /* keep per-chain half-window histograms (needed by gb_chains_convergence*) */
+#define GB_CHAINS_PER_COLOUR 2u /* always launch one kernel per colour (disables the shared-memory-resident multi-sweep kernels small models use; same results) */
 
 const char* gb_last_error(void);
 int gb_version(void);

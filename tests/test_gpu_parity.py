@@ -102,11 +102,13 @@ def test_init_state(res, name, evid):
     ("one.uai", False, 4, 50), ("sample.uai", False, 6, 40), ("deterministic.uai", False, 8, 40),
     ("Grids_11.uai", False, 16, 12), ("Promedus_11.uai", True, 8, 6), ("Pedigree_11.uai", True, 8, 6),
     ("ObjectDetection_11.uai", False, 8, 10), ("dv-rel_1.uai", True, 5, 8)])
-def test_sweep_bitexact_f64(res, name, evid, n_chains, n_sweeps):
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+def test_sweep_bitexact_f64(res, name, evid, n_chains, n_sweeps, per_colour):
+    """both launch paths (k_sweep_resident with TMA-staged tables, k_sweep_colour) against the oracle"""
     dm, om = load_pair(res, name, evid)
     order, coff = dm.schedule()
     seed, first = 4242, 16
-    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0)
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0, per_colour=per_colour)
     st0 = ch.get_state(0, n_chains)
     ch.burnin(2)
     ch.sweep(n_sweeps, record=True)
@@ -160,12 +162,14 @@ def test_table_thresholds_match_oracle_conditionals(res, name, evid):
     assert total == n_thr
 
 
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
 @pytest.mark.parametrize("n_chains,first", [(13, 16), (64, 0), (2100, 8)])
-def test_table_sweep_bitexact_grids(res, n_chains, first):
+def test_table_sweep_bitexact_grids(res, n_chains, first, per_colour):
+    """k_sweep_tab_resident and k_sweep_tab (cp.async ring) against the oracle with 32-bit draws"""
     dm, om = load_pair(res, "Grids_11.uai", False)
     order, _ = dm.schedule()
     seed, n_sweeps = 777, 8 if n_chains < 1000 else 2
-    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.TABLE, device=0)
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.TABLE, device=0, per_colour=per_colour)
     st0 = ch.get_state(0, n_chains)
     ch.burnin(1)
     ch.sweep(n_sweeps)
@@ -177,7 +181,8 @@ def test_table_sweep_bitexact_grids(res, n_chains, first):
     assert ch.total_samples == n_sweeps * 100 * n_chains
 
 
-def test_table_sweep_bitexact_ising_and_evidence():
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+def test_table_sweep_bitexact_ising_and_evidence(per_colour):
     arrays = list(gb.ising_torus(6, 8, wmax=4.9, seed=5))
     arrays[1] = arrays[1].copy()
     arrays[1][[3, 17, 40]] = [1, 0, 1]  # evidence folds into the tables
@@ -186,7 +191,7 @@ def test_table_sweep_bitexact_ising_and_evidence():
     order, coff = dm.schedule()
     assert len(order) == 45
     n_chains, seed = 24, 99
-    ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.TABLE, history=True, device=0)
+    ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.TABLE, history=True, device=0, per_colour=per_colour)
     st0 = ch.get_state(0, n_chains)
     ch.advance(10)
     samp = oracle.Sampler(oracle.Generator(1), om)
@@ -197,6 +202,24 @@ def test_table_sweep_bitexact_ising_and_evidence():
     assert np.all(hist.reshape(2, -1, 2, n_chains).sum(2)[:, order] == 5)
     conv = ch.convergence(gb.HELLINGER)
     assert np.all(conv[[3, 17, 40]] == 1.0) and np.all(np.isfinite(conv))
+
+
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+@pytest.mark.parametrize("name,evid", [("Promedus_11.uai", True), ("Pedigree_11.uai", True)])
+def test_table_sweep_bitexact_wide_blankets(res, name, evid, per_colour):
+    """bundled problems whose variables have up to 8 free neighbours (256 configurations): NN = 8 records"""
+    dm, om = load_pair(res, name, evid)
+    if not dm.table_mode()[0]:
+        pytest.skip("table mode does not apply to this model")
+    order, _ = dm.schedule()
+    seed, n_chains, n_sweeps = 31, 24, 4
+    ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.TABLE, device=0, per_colour=per_colour)
+    st0 = ch.get_state(0, n_chains)
+    ch.sweep(n_sweeps)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, ocounts = samp.sweep_run(order, seed, 0, st0, 0, n_sweeps, bits=32, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
 
 
 def test_table_mode_rejects_unsuitable_models(res):
