@@ -8,14 +8,120 @@ Status / error-report lines keep the reference's format (cmd/root.go:256-306, 49
 (cmd/root.go:455-458, 520-533).
 """
 import argparse
+import json
 import math
+import os
 import sys
+import threading
 import time
 
 import numpy as np
 
 from . import core
-from ._lib import F32, F64, HELLINGER, TABLE
+from ._lib import F32, F64, HELLINGER, JS, MAX_ABS, MEAN_ABS, TABLE
+
+
+def letter26(n):
+    """model/variable.go:167-189: Excel-column style variable names (0 -> A, 25 -> Z, 26 -> AA)"""
+    if n == 0:
+        return "A"
+    n += 1
+    digits = []
+    while n > 0:
+        n, r = divmod(n - 1, 26)
+        digits.append("ABCDEFGHIJKLMNOPQRSTUVWXYZ"[r])
+    return "".join(reversed(digits))
+
+
+def variable_json(vid, card, fixed, marginal, state, collapsed):
+    """One line of the trace file: encoding/json of model.Variable (model/variable.go:10-18; struct field
+    order, map keys sorted) — what script/trace_file_process.py reads from the `// VARS (ESTIMATED)` section."""
+    rec = {"ID": int(vid), "Name": letter26(int(vid)), "Card": int(card), "FixedVal": int(fixed),
+           "Marginal": [float(x) for x in marginal], "State": {k: float(state[k]) for k in sorted(state)},
+           "Collapsed": bool(collapsed)}
+    return json.dumps(rec, separators=(",", ":"))
+
+
+def per_var_measures(cards, p, q, fixed_p=None, fixed_q=None):
+    """model/error.go:81-249 per variable: dict measure-name -> array [n_vars] (0 where either side is fixed).
+    Names follow the `*-Error` state keys of cmd/root.go:651-655."""
+    cards = np.asarray(cards)
+    offs = np.concatenate([[0], np.cumsum(cards)])
+    n = len(cards)
+    out = {k: np.zeros(n) for k in ("Hell", "JS", "MaxAD", "AvgAD")}
+    for v in range(n):
+        if (fixed_p is not None and fixed_p[v] >= 0) or (fixed_q is not None and fixed_q[v] >= 0):
+            continue
+        a, b = np.asarray(p[offs[v]:offs[v + 1]], dtype=np.float64), np.asarray(q[offs[v]:offs[v + 1]], dtype=np.float64)
+        a, b = a / max(a.sum(), 1e-12), b / max(b.sum(), 1e-12)
+        d = np.abs(a - b)
+        out["MaxAD"][v], out["AvgAD"][v] = d.max(), d.sum() / len(d)
+        out["Hell"][v] = math.sqrt(float(((np.sqrt(a) - np.sqrt(b)) ** 2).sum())) / math.sqrt(2.0)
+        mid = np.maximum((a + b) * 0.5, 1e-12)
+        ac, bc = np.maximum(a, 1e-12), np.maximum(b, 1e-12)
+        out["JS"][v] = 0.5 * (float((ac * np.log2(ac / mid)).sum()) + float((bc * np.log2(bc / mid)).sum()))
+    return out
+
+
+class Monitor:
+    """The gauges of cmd/monitor.go:53-67 under the reference's expvar names.  `snapshot()` is the JSON
+    object expvar serves at /debug/vars; with an address it is served over HTTP like the reference's
+    monitor (every path redirects there), otherwise it is only kept (and written to the trace file)."""
+    NAMES = ["Burn-In", "Convergence-Window", "Base-Chain-Count", "Chain-Adds-For-Adaptive-Step", "Total-Chain-Count",
+             "Max-Iterations", "Max-Seconds", "Run-Time", "Total-Samples", "Iterations", "Last-Mean-Hellinger",
+             "Last-Max-Hellinger", "Last-Mean-JSD", "Last-Max-JSD"]
+
+    def __init__(self):
+        self.v = {k: 0 for k in self.NAMES}
+        self.server = None
+
+    def set(self, name, value):
+        assert name in self.v, name
+        self.v[name] = value
+
+    def add(self, name, delta):
+        self.v[name] += delta
+
+    def score(self, es):  # cmd/root.go:262-265
+        self.set("Last-Mean-Hellinger", es["MeanHellinger"])
+        self.set("Last-Max-Hellinger", es["MaxHellinger"])
+        self.set("Last-Mean-JSD", es["MeanJSDiverge"])
+        self.set("Last-Max-JSD", es["MaxJSDiverge"])
+
+    def snapshot(self):
+        return dict(self.v)
+
+    def start(self, addr):
+        from http.server import BaseHTTPRequestHandler, HTTPServer
+        host, _, port = addr.rpartition(":")
+        mon = self
+
+        class H(BaseHTTPRequestHandler):
+            def do_GET(self):
+                if self.path != "/debug/vars":
+                    self.send_response(307)
+                    self.send_header("Location", "/debug/vars")
+                    self.end_headers()
+                    return
+                body = json.dumps(mon.snapshot()).encode()
+                self.send_response(200)
+                self.send_header("Content-Type", "application/json; charset=utf-8")
+                self.send_header("Content-Length", str(len(body)))
+                self.end_headers()
+                self.wfile.write(body)
+
+            def log_message(self, *a):
+                pass
+
+        self.server = HTTPServer((host or "127.0.0.1", int(port)), H)
+        threading.Thread(target=self.server.serve_forever, daemon=True).start()
+        sys.stderr.write("HTTP now available at %s (see debug/vars/)\n" % addr)
+
+    def stop(self):
+        if self.server is not None:
+            self.server.shutdown()
+            self.server.server_close()
+            self.server = None
 
 
 def error_report(prefix, es, short, out):
@@ -54,21 +160,53 @@ def build_parser():
     s.add_argument("--replicas", type=int, default=1024, help="device chains behind each reference chain")
     s.add_argument("--precision", default="f32", choices=["f64", "f32", "table"])
     s.add_argument("--device", type=int, default=0)
+    s.add_argument("--addr", default="", help="ip:port for the expvar-style monitor (cmd/monitor.go); empty = no HTTP server")
     return ap
 
 
-def sample(args, out=sys.stdout):
+def dump_params(args, burn, cw, base, max_iters, seed, dst):
+    """startupParams.dump (cmd/root.go:97-112)"""
+    dst.write("Verbose:                %s\n" % str(bool(args.verbose)).lower())
+    dst.write("Model:                  %s\n" % args.model)
+    dst.write("Apply Evidence:         %s\n" % str(bool(args.evidence)).lower())
+    dst.write("Solution:               %s\n" % str(bool(args.solution)).lower())
+    dst.write("Sampler:                %s\n" % args.sampler)
+    dst.write("Burn In:                %12d\n" % burn)
+    dst.write("Converge Win:           %12d\n" % cw)
+    dst.write("Num Base Chain:         %12d\n" % base)
+    dst.write("Chains Added per Adapt: %12d\n" % args.chainadds)
+    dst.write("Max Iters:              %12d\n" % max_iters)
+    dst.write("Max Secs:               %12d\n" % args.maxsecs)
+    dst.write("Rnd Seed:               %12d\n" % seed)
+    dst.write("Monitor Addr:           %s\n" % args.addr)
+    dst.write("Experiment Mode:        %s\n" % str(bool(args.experiment)).lower())
+
+
+def sample(args, out=sys.stdout, monitor=None):
     start = time.time()
+    mon = monitor if monitor is not None else Monitor()
+    if getattr(args, "addr", ""):
+        mon.start(args.addr)
+    try:
+        return _sample(args, out, mon, start)
+    finally:
+        mon.stop()
+
+
+def _sample(args, out, mon, start):
     prec = {"f64": F64, "f32": F32, "table": TABLE}[args.precision]
     out.write("Reading model from %s\n" % args.model)
     mod = core.Model.from_uai(args.model, use_evidence=args.evidence, device=args.device)
     n, cards, fixed = mod.n_vars, mod.cards, mod.fixed
+    offs = np.concatenate([[0], np.cumsum(cards)])
     out.write("Model has %d vars and %d functions\n" % (n, mod.n_funcs))
     sol = None
     if args.solution:
         sol_cards, sol = core.mar_load(args.model + ".MAR")
         uniform = np.concatenate([np.full(c, 1.0 / c) for c in cards])
-        error_report("START", core.error_suite(cards, sol, uniform, fixed2=fixed), False, out)
+        es = core.error_suite(cards, sol, uniform, fixed2=fixed)
+        mon.score(es)
+        error_report("START", es, False, out)
     if args.experiment and not args.trace:
         raise core.GrampleError("Experiment mode requires a trace file")
     # defaults derived from n (cmd/root.go:344-363)
@@ -78,8 +216,13 @@ def sample(args, out=sys.stdout):
     cw = args.cwin if args.cwin > 0 else 2000
     base = max(2, args.chains if args.chains > 0 else 2)
     max_iters = args.maxiters if args.maxiters >= 0 else 20000 * n * args.replicas
+    mon.set("Burn-In", burn)  # cmd/root.go:367-370
+    mon.set("Convergence-Window", cw)
+    mon.set("Max-Iterations", max_iters)
+    mon.set("Max-Seconds", args.maxsecs)
     if args.sampler != "adaptive" and args.chainadds != 1:
         raise core.GrampleError("Sampler is not adaptive: ChainAdds=%d makes no sense" % args.chainadds)
+    mon.set("Chain-Adds-For-Adaptive-Step", args.chainadds)
     per = (args.replicas + 7) // 8 * 8
 
     out.write("Creating chains and performing burn-in (%d)\n" % burn)
@@ -92,12 +235,15 @@ def sample(args, out=sys.stdout):
             models.append(m)
         else:
             models.append(mod)
+        mon.add("Base-Chain-Count", 1)  # cmd/root.go:428-429
+        mon.add("Total-Chain-Count", 1)
     chains = core.Chains(models, [args.replicas] * base, seed=seed, precision=prec, history=True, device=args.device)
     chains.burnin((burn + n_free - 1) // max(n_free, 1))
     next_id = base * per
     trace = open(args.trace, "w") if args.trace else None
     if args.experiment:
         trace.write("// EXPERIMENT RESULTS\nRunSecs, MaxHell, NegLogMaxHell, MaxJS, NegLogMaxJS, CollapseCount\n")
+    nl = lambda x: -math.log2(x) if x > 0 else float("inf")
 
     out.write("Main Sampling Start\n")
     stop, next_status = start + args.maxsecs, start + 2.5
@@ -110,18 +256,21 @@ def sample(args, out=sys.stdout):
         if args.maxsecs > 0 and now > stop:
             working = False
         count = chains.total_samples
+        mon.set("Iterations", count)  # cmd/root.go:492
+        mon.set("Total-Samples", count)
         if max_iters > 0 and count > max_iters:
             working = False
         if now > next_status or not working or args.experiment:
             if now > next_status or not working:
+                mon.set("Run-Time", now - start)  # cmd/root.go:502
                 out.write("  Samps: %12d | RT %12.2fsec\n" % (count, now - start))
             if sol is not None:
                 merged, col = chains.merged_marginals()
                 score = core.error_suite(cards, sol, merged, fixed2=fixed)
                 if now > next_status or not working:
+                    mon.score(score)
                     error_report("", score, True, out)
                 if args.experiment:
-                    nl = lambda x: -math.log2(x) if x > 0 else float("inf")
                     trace.write("%.1f, %.8f, %.5f, %.8f, %.5f, %d\n" % (now - start, score["MaxHellinger"], nl(score["MaxHellinger"]),
                                                                        score["MaxJSDiverge"], nl(score["MaxJSDiverge"]), int(col.sum())))
             if now > next_status or not working:
@@ -134,24 +283,89 @@ def sample(args, out=sys.stdout):
             chosen = chains.adapt(mod, args.chainadds, args.replicas, cw, first_chain_id=next_id, measure=HELLINGER)
             next_id += len(chosen) * per
             if chains.n_groups != pre:
+                mon.set("Total-Chain-Count", chains.n_groups)  # cmd/root.go:557
                 out.write("ADAPT: %d Chains (was %d)\n" % (chains.n_groups, pre))
 
+    run_time = time.time() - start
     merged, col = chains.merged_marginals()  # cmd/root.go:565-571
-    offs = np.concatenate([[0], np.cumsum(cards)])
     final = merged.copy()
     for v in range(n):
         final[offs[v]:offs[v + 1]] /= final[offs[v]:offs[v + 1]].sum()
     out.write("DONE\n")
+    state = [dict() for _ in range(n)]  # per-variable Variable.State (cmd/root.go:600-657)
+    merlin = None
     if sol is not None:
-        error_report("FINAL", core.error_suite(cards, sol, final, fixed2=fixed), False, out)
-    conv = chains.convergence(HELLINGER, merged)
-    if args.verbose or trace:
-        dst = trace if trace else out
-        dst.write("// VARS (ESTIMATED)\n")
+        score = core.error_suite(cards, sol, final, fixed2=fixed)
+        mon.score(score)
+        error_report("FINAL", score, False, out)
+        if args.experiment:  # cmd/root.go:582-597
+            trace.write("%.1f, %.8f, %.5f, %.8f, %.5f, %d\n" % (run_time, score["MaxHellinger"], nl(score["MaxHellinger"]),
+                                                               score["MaxJSDiverge"], nl(score["MaxJSDiverge"]), int(col.sum())))
+            trace.write("// FINAL STATUS\n")
+            error_report("FINAL", score, False, trace)
+        for v in range(n):
+            for c in range(cards[v]):
+                state[v]["SOL-MAR[%d]" % c] = sol[offs[v] + c]
+        merlin_path = args.model + ".merlin.MAR"  # cmd/root.go:609-635
+        if os.path.exists(merlin_path):
+            _, merlin = core.mar_load(merlin_path)
+            ms = core.error_suite(cards, sol, merlin)
+            error_report("MERLIN SCORE", ms, False, out)
+            if args.experiment:
+                trace.write("// MERLIN SCORES\n")
+                error_report("MERLIN SCORE", ms, False, trace)
+            error_report("OUR SCORE USING MERLIN AS SOLUTION", core.error_suite(cards, merlin, final, fixed2=fixed), False, out)
+    # final convergence under all four measures and per-variable errors (cmd/root.go:638-657)
+    for key, measure in (("Hell", HELLINGER), ("JS", JS), ("MaxAD", MAX_ABS), ("AvgAD", MEAN_ABS)):
+        conv = chains.convergence(measure, merged)
+        for v in range(n):
+            state[v][key + "-Convergence"] = conv[v]
+    if sol is not None:
+        errs = per_var_measures(cards, final, sol, fixed_p=fixed)
+        for key, arr in errs.items():
+            for v in range(n):
+                state[v][key + "-Error"] = arr[v]
+
+    def line(v):
+        return variable_json(v, cards[v], fixed[v], final[offs[v]:offs[v + 1]], state[v], col[v])
+
+    if trace or args.verbose:  # cmd/root.go:659-710
+        if trace:
+            trace.write("// EVIDENCE\n")
+        for v in range(n):
+            if fixed[v] >= 0:
+                if trace:
+                    trace.write(line(v) + "\n")
+                if args.verbose:
+                    out.write("Variable[%d] %s (Card:%d, %s) EVID=%d\n" % (v, letter26(v), cards[v], state[v], fixed[v]))
+        if trace:
+            trace.write("// VARS (ESTIMATED)\n")
         for v in range(n):
             if fixed[v] < 0:
-                dst.write('{"ID":%d,"Card":%d,"Marginal":%s,"Collapsed":%s,"Hell-Convergence":%.6f}\n' % (
-                    v, cards[v], final[offs[v]:offs[v + 1]].tolist(), "true" if col[v] else "false", conv[v]))
+                if trace:
+                    trace.write(line(v) + "\n")
+                if args.verbose:
+                    out.write("Variable[%d] %s (Card:%d, %s) %s\n" % (v, letter26(v), cards[v], state[v], final[offs[v]:offs[v + 1]].tolist()))
+        if merlin is not None:
+            mh = per_var_measures(cards, final, merlin, fixed_p=fixed)["Hell"]
+            report = [v for v in range(n) if fixed[v] < 0]
+            for v in report:
+                state[v]["MerlinHellError"] = mh[v]
+            report.sort(key=lambda v: state[v]["MerlinHellError"])
+            if trace:
+                trace.write("// VARS SORTED BY DIST FROM HELLINGER\n")
+                for v in report:
+                    trace.write(line(v) + "\n")
+        if trace:
+            trace.write("// OPERATING PARAMS\n")
+            dump_params(args, burn, cw, base, max_iters, seed, trace)
+            trace.write("// MONITOR\n" + json.dumps(mon.snapshot()) + "\n")
+            # cmd/root.go:715-717: json of model.Model (Funcs are `json:"-"`): Type, Name, Vars
+            trace.write("// ENTIRE MODEL\n")
+            with open(args.model) as f:  # model type = first field of the UAI file (model/uai.go:73-80)
+                mtype = next((ln.split()[0] for ln in f if ln.strip() and not ln.startswith("c")), "MARKOV")
+            trace.write(json.dumps({"Type": mtype, "Name": os.path.splitext(args.model)[0],  # model/model.go:65
+                                    "Vars": [json.loads(line(v)) for v in range(n)]}, indent=2) + "\n")
     if trace:
         trace.close()
     return final, col

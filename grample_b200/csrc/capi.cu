@@ -60,6 +60,8 @@ int grid_for(int64_t items, int threads) {
     return (int)blocks;
 }
 
+constexpr int kMaxDevices = 64;  // per-device caches of launch configuration
+
 }  // namespace
 
 struct gb_model {
@@ -174,9 +176,17 @@ struct gb_chains {
     std::vector<int32_t> col_any32;    // col_any widened for the ABI's int32 output
     double* h_merge = nullptr;         // pinned staging buffer for the device -> host copy
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // groups are independent between monitor intervals (like the reference's goroutine per chain,
+    // chain.go:197-215): their launches fan out over side streams and join back on `stream`
+    std::vector<cudaStream_t> side;
+    std::vector<cudaEvent_t> ev_join;
+    cudaEvent_t ev_fork = nullptr;
 
     ~gb_chains() {
         cudaSetDevice(device);
+        for (auto st : side) cudaStreamDestroy(st);
+        for (auto e : ev_join) cudaEventDestroy(e);
+        if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& g : groups) {
             cudaFree(g.d_state);
             cudaFree(g.d_counts);
@@ -248,7 +258,8 @@ void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int
 
 template <int VB, int NN, bool HIST, int PF>
 void launch_tab_variant(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
-    static int resident = 0;  // CTAs that fit the device at once (persistent tile loop)
+    static int resident_dev[kMaxDevices] = {};  // per device: CTAs that fit at once (persistent tile loop)
+    int& resident = resident_dev[c->device % kMaxDevices];
     constexpr size_t ring = (size_t)(PF > 0 ? (PF + 1) * NN * 256 * 8 : 0);  // cp.async prefetch ring
     if (!resident) {
         int per_sm = 0, sms = 0;
@@ -328,7 +339,8 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_s
     const int64_t items = (int64_t)max_col * (CW == 0 ? ch : ch / 4);
     int threads = 32;
     while (threads < 256 && threads < items) threads *= 2;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
+    size_t& configured = configured_dev[c->device % kMaxDevices];
     if (smem > configured) {
         CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -413,7 +425,8 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     const int64_t items = (int64_t)max_col * (p.ch / 8);
     int threads = 32;
     while (threads < 256 && threads < items) threads *= 2;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
+    size_t& configured = configured_dev[c->device % kMaxDevices];
     if (p.smem > configured) {
         CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_tab_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         configured = p.smem;
@@ -463,9 +476,50 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
     }
 }
 
+// Run f(group) for every group with the groups' kernels on different streams (up to 128 at once): a
+// variant's group is a few hundred chains, far too few to fill the device alone.  Everything a group's
+// kernels touch (state, counts, histograms) is private to the group.  Fork: the side streams wait for
+// what is already queued on the main stream; join: the main stream waits for every side stream.
+static const size_t kSideStreams = std::getenv("GB_SIDE_STREAMS") ? (size_t)std::atoi(std::getenv("GB_SIDE_STREAMS")) : 128;  // = the device's limit of concurrently resident kernels
+template <typename F>
+void for_each_group_concurrent(gb_chains* c, F&& f) {
+    static const bool serial = std::getenv("GB_SERIAL_GROUPS") != nullptr;  // A/B knob
+    if (c->groups.size() < 2 || serial) {
+        for (auto& g : c->groups) f(g);
+        return;
+    }
+    const size_t K = std::min(kSideStreams, c->groups.size());
+    while (c->side.size() < K) {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        c->side.push_back(st);
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->ev_join.push_back(ev);
+    }
+    if (!c->ev_fork) CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    cudaStream_t main_stream = c->stream;
+    CUDA_CHECK(cudaEventRecord(c->ev_fork, main_stream));
+    for (size_t k = 0; k < K; k++) CUDA_CHECK(cudaStreamWaitEvent(c->side[k], c->ev_fork, 0));
+    try {
+        for (size_t i = 0; i < c->groups.size(); i++) {
+            c->stream = c->side[i % K];
+            f(c->groups[i]);
+        }
+    } catch (...) {
+        c->stream = main_stream;
+        throw;
+    }
+    c->stream = main_stream;
+    for (size_t k = 0; k < K; k++) {
+        CUDA_CHECK(cudaEventRecord(c->ev_join[k], c->side[k]));
+        CUDA_CHECK(cudaStreamWaitEvent(main_stream, c->ev_join[k], 0));
+    }
+}
+
 void sweeps(gb_chains* c, int64_t n, int record) {
     CUDA_CHECK(cudaSetDevice(c->device));
-    for (auto& g : c->groups) run_group(c, g, n, record, 0, -1);
+    for_each_group_concurrent(c, [&](Group& g) { run_group(c, g, n, record, 0, -1); });
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -945,7 +999,7 @@ int gb_chains_advance(gb_chains* c, int32_t cw) {
     if (cw < 0) throw gb::Err("Invalid convergence window");
     CUDA_CHECK(cudaSetDevice(c->device));
     c->last_cw = cw;
-    for (auto& g : c->groups) advance_group(c, g, cw);
+    for_each_group_concurrent(c, [&](Group& g) { advance_group(c, g, cw); });
     CUDA_CHECK(cudaGetLastError());
     GB_END
 }

@@ -148,3 +148,52 @@ def test_error_suite_and_mar_reader_match_reference_vectors(res):
         b = oracle.error_suite(cards, s.marginal_list(), np.split(other, np.cumsum(cards)[:-1]))
         for k in a:
             assert a[k] == pytest.approx(b[k], rel=1e-12)
+
+
+# ------------------------------------------------------------------ CLI host logic (no device needed)
+def test_cli_letter26_and_variable_json():
+    """model/variable.go:167-189 naming and the encoding/json field order of model.Variable"""
+    import json
+
+    from grample_b200 import cli
+    assert [cli.letter26(i) for i in (0, 1, 25, 26, 27, 51, 52, 701, 702)] == ["A", "B", "Z", "AA", "AB", "AZ", "BA", "ZZ", "AAA"]
+    line = cli.variable_json(27, 2, -1, [0.25, 0.75], {"JS-Error": 0.5, "Hell-Convergence": 1.5}, True)
+    assert line == '{"ID":27,"Name":"AB","Card":2,"FixedVal":-1,"Marginal":[0.25,0.75],"State":{"Hell-Convergence":1.5,"JS-Error":0.5},"Collapsed":true}'
+    assert json.loads(line)["State"]["JS-Error"] == 0.5
+
+
+def test_cli_per_var_measures_match_oracle():
+    """the per-variable *-Error states (cmd/root.go:651-655) against the oracle's model/error.go restatement"""
+    import numpy as np
+
+    import oracle
+    from grample_b200 import cli
+    rng = np.random.default_rng(3)
+    cards = np.array([2, 3, 5, 2], dtype=np.int32)
+    p, q = rng.random(cards.sum()), rng.random(cards.sum())
+    fixed = np.array([-1, -1, -1, 1], dtype=np.int32)
+    got = cli.per_var_measures(cards, p, q, fixed_p=fixed)
+    offs = np.concatenate([[0], np.cumsum(cards)])
+    for name, which in (("MaxAD", 0), ("AvgAD", 1), ("Hell", 2), ("JS", 3)):
+        for v in range(4):
+            ref = oracle.measure(which, p[offs[v]:offs[v + 1]], q[offs[v]:offs[v + 1]], fixed1=int(fixed[v]))
+            assert abs(got[name][v] - ref) < 1e-12, (name, v)
+    assert got["Hell"][3] == 0.0
+
+
+def test_cli_monitor_gauges_http():
+    """cmd/monitor.go:44-67: expvar names, every path redirects to /debug/vars"""
+    import json
+    import urllib.request
+
+    from grample_b200 import cli
+    mon = cli.Monitor()
+    assert len(mon.snapshot()) == 14
+    mon.set("Burn-In", 7)
+    mon.add("Total-Chain-Count", 2)
+    mon.start("127.0.0.1:18765")
+    try:
+        body = json.loads(urllib.request.urlopen("http://127.0.0.1:18765/", timeout=5).read())
+    finally:
+        mon.stop()
+    assert body["Burn-In"] == 7 and body["Total-Chain-Count"] == 2 and "Last-Max-JSD" in body

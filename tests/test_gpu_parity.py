@@ -613,6 +613,23 @@ def test_cli_sample_adaptive(res, tmp_path):
     lines = trace.read_text().splitlines()
     assert lines[1] == "RunSecs, MaxHell, NegLogMaxHell, MaxJS, NegLogMaxJS, CollapseCount"
     assert len(lines[2].split(",")) == 6  # the row format script/trace_file_process.py parses
+    # final dump (cmd/root.go:640-717): evidence, estimated variables with the State map trace_file_process.py flattens
+    import json
+    i_ev, i_est = lines.index("// EVIDENCE"), lines.index("// VARS (ESTIMATED)")
+    i_par = lines.index("// OPERATING PARAMS")
+    ev = [json.loads(x) for x in lines[i_ev + 1:i_est]]
+    est = [json.loads(x) for x in lines[i_est + 1:i_par]]
+    assert len(ev) == 37 and all(r["FixedVal"] >= 0 for r in ev)
+    assert len(est) == 385 - 37 and list(est[0].keys()) == ["ID", "Name", "Card", "FixedVal", "Marginal", "State", "Collapsed"]
+    keys = set(est[0]["State"].keys())
+    assert {"Hell-Convergence", "JS-Convergence", "MaxAD-Convergence", "AvgAD-Convergence", "Hell-Error", "JS-Error",
+            "MaxAD-Error", "AvgAD-Error", "SOL-MAR[0]", "SOL-MAR[1]"} <= keys
+    assert sum(r["Collapsed"] for r in est) == int(col.sum())
+    assert all(r["State"]["Hell-Convergence"] == 1.0 for r in est if r["Collapsed"])  # chain.go:63-66
+    assert "// MONITOR" in lines and "// ENTIRE MODEL" in lines
+    mon = json.loads(lines[lines.index("// MONITOR") + 1])
+    assert set(mon) == set(cli.Monitor.NAMES) and mon["Total-Chain-Count"] == 2 + int(col.sum()) and mon["Base-Chain-Count"] == 2
+    assert mon["Total-Samples"] > 0 and 0 < mon["Last-Mean-Hellinger"] < 1
 
 
 def test_cli_errors(res):

@@ -5,14 +5,16 @@ R=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gol
 for name, evid in (('Grids_11.uai', False), ('Pedigree_11.uai', True), ('ObjectDetection_11.uai', False)):
     m = gb.Model.from_uai(R+name, use_evidence=evid, device=0)
     for prec in (gb.F64, gb.F32) + ((gb.TABLE,) if m.table_mode()[0] else ()):
-        ch = gb.Chains(m, 13, seed=1, precision=prec, history=True, device=0)
-        ch.burnin(2); ch.advance(6); ch.scan(50) if prec == gb.F64 else None
-        ch.merged_marginals(); ch.convergence()
+        for pc in (False, True):  # resident multi-sweep kernels (TMA-staged tables) and per-colour launches (cp.async ring)
+            ch = gb.Chains(m, 13, seed=1, precision=prec, history=True, device=0, per_colour=pc)
+            ch.burnin(2); ch.advance(6); ch.scan(50) if prec == gb.F64 else None
+            ch.merged_marginals(); ch.convergence()
     nm, v, marg = m.collapse(-1, seed=3)
     ch = gb.Chains([m, nm], [9, 17], seed=2, precision=gb.F32, history=True, device=0)
     ch.advance(4); ch.adapt(m, 2, 8, 4, first_chain_id=64)
     ch.advance(4); ch.merged_marginals()
 a = gb.ising_torus(32, 32)
 m = gb.Model.from_arrays(*a, device=0)
-ch = gb.Chains(m, 2100, seed=1, precision=gb.TABLE, device=0); ch.sweep(3); ch.merged_marginals()
+for pc in (False, True):
+    ch = gb.Chains(m, 2100, seed=1, precision=gb.TABLE, device=0, per_colour=pc); ch.sweep(3); ch.merged_marginals()
 print('sanitizer workload ok')
