@@ -49,6 +49,7 @@ def parse_args():
                     help="table: float64 conditionals tabulated per neighbour configuration, integer sweep")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the small-model secondary numbers")
     return ap.parse_args()
 
 
@@ -110,6 +111,28 @@ def cpu_reference_throughput(arrays, seconds, threads):
     steps = max(20000, int(rate * seconds / threads))
     ups, secs = oracle.throughput(om, n_threads=threads, steps=steps, seed=2, lean=True)
     return ups / secs, ups, secs
+
+
+def small_model_rates(gb, dev, sweeps=500):
+    """variable-updates/sec on the bundled problems of BASELINE.json configs[1..3] (state and tables are
+    on-chip resident: these are issue/latency-bound, not HBM-bound, and are not the headline)"""
+    res = os.path.join(ROOT, "tests", "golden", "res")
+    out = {}
+    for name, evid, n_chains in (("Promedus_11.uai", True, 4096), ("Pedigree_11.uai", True, 8192), ("ObjectDetection_11.uai", False, 8192)):
+        try:
+            m = gb.Model.from_uai(os.path.join(res, name), use_evidence=evid, device=dev)
+            n_free = len(m.schedule()[0])
+            modes = [("f32", gb.F32), ("f64", gb.F64)] + ([("table", gb.TABLE)] if m.table_mode()[0] else [])
+            entry = {"chains": n_chains, "free_vars": n_free}
+            for label, prec in modes:
+                ch = gb.Chains(m, n_chains, seed=1, precision=prec, device=dev)
+                ch.sweep(20)
+                ms = ch.sweep_timed(sweeps)
+                entry[label] = {"us_per_sweep": round(1e3 * ms / sweeps, 2), "updates_per_sec": n_free * n_chains * sweeps / (ms * 1e-3)}
+            out[name.replace(".uai", "") + ("+evid" if evid else "")] = entry
+        except Exception as e:  # never lose the headline line over a secondary number
+            out[name] = {"error": str(e)[:200]}
+    return out
 
 
 def run_reference(args):
@@ -250,6 +273,13 @@ def run_native(args):
             dist.destroy_process_group()
         return
 
+    # ---------------- secondary workloads (reported next to the headline, N = 1 only): the bundled UAI
+    # problems of BASELINE.json configs[1..3] at their chain counts, device time of one 500-sweep launch
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        del chains
+        secondary = small_model_rates(gb, dev)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -277,6 +307,8 @@ def run_native(args):
             "roofline": roofline, "sanity": {"mean_hellinger_vs_uniform": score["MeanHellinger"]}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if secondary is not None:
+        line["secondary"] = secondary
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

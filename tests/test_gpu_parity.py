@@ -97,6 +97,46 @@ def test_init_state(res, name, evid):
         ch.set_state(0, bad)
 
 
+# ------------------------------------------------------------------ committed golden vectors (tests/golden/make_golden.py)
+def _golden(name):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)) as f:
+        return json.load(f)
+
+
+def test_conditionals_match_golden_fixture(res):
+    """K5 against the committed (state, var) -> e[k] vectors: 1e-9 relative in float64, 1e-4 in float32"""
+    models = {}
+    for rec in _golden("conditionals.json"):
+        key = (rec["model"], rec["evidence"])
+        if key not in models:
+            models[key] = gb.Model.from_uai(res(rec["model"]), use_evidence=rec["evidence"], device=0)
+        ref = np.array([float(x) for x in rec["e"]])
+        for prec, tol in ((gb.F64, 1e-9), (gb.F32, 1e-4)):
+            e = models[key].conditional(np.asarray([rec["state"]], dtype=np.int32), [rec["var"]], precision=prec)[0]
+            np.testing.assert_allclose(e / e.sum(), ref / ref.sum(), rtol=tol, atol=0)
+
+
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+def test_trajectories_match_golden_fixture(res, per_colour):
+    """states and counts after n sweeps from committed initial states: f64 kernels (53-bit draws) and table
+    kernels (32-bit draws), both launch paths, bit for bit — no oracle call at run time"""
+    for t in _golden("trajectories.json"):
+        dm = gb.Model.from_uai(res(t["model"]), use_evidence=t["evidence"], device=0)
+        st0 = np.asarray(t["initial"], dtype=np.int32)
+        for bits, prec in ((53, gb.F64), (32, gb.TABLE)):
+            g = t.get("bits%d" % bits)
+            if g is None or (prec == gb.TABLE and not dm.table_mode()[0]):
+                continue
+            ch = gb.Chains(dm, st0.shape[0], seed=t["seed"], first_chain_id=t["first_chain"], precision=prec, device=0,
+                           per_colour=per_colour)
+            ch.set_state(0, st0)
+            ch.sweep(t["n_sweeps"], record=True)
+            assert ch.get_state(0, st0.shape[0]).tolist() == g["final"], (t["model"], bits)
+            assert ch.group_counts(0).tolist() == g["counts"], (t["model"], bits)
+
+
 # ------------------------------------------------------------------ sweeps (K1): bit-exact trajectories
 @pytest.mark.parametrize("name,evid,n_chains,n_sweeps", [
     ("one.uai", False, 4, 50), ("sample.uai", False, 6, 40), ("deterministic.uai", False, 8, 40),
