@@ -77,6 +77,8 @@ _SIGS = {
     "gb_chains_convergence_partial_dev": (C.c_int, [_vp, C.c_int, _f64p, C.POINTER(_vp), _i64p]),
     "gb_convergence_finalize": (C.c_int, [_vp, _f64p, C.c_int32, C.c_int64, _i32p, _f64p]),
     "gb_chains_adapt": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int, C.c_int32, C.c_int32, C.c_uint64, _i32p, _i32p]),
+    "gb_chains_adapt_scores": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _f64p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
+                                         _i32p, _i32p]),
     "gb_chains_get_state": (C.c_int, [_vp, C.c_int32, _i32p]),
     "gb_chains_set_state": (C.c_int, [_vp, C.c_int32, _i32p]),
     "gb_chains_group_counts": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_uint64)]),

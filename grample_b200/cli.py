@@ -182,18 +182,59 @@ def dump_params(args, burn, cw, base, max_iters, seed, dst):
     dst.write("Experiment Mode:        %s\n" % str(bool(args.experiment)).lower())
 
 
+class _Null:
+    def write(self, *_):
+        pass
+
+    def close(self):
+        pass
+
+
+def _dist_env():
+    """(dist module or None, rank, world, local device).  Under torchrun (WORLD_SIZE > 1) the replicas of every
+    reference chain are sharded over one process per GPU (NCCL); rank 0 reports."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None, 0, 1, None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist, dist.get_rank(), world, local
+
+
 def sample(args, out=sys.stdout, monitor=None):
     start = time.time()
+    dist, rank, world, local = _dist_env()
+    if local is not None:
+        args.device = local
+    if rank != 0:
+        out = _Null()
     mon = monitor if monitor is not None else Monitor()
-    if getattr(args, "addr", ""):
+    if getattr(args, "addr", "") and rank == 0:
         mon.start(args.addr)
     try:
-        return _sample(args, out, mon, start)
+        return _sample(args, out, mon, start, dist, rank, world)
     finally:
         mon.stop()
+        if dist is not None and dist.is_initialized() and os.environ.get("GB_KEEP_PROCESS_GROUP") is None:
+            dist.destroy_process_group()
 
 
-def _sample(args, out, mon, start):
+def _agree(dist, device, *flags):
+    """rank 0's view of time-dependent loop decisions, so every rank takes the same branch"""
+    if dist is None:
+        return flags
+    import torch
+    t = torch.tensor([int(f) for f in flags], dtype=torch.int32, device=f"cuda:{device}")
+    dist.broadcast(t, src=0)
+    return tuple(bool(x) for x in t.tolist())
+
+
+def _sample(args, out, mon, start, dist=None, rank=0, world=1):
+    from . import distributed as gbd
     prec = {"f64": F64, "f32": F32, "table": TABLE}[args.precision]
     out.write("Reading model from %s\n" % args.model)
     mod = core.Model.from_uai(args.model, use_evidence=args.evidence, device=args.device)
@@ -211,6 +252,11 @@ def _sample(args, out, mon, start):
         raise core.GrampleError("Experiment mode requires a trace file")
     # defaults derived from n (cmd/root.go:344-363)
     seed = args.seed if args.seed >= 1 else int(time.time_ns() % (1 << 31))
+    if dist is not None:  # a time-derived seed must be the same on every rank
+        import torch
+        t = torch.tensor([seed], dtype=torch.int64, device=f"cuda:{args.device}")
+        dist.broadcast(t, src=0)
+        seed = int(t.item())
     n_free = len(mod.schedule()[0])
     burn = args.burnin if args.burnin >= 0 else 2000 * n
     cw = args.cwin if args.cwin > 0 else 2000
@@ -223,7 +269,10 @@ def _sample(args, out, mon, start):
     if args.sampler != "adaptive" and args.chainadds != 1:
         raise core.GrampleError("Sampler is not adaptive: ChainAdds=%d makes no sense" % args.chainadds)
     mon.set("Chain-Adds-For-Adaptive-Step", args.chainadds)
-    per = (args.replicas + 7) // 8 * 8
+    per = (args.replicas + 7) // 8 * 8          # global chain ids per reference chain / variant
+    shard_first, n_local = gbd.shard(args.replicas, world, rank)
+    if n_local == 0:
+        raise core.GrampleError("--replicas %d leaves rank %d without chains (need >= %d)" % (args.replicas, rank, 8 * world))
 
     out.write("Creating chains and performing burn-in (%d)\n" % burn)
     models = []
@@ -237,10 +286,12 @@ def _sample(args, out, mon, start):
             models.append(mod)
         mon.add("Base-Chain-Count", 1)  # cmd/root.go:428-429
         mon.add("Total-Chain-Count", 1)
-    chains = core.Chains(models, [args.replicas] * base, seed=seed, precision=prec, history=True, device=args.device)
+    chains = core.Chains(models[0], n_local, seed=seed, first_chain_id=shard_first, precision=prec, history=True, device=args.device)
+    for idx in range(1, base):
+        chains.add_group(models[idx], n_local, idx * per + shard_first)
     chains.burnin((burn + n_free - 1) // max(n_free, 1))
     next_id = base * per
-    trace = open(args.trace, "w") if args.trace else None
+    trace = open(args.trace, "w") if (args.trace and rank == 0) else (_Null() if args.trace else None)
     if args.experiment:
         trace.write("// EXPERIMENT RESULTS\nRunSecs, MaxHell, NegLogMaxHell, MaxJS, NegLogMaxJS, CollapseCount\n")
     nl = lambda x: -math.log2(x) if x > 0 else float("inf")
@@ -255,39 +306,42 @@ def _sample(args, out, mon, start):
         now = time.time()
         if args.maxsecs > 0 and now > stop:
             working = False
-        count = chains.total_samples
+        count = gbd.total_samples(chains, dist)
         mon.set("Iterations", count)  # cmd/root.go:492
         mon.set("Total-Samples", count)
         if max_iters > 0 and count > max_iters:
             working = False
-        if now > next_status or not working or args.experiment:
-            if now > next_status or not working:
+        status = now > next_status
+        working, status = _agree(dist, args.device, working, status)
+        if status or not working or args.experiment:
+            if status or not working:
                 mon.set("Run-Time", now - start)  # cmd/root.go:502
                 out.write("  Samps: %12d | RT %12.2fsec\n" % (count, now - start))
             if sol is not None:
-                merged, col = chains.merged_marginals()
+                merged, col = gbd.merged_marginals(chains, dist)
                 score = core.error_suite(cards, sol, merged, fixed2=fixed)
-                if now > next_status or not working:
+                if status or not working:
                     mon.score(score)
                     error_report("", score, True, out)
                 if args.experiment:
                     trace.write("%.1f, %.8f, %.5f, %.8f, %.5f, %d\n" % (now - start, score["MaxHellinger"], nl(score["MaxHellinger"]),
                                                                        score["MaxJSDiverge"], nl(score["MaxJSDiverge"]), int(col.sum())))
-            if now > next_status or not working:
+            if status or not working:
                 next_status = now + 5
-        if keep_adapting and now > no_adapt:
+        (stop_adapt,) = _agree(dist, args.device, keep_adapting and now > no_adapt)
+        if stop_adapt:
             out.write("STOPPING ADAPTATION\n")
             keep_adapting = False
         if working and keep_adapting and args.sampler == "adaptive":
             pre = chains.n_groups
-            chosen = chains.adapt(mod, args.chainadds, args.replicas, cw, first_chain_id=next_id, measure=HELLINGER)
-            next_id += len(chosen) * per
+            chosen, stride = gbd.adapt(chains, mod, args.chainadds, args.replicas, cw, next_id, HELLINGER, dist)
+            next_id += len(chosen) * stride
             if chains.n_groups != pre:
                 mon.set("Total-Chain-Count", chains.n_groups)  # cmd/root.go:557
                 out.write("ADAPT: %d Chains (was %d)\n" % (chains.n_groups, pre))
 
     run_time = time.time() - start
-    merged, col = chains.merged_marginals()  # cmd/root.go:565-571
+    merged, col = gbd.merged_marginals(chains, dist)  # cmd/root.go:565-571
     final = merged.copy()
     for v in range(n):
         final[offs[v]:offs[v + 1]] /= final[offs[v]:offs[v + 1]].sum()
@@ -317,7 +371,7 @@ def _sample(args, out, mon, start):
             error_report("OUR SCORE USING MERLIN AS SOLUTION", core.error_suite(cards, merlin, final, fixed2=fixed), False, out)
     # final convergence under all four measures and per-variable errors (cmd/root.go:638-657)
     for key, measure in (("Hell", HELLINGER), ("JS", JS), ("MaxAD", MAX_ABS), ("AvgAD", MEAN_ABS)):
-        conv = chains.convergence(measure, merged)
+        conv = gbd.convergence(chains, measure, merged, col, cw, dist)
         for v in range(n):
             state[v][key + "-Convergence"] = conv[v]
     if sol is not None:

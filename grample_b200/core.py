@@ -288,6 +288,17 @@ class Chains:
                                     max_groups, C.c_uint64(first_chain_id), _ptr(chosen, _i32p), C.byref(n)))
         return chosen[:n.value].tolist()
 
+    def adapt_scores(self, base_model, new_chain_count, chains_per_new_model, scores, total_chains, first_chain_id,
+                     id_stride=0, max_groups=128):
+        """Adapt with caller-supplied (globally reduced) convergence scores — the multi-GPU form"""
+        chosen = np.zeros(max(new_chain_count, 1), dtype=np.int32)
+        n = C.c_int32()
+        sc = _f64(scores)
+        check(lib().gb_chains_adapt_scores(self.h, base_model.h, new_chain_count, chains_per_new_model, _ptr(sc, _f64p),
+                                           int(total_chains), max_groups, C.c_uint64(first_chain_id), C.c_uint64(id_stride),
+                                           _ptr(chosen, _i32p), C.byref(n)))
+        return chosen[:n.value].tolist()
+
     def _group_chains(self, group):
         # groups keep their chain counts on the C side; recover via state size
         raise NotImplementedError

@@ -1093,14 +1093,18 @@ int gb_convergence_finalize(const gb_model* base, const double* wb, int32_t cw, 
     GB_END
 }
 
-int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
-                    int measure, int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out,
-                    int32_t* n_chosen_out) {
+// scores == nullptr: ChainConvergence over this handle's chains; otherwise the caller's per-variable
+// scores (multi-GPU: computed from the all-reduced within/between sums, identical on every rank, so
+// every rank chooses the same variables); total_chains_hint < 0: this handle's chain count
+static int adapt_impl(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                      int measure, int32_t cw, const double* scores, int64_t total_chains_hint, int32_t max_groups,
+                      uint64_t first_chain_id, uint64_t id_stride, int32_t* chosen_out, int32_t* n_chosen_out) {
     if (n_chosen_out) *n_chosen_out = 0;
     GB_TRY
     CUDA_CHECK(cudaSetDevice(c->device));
     int64_t total = 0;
     for (auto& g : c->groups) total += g.n_chains;
+    if (total_chains_hint >= 0) total = total_chains_hint;
     if (total < 2) throw gb::Err("At least 2 chains required for adaptation");
     if ((int32_t)c->groups.size() >= max_groups) return 0;  // adaptive.go:62-64
     const gb::HostModel& b = base->h;
@@ -1116,10 +1120,14 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
         targets = cand;
     } else {
         std::vector<double> conv(b.n_vars);
-        convergence_partial(c, measure, nullptr);
-        std::vector<double> wb((size_t)2 * b.n_vars);
-        CUDA_CHECK(cudaMemcpy(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        convergence_finalize(b, wb.data(), cw, total, col.data(), conv.data());
+        if (scores) {
+            conv.assign(scores, scores + b.n_vars);
+        } else {
+            convergence_partial(c, measure, nullptr);
+            std::vector<double> wb((size_t)2 * b.n_vars);
+            CUDA_CHECK(cudaMemcpy(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            convergence_finalize(b, wb.data(), cw, total, col.data(), conv.data());
+        }
         // adaptive.go:111-119: sort descending, take from the END (= lowest scores); ties by id
         std::stable_sort(cand.begin(), cand.end(), [&](int32_t x, int32_t y) { return conv[x] > conv[y]; });
         for (int i = 0; i < new_chain_count; i++) targets.push_back(cand[cand.size() - 1 - i]);
@@ -1134,7 +1142,7 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
             delete nm;
             throw;
         }
-        first += (uint64_t)((chains_per_new_model + 7) / 8 * 8);
+        first += id_stride ? id_stride : (uint64_t)((chains_per_new_model + 7) / 8 * 8);
         // adaptive.go:145: NewChain(..., burnIn=2) — two single-variable steps; one un-recorded
         // sweep (>= 2 updates) is the sweep-granular equivalent
         run_group(c, c->groups.back(), 1, 0, 0, -1);
@@ -1144,6 +1152,24 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
     CUDA_CHECK(cudaGetLastError());
     if (n_chosen_out) *n_chosen_out = n_done;
     GB_END
+}
+
+int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                    int measure, int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out,
+                    int32_t* n_chosen_out) {
+    return adapt_impl(c, base, new_chain_count, chains_per_new_model, measure, cw, nullptr, -1, max_groups, first_chain_id, 0,
+                      chosen_out, n_chosen_out);
+}
+
+int gb_chains_adapt_scores(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                           const double* scores, int64_t total_chains, int32_t max_groups, uint64_t first_chain_id,
+                           uint64_t id_stride, int32_t* chosen_out, int32_t* n_chosen_out) {
+    if (!scores) {
+        g_err = "scores must not be NULL";
+        return 1;
+    }
+    return adapt_impl(c, base, new_chain_count, chains_per_new_model, GB_HELLINGER, 0, scores, total_chains, max_groups,
+                      first_chain_id, id_stride, chosen_out, n_chosen_out);
 }
 
 int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out) {

@@ -67,6 +67,29 @@ def convergence(chains, measure, merged, collapsed, cw, dist=None):
     return core.convergence_finalize(chains.base, wb, cw, int(total.item()), collapsed)
 
 
+def adapt(chains, base_model, new_chain_count, replicas, cw, next_variant_id, measure, dist=None, max_groups=128):
+    """(*ConvergenceSampler).Adapt over the chains of every rank.  Each new variant gets `replicas` chains
+    globally, sharded like the base chains; `next_variant_id` is the global id of the new variants' first
+    chain (consecutive variants are `stride` apart).  Every rank computes the same scores from the
+    all-reduced sums, so every rank collapses the same variables.  Returns (chosen variables, stride)."""
+    stride = (replicas + CHAIN_BLOCK - 1) // CHAIN_BLOCK * CHAIN_BLOCK
+    if dist is None or dist.get_world_size() == 1:
+        return chains.adapt(base_model, new_chain_count, replicas, cw, first_chain_id=next_variant_id, measure=measure,
+                            max_groups=max_groups), stride
+    world, rank = dist.get_world_size(), dist.get_rank()
+    first, n = shard(replicas, world, rank)
+    if n == 0:
+        raise core.GrampleError("fewer than %d replicas per variant: rank %d would hold no chains" % (CHAIN_BLOCK * world, rank))
+    merged, col = merged_marginals(chains, dist)
+    import torch
+    total = torch.tensor([chains.n_chains], dtype=torch.int64, device=f"cuda:{chains.device}")
+    dist.all_reduce(total)
+    scores = convergence(chains, measure, merged, col, cw, dist)
+    chosen = chains.adapt_scores(base_model, new_chain_count, n, scores, int(total.item()), next_variant_id + first,
+                                 id_stride=stride, max_groups=max_groups)
+    return chosen, stride
+
+
 def total_samples(chains, dist=None):
     if dist is None or dist.get_world_size() == 1:
         return chains.total_samples

@@ -195,6 +195,17 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
                     int measure, int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out,
                     int32_t* n_chosen_out);
 
+/* Multi-GPU form of Adapt: `scores` [n_vars] are the ChainConvergence scores finalised from the
+ * all-reduced within/between sums (gb_chains_convergence_partial_dev -> all-reduce ->
+ * gb_convergence_finalize), identical on every rank, so every rank picks the same variables;
+ * total_chains = chains over all ranks; chains_per_new_model = THIS rank's share of each new
+ * variant's chains, first_chain_id = global id of this rank's first chain of the first new variant,
+ * id_stride = global chains per variant (distance between consecutive variants' ids; 0 = padded
+ * chains_per_new_model). */
+int gb_chains_adapt_scores(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                           const double* scores, int64_t total_chains, int32_t max_groups, uint64_t first_chain_id,
+                           uint64_t id_stride, int32_t* chosen_out, int32_t* n_chosen_out);
+
 /* state access for tests / the Go shim's LastSample: state[chain][var] int32 (host) */
 int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out);
 int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in);

@@ -543,6 +543,24 @@ def test_adapt(res):
 
 
 # ------------------------------------------------------------------ parity level 2: statistics vs .MAR
+def test_adapt_scores_equals_adapt(res):
+    """the multi-GPU form of Adapt (caller-supplied, globally reduced scores) picks the same variables as
+    the single-device form when fed this device's own scores"""
+    dm, _ = load_pair(res, "Pedigree_11.uai", True)
+    picks = []
+    for mode in ("own", "scores"):
+        ch = gb.Chains([dm, dm], [16, 16], seed=3, precision=gb.F32, history=True, device=0)
+        ch.advance(20)
+        if mode == "own":
+            picks.append(ch.adapt(dm, 5, 16, 20, first_chain_id=64))
+        else:
+            merged, col = ch.merged_marginals()
+            conv = ch.convergence(gb.HELLINGER, merged)
+            picks.append(ch.adapt_scores(dm, 5, 16, conv, ch.n_chains, first_chain_id=64))
+        assert ch.n_groups == 7
+    assert picks[0] == picks[1] and len(picks[0]) == 5
+
+
 def test_objectdetection_marginals_f32(res):
     """the reference algorithm reaches mean Hellinger < 0.01 on ObjectDetection_11 at
     ~1 M recorded updates; the device sampler must do no worse at equal recorded updates."""
