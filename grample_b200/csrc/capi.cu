@@ -443,27 +443,35 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
     if (!(c->flags & GB_CHAINS_HISTORY)) n_half = -1;
     const ResidentPlan plan = resident_plan(c, g);
     const gb::HostModel& h = g.model->h;
-    if (plan.ch && n_sweeps < (1ll << 30)) {
+    if (plan.ch) {
         const int mc = h.max_card;
-        const int32_t ns = (int32_t)n_sweeps;
-        if (c->precision == GB_TABLE) {
-            launch_tab_resident(c, g, plan, ns, record, n_pre, n_half);
-        } else if (c->precision == GB_F32) {
-            if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 4) launch_resident<float, 4, 4>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 8) launch_resident<float, 8, 0>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 16) launch_resident<float, 16, 0>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 32) launch_resident<float, 32, 0>(c, g, plan, ns, record, n_pre, n_half);
-            else launch_resident<float, 64, 0>(c, g, plan, ns, record, n_pre, n_half);
-        } else {
-            if (mc <= 2) launch_resident<double, 2, 4>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 4) launch_resident<double, 4, 4>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 8) launch_resident<double, 8, 0>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 16) launch_resident<double, 16, 0>(c, g, plan, ns, record, n_pre, n_half);
-            else if (mc <= 32) launch_resident<double, 32, 0>(c, g, plan, ns, record, n_pre, n_half);
-            else launch_resident<double, 64, 0>(c, g, plan, ns, record, n_pre, n_half);
+        // One launch runs at most kMaxSweepsPerLaunch sweeps: the CTA's shared-memory counters are 32-bit
+        // (sweeps x chains per CTA must stay below 2^31) and a single kernel should not run for minutes.
+        // A later launch continues the window schedule: its n_pre is shifted (it may go negative).
+        int64_t kMaxSweepsPerLaunch = std::min<int64_t>(1 << 20, ((int64_t)1 << 31) / plan.ch - 1);
+        if (const char* e = std::getenv("GB_MAX_SWEEPS_PER_LAUNCH")) kMaxSweepsPerLaunch = std::max(1, std::atoi(e));  // test knob
+        for (int64_t s0 = 0; s0 < n_sweeps; s0 += kMaxSweepsPerLaunch) {
+            const int32_t ns = (int32_t)std::min<int64_t>(kMaxSweepsPerLaunch, n_sweeps - s0);
+            const int32_t pre = (int32_t)std::max<int64_t>((int64_t)n_pre - s0, -(1ll << 30));
+            if (c->precision == GB_TABLE) {
+                launch_tab_resident(c, g, plan, ns, record, pre, n_half);
+            } else if (c->precision == GB_F32) {
+                if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 4) launch_resident<float, 4, 4>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 8) launch_resident<float, 8, 0>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 16) launch_resident<float, 16, 0>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 32) launch_resident<float, 32, 0>(c, g, plan, ns, record, pre, n_half);
+                else launch_resident<float, 64, 0>(c, g, plan, ns, record, pre, n_half);
+            } else {
+                if (mc <= 2) launch_resident<double, 2, 4>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 4) launch_resident<double, 4, 4>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 8) launch_resident<double, 8, 0>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 16) launch_resident<double, 16, 0>(c, g, plan, ns, record, pre, n_half);
+                else if (mc <= 32) launch_resident<double, 32, 0>(c, g, plan, ns, record, pre, n_half);
+                else launch_resident<double, 64, 0>(c, g, plan, ns, record, pre, n_half);
+            }
+            g.sweep += (uint32_t)ns;
         }
-        g.sweep += (uint32_t)n_sweeps;
         if (record) {
             c->total_samples += n_sweeps * (int64_t)h.order.size() * g.n_chains;
             g.total_samples += n_sweeps * (int64_t)h.order.size() * g.n_chains;

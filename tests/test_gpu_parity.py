@@ -262,6 +262,23 @@ def test_table_sweep_bitexact_wide_blankets(res, name, evid, per_colour):
     assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
 
 
+def test_resident_launch_chunking_keeps_the_window_schedule(res, monkeypatch):
+    """a round split over several resident launches (32-bit shared counters bound the sweeps per launch)
+    gives the same states, counts and half-window histograms as one launch"""
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    out = []
+    for limit in (None, "3"):
+        if limit:
+            monkeypatch.setenv("GB_MAX_SWEEPS_PER_LAUNCH", limit)
+        for prec in (gb.F64, gb.TABLE):
+            ch = gb.Chains(dm, 24, seed=8, precision=prec, history=True, device=0)
+            ch.advance(10)
+            out.append((ch.get_state(0, 24), ch.group_counts(0), ch.group_history(0, 24), ch.total_samples))
+    monkeypatch.delenv("GB_MAX_SWEEPS_PER_LAUNCH")
+    for a, b in ((out[0], out[2]), (out[1], out[3])):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+
+
 def test_table_mode_rejects_unsuitable_models(res):
     dm, _ = load_pair(res, "ObjectDetection_11.uai", False)
     assert dm.table_mode()[0] is False
