@@ -67,8 +67,10 @@ __device__ __forceinline__ Real ld_tab(const Real* p) {
 // float64 follows the reference literally (min-shift only when min < -8, sequential floor with
 // a running total).  float32 uses a max-shift instead (the floor is scale-invariant; min-shift
 // would overflow float32 for wide conditionals) and a multiply in place of the divide.
+// `card` may be smaller than MAXC (entries past it are ignored); callers that know card == MAXC pass it
+// as a constant so that the `k < card` predicates fold away.
 template <typename Real, int MAXC>
-__device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], int card) {
+__device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int card) {
     if constexpr (std::is_same<Real, double>::value) {
         double mn = w[0];
 #pragma unroll
@@ -146,11 +148,12 @@ __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real
 // exponentiate, floor, inverse CDF.  `row` points at the first of the 4 chains in the row of
 // variable 0, `stride` is the row stride in bytes (global layout: n_pad; shared-memory-resident
 // layout: chains per CTA).  CW = chains whose weight vectors are held in registers at once.
-template <typename Real, int MAXC, int CW, bool GT = true>
-__device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
-                                                const uint32_t stride, const int v, const int card, const uint32_t chain0,
-                                                const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
-                                                int (&x)[4]) {
+template <typename Real, int MAXC, int CW, bool GT, bool EXACT>
+__device__ __forceinline__ void lse_update_quad_impl(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
+                                                     const uint32_t stride, const int v, const int card_rt, const uint32_t chain0,
+                                                     const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
+                                                     int (&x)[4]) {
+    const int card = EXACT ? MAXC : card_rt;  // EXACT: the cardinality is the compile-time bound, predicates fold
     const int32_t* __restrict__ prog = m.prog + __ldg(m.prog_off + v);
     const int nf = __ldg(prog);
     Real u[4];
@@ -201,13 +204,38 @@ __device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* _
     }
 }
 
+// Dispatch on the variable's cardinality: binary and ternary variables (the bulk of the UAI problems) run
+// bodies unrolled to exactly their cardinality instead of predicated-off iterations up to MAXC.  Same
+// arithmetic in the same order, so trajectories do not change.
+template <typename Real, int MAXC, int CW, bool GT = true>
+__device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
+                                                const uint32_t stride, const int v, const int card, const uint32_t chain0,
+                                                const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
+                                                int (&x)[4]) {
+    if constexpr (MAXC > 2) {
+        if (card == 2) {
+            lse_update_quad_impl<Real, 2, CW, GT, true>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+            return;
+        }
+    }
+    if constexpr (MAXC > 3) {
+        if (card == 3) {
+            lse_update_quad_impl<Real, 3, CW, GT, true>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+            return;
+        }
+    }
+    if (card == MAXC) lse_update_quad_impl<Real, MAXC, CW, GT, true>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+    else lse_update_quad_impl<Real, MAXC, CW, GT, false>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+}
+
 // One variable x ONE chain (same arithmetic and draws as lse_update_quad for that chain): used by the
 // resident kernel for high-cardinality models, where one thread per chain gives 4x the parallelism
 // and a quarter of the registers.  `cell` points at this chain's byte in the row of variable 0.
-template <typename Real, int MAXC, bool GT = true>
-__device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
-                                              const uint32_t stride, const int v, const int card, const uint32_t chain,
-                                              const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+template <typename Real, int MAXC, bool GT, bool EXACT>
+__device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
+                                                   const uint32_t stride, const int v, const int card_rt, const uint32_t chain,
+                                                   const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+    const int card = EXACT ? MAXC : card_rt;
     const int32_t* __restrict__ p = m.prog + __ldg(m.prog_off + v);
     const int nf = __ldg(p++);
     Real u;
@@ -233,6 +261,24 @@ __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __r
     }
     stabilise_exp_floor<Real, MAXC>(w, card);
     return inverse_cdf<Real, MAXC>(w, card, u);
+}
+
+// cardinality buckets of the one-thread-per-chain body: exact unrolls for 2, 3, 11 (ObjectDetection) and MAXC
+template <typename Real, int MAXC, bool GT = true>
+__device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
+                                              const uint32_t stride, const int v, const int card, const uint32_t chain,
+                                              const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+    if constexpr (MAXC > 2) {
+        if (card == 2) return lse_update_one_impl<Real, 2, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    }
+    if constexpr (MAXC > 3) {
+        if (card == 3) return lse_update_one_impl<Real, 3, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    }
+    if constexpr (MAXC > 11) {
+        if (card == 11) return lse_update_one_impl<Real, 11, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    }
+    if (card == MAXC) return lse_update_one_impl<Real, MAXC, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    return lse_update_one_impl<Real, MAXC, GT, false>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
 }
 
 // One launch = one colour of one group.  Work item = (variable of the colour, quad of 4 chains);
