@@ -337,8 +337,7 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_s
     int max_col = 1;
     for (size_t i = 0; i + 1 < hm.colour_off.size(); i++) max_col = std::max(max_col, hm.colour_off[i + 1] - hm.colour_off[i]);
     const int64_t items = (int64_t)max_col * (CW == 0 ? ch : ch / 4);
-    int threads = 32;
-    while (threads < 256 && threads < items) threads *= 2;
+    const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
     static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
     size_t& configured = configured_dev[c->device % kMaxDevices];
     if (smem > configured) {
@@ -423,8 +422,7 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     int max_col = 1;
     for (size_t i = 0; i + 1 < h.colour_off.size(); i++) max_col = std::max(max_col, h.colour_off[i + 1] - h.colour_off[i]);
     const int64_t items = (int64_t)max_col * (p.ch / 8);
-    int threads = 32;
-    while (threads < 256 && threads < items) threads *= 2;
+    const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
     static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
     size_t& configured = configured_dev[c->device % kMaxDevices];
     if (p.smem > configured) {
