@@ -167,6 +167,23 @@ def test_sweep_bitexact_f64(res, name, evid, n_chains, n_sweeps, per_colour):
     assert np.array_equal(per_var, exp)
 
 
+@pytest.mark.parametrize("name,evid,n_chains", [("Grids_11.uai", False, 256), ("Promedus_11.uai", True, 128),
+                                                ("Pedigree_11.uai", True, 160), ("ObjectDetection_11.uai", False, 128)])
+def test_sweep_bitexact_f64_many_chains_per_colour(res, name, evid, n_chains):
+    """k_sweep_colour with >= 128 chains per group: whole warps work on one variable (warp-aggregated
+    count updates), ragged last warps mix variables — bit-exact either way"""
+    dm, om = load_pair(res, name, evid)
+    order, _ = dm.schedule()
+    seed, first, n_sweeps = 77, 32, 2
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0, per_colour=True)
+    st0 = ch.get_state(0, n_chains)
+    ch.sweep(n_sweeps, record=True)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, ocounts = samp.sweep_run(order, seed, first, st0, 0, n_sweeps, bits=53, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+
+
 # ------------------------------------------------------------------ table mode (K1-table)
 def expected_threshold(e):
     """largest 32-bit draw t with (t * 2^-32) * tot <= e0 (sampler.go:115-123 evaluated in float64)"""
