@@ -20,7 +20,7 @@ def main():
     for name, evid, chains, bytes_per_update in CASES:
         m = gb.Model.from_uai(os.path.join(RES, name), use_evidence=evid, device=0)
         order, coff = m.schedule()
-        modes = [("f32", gb.F32), ("f64", gb.F64)] + ([("table", gb.TABLE)] if m.table_mode()[0] else [])
+        modes = [("f32", gb.F32), ("f64", gb.F64), ("hybrid", gb.HYBRID)] + ([("table", gb.TABLE)] if m.table_mode()[0] else [])
         for label, prec in modes:
             ch = gb.Chains(m, chains, seed=1, precision=prec, device=0)
             ch.sweep(20)

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgrample_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "grample_b200.h")
 
-F64, F32, TABLE = 0, 1, 2
+F64, F32, TABLE, HYBRID = 0, 1, 2, 3
 MAX_ABS, MEAN_ABS, HELLINGER, JS = 0, 1, 2, 3
 CHAINS_HISTORY = 1
 CHAINS_PER_COLOUR = 2
@@ -37,6 +37,7 @@ _SIGS = {
     "gb_model_create": (C.c_int, [C.c_int32, _i32p, _i32p, C.c_int32, _i32p, _i32p, _i64p, _f64p, C.c_int, C.POINTER(_vp)]),
     "gb_model_load_uai": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_vp)]),
     "gb_model_destroy": (None, [_vp]),
+    "gb_model_hybrid_mask": (C.c_int, [_vp, _i32p]),
     "gb_model_n_vars": (C.c_int, [_vp, _i32p]),
     "gb_model_n_funcs": (C.c_int, [_vp, _i32p]),
     "gb_model_total_card": (C.c_int, [_vp, _i32p]),

@@ -18,7 +18,7 @@ import time
 import numpy as np
 
 from . import core
-from ._lib import F32, F64, HELLINGER, JS, MAX_ABS, MEAN_ABS, TABLE
+from ._lib import F32, F64, HELLINGER, HYBRID, JS, MAX_ABS, MEAN_ABS, TABLE
 
 
 def letter26(n):
@@ -158,7 +158,7 @@ def build_parser():
     s.add_argument("-x", "--maxsecs", type=int, default=300)
     s.add_argument("-p", "--experiment", action="store_true")
     s.add_argument("--replicas", type=int, default=1024, help="device chains behind each reference chain")
-    s.add_argument("--precision", default="f32", choices=["f64", "f32", "table"])
+    s.add_argument("--precision", default="f32", choices=["f64", "f32", "table", "hybrid"])
     s.add_argument("--device", type=int, default=0)
     s.add_argument("--addr", default="", help="ip:port for the expvar-style monitor (cmd/monitor.go); empty = no HTTP server")
     return ap
@@ -235,7 +235,7 @@ def _agree(dist, device, *flags):
 
 def _sample(args, out, mon, start, dist=None, rank=0, world=1):
     from . import distributed as gbd
-    prec = {"f64": F64, "f32": F32, "table": TABLE}[args.precision]
+    prec = {"f64": F64, "f32": F32, "table": TABLE, "hybrid": HYBRID}[args.precision]
     out.write("Reading model from %s\n" % args.model)
     mod = core.Model.from_uai(args.model, use_evidence=args.evidence, device=args.device)
     n, cards, fixed = mod.n_vars, mod.cards, mod.fixed

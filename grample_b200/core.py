@@ -130,6 +130,12 @@ class Model:
         check(lib().gb_model_table_mode(self.h, C.byref(ok), C.byref(n)))
         return bool(ok.value), n.value
 
+    def hybrid_mask(self):
+        """int32 [n_vars]: 1 where precision=HYBRID samples the variable from a threshold table"""
+        out = np.zeros(self.n_vars, dtype=np.int32)
+        check(lib().gb_model_hybrid_mask(self.h, _ptr(out, _i32p)))
+        return out
+
     def thresholds(self, var):
         n = C.c_int32()
         check(lib().gb_model_thresholds(self.h, int(var), C.byref(n), None))

@@ -112,15 +112,14 @@ struct gb_model {
         d_order = up(h.order);
         d_colour_off = up(h.colour_off);
     }
-    // table mode: evaluate every (variable, neighbour configuration) conditional once on the device
-    void ensure_tab() {
-        if (tab_built) return;
-        if (device < 0) throw gb::Err("table mode needs a device-resident model (there is no CPU fallback)");
-        if (!h.tab_ok) throw gb::Err("table mode does not apply to this model: " + h.tab_why);
+    // thresholds: evaluate every (tabulated variable, neighbour configuration) conditional once on the device
+    bool thr_built = false;
+    void ensure_thresholds() {
+        if (thr_built) return;
+        if (device < 0) throw gb::Err("table / hybrid mode needs a device-resident model (there is no CPU fallback)");
         require_device(device);
         tab.tp_off = up(h.tp_off);
         tab.tprog = up(h.tprog);
-        tab.trec = up(h.trec);
         tab.n_order = (int32_t)h.order.size();
         tab.n_thr = (int32_t)h.n_thresholds;
         uint32_t* thr = nullptr;
@@ -128,11 +127,23 @@ struct gb_model {
         allocs.push_back(thr);
         tab.thr = thr;
         const int n = (int)h.order.size();
-        gb::k_build_thresholds<<<std::max(1, std::min((n + 127) / 128, 148 * 16)), 128>>>(dev, tab, d_order, n);
-        CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaDeviceSynchronize());
+        if (h.n_tab_vars > 0) {
+            gb::k_build_thresholds<<<std::max(1, std::min((n + 127) / 128, 148 * 16)), 128>>>(dev, tab, d_order, n);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaDeviceSynchronize());
+        }
+        thr_built = true;
+    }
+    // table mode proper: every sampled variable tabulated with <= 256 configurations, fixed-size records
+    void ensure_tab() {
+        if (tab_built) return;
+        if (!h.tab_ok) throw gb::Err("table mode does not apply to this model: " + h.tab_why);
+        ensure_thresholds();
+        tab.trec = up(h.trec);
         tab_built = true;
     }
+    // hybrid mode tabulates what qualifies (binary, <= 4096 configurations) in models whose cardinalities are <= 4
+    bool hybrid_tables() const { return h.max_card <= 4 && h.n_tab_vars > 0; }
 };
 
 namespace {
@@ -213,6 +224,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     if (n_chains < 1) throw gb::Err("a chain group needs at least 1 chain");
     if (first_chain % 8) throw gb::Err("first_chain_id must be a multiple of 8 (chains share Philox calls in blocks of 8)");
     if (c->precision == GB_TABLE) model->ensure_tab();
+    if (c->precision == GB_HYBRID && model->hybrid_tables()) model->ensure_thresholds();
     if (!c->groups.empty() && (model->h.n_vars != c->base().n_vars || model->h.card != c->base().card))
         throw gb::Err("Cannot merge chain with different variables");
     if (model->h.order.empty()) throw gb::Err("No Variables to select");
@@ -251,8 +263,9 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
 template <typename Real, int MAXC, int CW>
 void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half) {
     const int64_t items = (int64_t)n * (g.n_pad / 4);
+    const int hybrid = c->precision == GB_HYBRID && g.model->hybrid_tables();
     gb::k_sweep_colour<Real, MAXC, CW><<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, d_vars, n,
-                                                                                   g.sweep, record, hist_half);
+                                                                                   g.sweep, record, hist_half, g.model->tab, hybrid);
     c->launches++;
 }
 
@@ -347,7 +360,7 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_s
     const gb::HostModel& h = g.model->h;
     gb::k_sweep_resident<Real, MAXC, CW, TS><<<g.n_pad / ch, threads, smem, c->stream>>>(
         g.model->dev, g.dev, g.model->d_order, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, ch, g.sweep, n_sweeps,
-        record, n_pre, n_half);
+        record, n_pre, n_half, g.model->tab, (int)(c->precision == GB_HYBRID && g.model->hybrid_tables()));
     c->launches++;
 }
 
@@ -864,11 +877,17 @@ int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out)
     if (n_thresholds_out) *n_thresholds_out = m->h.n_thresholds;
     GB_END
 }
+int gb_model_hybrid_mask(const gb_model* m, int32_t* mask_out) {
+    GB_TRY
+    const bool on = m->hybrid_tables();
+    for (int v = 0; v < m->h.n_vars; v++) mask_out[v] = (on && m->h.tp_off[v] >= 0) ? 1 : 0;
+    GB_END
+}
 int gb_model_thresholds(gb_model* m, int32_t var, int32_t* n_out, uint32_t* out) {
     GB_TRY
     if (var < 0 || var >= m->h.n_vars) throw gb::Err("Invalid variable index");
-    m->ensure_tab();
-    if (m->h.tp_off[var] < 0) throw gb::Err("variable is not sampled");
+    m->ensure_thresholds();
+    if (m->h.tp_off[var] < 0) throw gb::Err("variable has no threshold table (not sampled, not binary, or too many neighbour configurations)");
     const int32_t* tp = m->h.tprog.data() + m->h.tp_off[var];
     int n = 1;
     for (int i = 0; i < tp[0]; i++) n *= m->h.card[tp[2 + 2 * i]];
@@ -922,7 +941,7 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
                      gb_chains** out) {
     GB_TRY
     if (n_groups < 1) throw gb::Err("at least one chain group is required");
-    if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE) throw gb::Err("unknown precision");
+    if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE && precision != GB_HYBRID) throw gb::Err("unknown precision");
     require_device(device);
     auto c = std::make_unique<gb_chains>();
     c->device = device;

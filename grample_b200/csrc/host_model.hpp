@@ -30,6 +30,7 @@ struct Err : std::runtime_error {
 constexpr int kNeighborVarMax = 12;
 constexpr int64_t kMaxTabSize = 1 << 23;
 constexpr int kMaxCard = 64;
+constexpr int64_t kTabWideCfg = 4096;  // hybrid mode tabulates binary variables with up to this many neighbour configurations
 constexpr int kTabTile = 64;  // sweep positions per CTA tile of k_sweep_tab (<= 4 neighbours); the locality order groups by it
 
 struct Factor {
@@ -62,6 +63,7 @@ struct HostModel {
     std::vector<int32_t> trec;                     // per sweep position: kTabRec words (see kernels.cuh)
     int64_t n_thresholds = 0;
     int tab_max_nbr = 0;                           // largest n_nbr over the sampled variables
+    int32_t n_tab_vars = 0;                        // sampled variables with a threshold table (binary, <= kTabWideCfg configurations)
 
     bool sampled(int v) const { return fixed[v] < 0 && !collapsed[v]; }
 
@@ -134,42 +136,40 @@ struct HostModel {
         tab_why.clear();
         tp_off.assign(n_vars, -1);
         tprog.clear();
+        trec.clear();
         n_thresholds = 0;
+        n_tab_vars = 0;
+        tab_max_nbr = 0;
         for (int v : order) {
-            if (card[v] != 2) {
-                tab_ok = false;
-                tab_why = "variable " + std::to_string(v) + " has cardinality " + std::to_string(card[v]) + " (table mode needs binary sampled variables)";
-                break;
-            }
+            std::string why;
+            if (card[v] != 2)
+                why = "variable " + std::to_string(v) + " has cardinality " + std::to_string(card[v]) + " (table mode needs binary sampled variables)";
             int64_t cfgs = 1;
             std::vector<int32_t> words;
-            for (int32_t u : nbrs[v]) {
-                if (u == v || fixed[u] >= 0 || card[u] == 1) continue;  // constant neighbours fold into the table
-                words.push_back(u);
-                words.push_back((int32_t)cfgs);
-                cfgs *= card[u];
-                if (cfgs > 256) break;
+            if (why.empty())
+                for (int32_t u : nbrs[v]) {
+                    if (u == v || fixed[u] >= 0 || card[u] == 1) continue;  // constant neighbours fold into the table
+                    words.push_back(u);
+                    words.push_back((int32_t)cfgs);
+                    cfgs *= card[u];
+                    if (cfgs > kTabWideCfg) break;
+                }
+            if (why.empty() && cfgs > 256) why = "variable " + std::to_string(v) + " has more than 256 neighbour configurations";
+            if (!why.empty() && tab_ok) {
+                tab_ok = false;  // GB_TABLE needs every sampled variable narrow; GB_HYBRID takes what qualifies
+                tab_why = why;
             }
-            if (cfgs > 256) {
-                tab_ok = false;
-                tab_why = "variable " + std::to_string(v) + " has more than 256 neighbour configurations";
-                break;
-            }
+            if (card[v] != 2 || cfgs > kTabWideCfg) continue;
             tp_off[v] = (int32_t)tprog.size();
             tprog.push_back((int32_t)words.size() / 2);
             tprog.push_back((int32_t)n_thresholds);
             tprog.insert(tprog.end(), words.begin(), words.end());
             n_thresholds += cfgs;
+            n_tab_vars++;
         }
-        if (!tab_ok) {
-            tp_off.assign(n_vars, -1);
-            tprog.clear();
-            n_thresholds = 0;
-            return;
-        }
+        if (!tab_ok) return;
         // fixed-size record per sweep position: {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
         // (2^n_nbr <= 256 configurations => n_nbr <= 8)
-        tab_max_nbr = 0;
         trec.assign(order.size() * 20, 0);
         for (size_t j = 0; j < order.size(); j++) {
             const int v = order[j];

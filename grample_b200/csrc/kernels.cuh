@@ -48,6 +48,28 @@ struct DevGroup {
     uint32_t seed_lo, seed_hi;
 };
 
+struct DevTab {
+    const int32_t* tp_off;  // [n_vars]
+    const int32_t* tprog;   // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
+    uint32_t* thr;          // [n_thresholds]
+    const int32_t* trec;    // [n_order][kTabRec] fixed-size record per sweep position
+    int32_t n_order, n_thr;
+};
+
+
+__device__ __forceinline__ Philox4 philox_wide(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+
 template <typename Real>
 __device__ __forceinline__ const Real* tables_of(const DevModel& m);
 template <>
@@ -281,12 +303,53 @@ __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __r
     return lse_update_one_impl<Real, MAXC, GT, false>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
 }
 
+// Hybrid mode (GB_HYBRID): a binary variable with a threshold table (<= 4096 configurations of its free
+// neighbours) is updated from the table — float64 conditional evaluated once per configuration, 32-bit
+// draw, same tie rule and Philox fields as the table kernels — and every other variable by the float64
+// log-sum-exp path.  One variable x 4 consecutive chains; tpo = the variable's offset in DevTab::tprog.
+__device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t tpo, const uint8_t* row, const uint32_t stride,
+                                                const int v, const uint32_t chain0, const uint32_t sweep, const uint32_t seed_lo,
+                                                const uint32_t seed_hi, int (&x)[4]) {
+    const int32_t* __restrict__ tp = t.tprog + tpo;
+    const int nn = __ldg(tp), thr_off = __ldg(tp + 1);
+    uint32_t idx[4] = {0u, 0u, 0u, 0u};
+    for (int i = 0; i < nn; i++) {
+        const int ov = __ldg(tp + 2 + 2 * i);
+        const uint32_t os = (uint32_t)__ldg(tp + 3 + 2 * i);
+        const uint32_t s4 = *reinterpret_cast<const uint32_t*>(row + (size_t)ov * stride);
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++) idx[ci] += ((s4 >> (8 * ci)) & 0xffu) * os;
+    }
+    // chains 8b .. 8b+7 share a call; this quad owns fields 4h .. 4h+3 (h = second quad of the block)
+    const bool second = (chain0 >> 2) & 1u;
+    const Philox4 a = philox_wide((uint32_t)v, sweep, chain0 >> 3, kTagDraw16Hi, seed_lo, seed_hi);
+    const uint32_t wa[2] = {second ? a.z : a.x, second ? a.w : a.y};
+    uint32_t T[4], hi[4];
+    bool tie = false;
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++) {
+        T[ci] = __ldg(t.thr + thr_off + idx[ci]);
+        hi[ci] = (wa[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
+        x[ci] = hi[ci] > (T[ci] >> 16) ? 1 : 0;
+        tie |= hi[ci] == (T[ci] >> 16);
+    }
+    if (tie) {  // draw > threshold <=> high halves equal and lo16 > (T & 0xffff)
+        const Philox4 b = philox_wide((uint32_t)v, sweep, chain0 >> 3, kTagDraw16Lo, seed_lo, seed_hi);
+        const uint32_t wb[2] = {second ? b.z : b.x, second ? b.w : b.y};
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++) {
+            const uint32_t lo = (wb[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
+            if (hi[ci] == (T[ci] >> 16) && lo > (T[ci] & 0xffffu)) x[ci] = 1;
+        }
+    }
+}
+
 // One launch = one colour of one group.  Work item = (variable of the colour, quad of 4 chains);
 // consecutive threads take consecutive quads of the same variable.
 template <typename Real, int MAXC, int CW>
 __global__ void __launch_bounds__(256)
 k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ vars, const int32_t n_vars_c,
-               const uint32_t sweep, const int record, const int hist_half) {
+               const uint32_t sweep, const int record, const int hist_half, const DevTab t, const int hybrid) {
     const Real* __restrict__ tab = tables_of<Real>(m);
     const int32_t n_quads = g.n_pad >> 2;
     const int64_t total = (int64_t)n_vars_c * n_quads;
@@ -302,8 +365,12 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
         const int32_t card = __ldg(m.card + v);
         const uint32_t chain0 = (uint32_t)(g.first_chain + 4u * (uint32_t)q);
         int x[4];
-        lse_update_quad<Real, MAXC, CW>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo,
-                                        g.seed_hi, x);
+        const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
+        if (tpo >= 0)
+            tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
+        else
+            lse_update_quad<Real, MAXC, CW>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo,
+                                            g.seed_hi, x);
         const uint32_t packed = (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
         *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + 4 * q) = packed;
 
@@ -381,7 +448,7 @@ __global__ void __launch_bounds__(256)
 k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
-                 const int32_t n_half) {
+                 const int32_t n_half, const DevTab t, const int hybrid) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     uint8_t* s_state = smem;                                                                  // [n_vars][CH]
@@ -445,8 +512,12 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const int lchain = cta_chain + 4 * q;  // local chain index of the quad
                     const uint32_t chain0 = (uint32_t)(g.first_chain + (uint64_t)lchain);
                     int x[4];
-                    lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep,
-                                                                    g.seed_lo, g.seed_hi, x);
+                    const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
+                    if (tpo >= 0)
+                        tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
+                    else
+                        lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep,
+                                                                        g.seed_lo, g.seed_hi, x);
                     *reinterpret_cast<uint32_t*>(s_state + (size_t)v * CH + 4 * q) =
                         (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
                     if (record) {
@@ -487,18 +558,11 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
 // by k_build_thresholds and stored as the largest 32-bit draw that still selects value 0 under
 // the reference's inverse-CDF rule (sampler.go:115-123: r = U*tot, r <= e0).  The sweep itself is
 // integer work: gather neighbour bytes -> configuration index -> threshold -> compare.
-struct DevTab {
-    const int32_t* tp_off;  // [n_vars]
-    const int32_t* tprog;   // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
-    uint32_t* thr;          // [n_thresholds]
-    const int32_t* trec;    // [n_order][kTabRec] fixed-size record per sweep position
-    int32_t n_order, n_thr;
-};
-
 __global__ void __launch_bounds__(128)
 k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__ order, const int32_t n_order) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_order; j += gridDim.x * blockDim.x) {
         const int v = order[j];
+        if (t.tp_off[v] < 0) continue;  // hybrid mode: this variable is sampled by the log-sum-exp path
         const int32_t* tp = t.tprog + t.tp_off[v];
         const int nn = tp[0], thr_off = tp[1];
         int n_cfg = 1;
@@ -544,18 +608,6 @@ k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__
 // thresholds are staged in shared memory.  One Philox call yields the high halves of 8 draws; the
 // low halves are generated only when a high half ties with its threshold (probability 2^-16).
 constexpr int kTabRec = 20;  // {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
-
-__device__ __forceinline__ Philox4 philox_wide(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return Philox4{c0, c1, c2, c3};
-}
 
 // NN = neighbour slots read per variable (4 or 8); records pad unused slots with the variable
 // itself at stride 0, so the loads are unconditional and branch-free.

@@ -47,7 +47,12 @@ enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 }
  *            stored as 32-bit inverse-CDF thresholds; the sweep is integer work (gather, index,
  *            compare) with 32-bit draws.  Applies when every sampled variable is binary with at
  *            most 256 joint configurations of its free neighbours (gb_model_table_mode). */
-enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2 };
+/*   GB_HYBRID per variable: binary variables with at most 4096 joint configurations of their free
+ *            neighbours are sampled from threshold tables as in GB_TABLE (float64 conditional per
+ *            configuration, 32-bit draws), every other variable by the GB_F64 path (53-bit draws) —
+ *            reference float64 arithmetic throughout, for models GB_TABLE rejects (collapsed variants
+ *            with wide blankets, mixed cardinalities).  Models with a cardinality above 4 run as GB_F64. */
+enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2, GB_HYBRID = 3 };
 /* gb_chains_create flags */
 #define GB_CHAINS_HISTORY 1u /* keep per-chain half-window histograms (needed by gb_chains_convergence*) */
 #define GB_CHAINS_PER_COLOUR 2u /* always launch one kernel per colour (disables the shared-memory-resident multi-sweep kernels small models use; same results) */
@@ -89,6 +94,8 @@ int gb_model_function_count(const gb_model* m, int32_t var, int32_t* out);
 int gb_model_schedule(const gb_model* m, int32_t* n_order, int32_t* n_colours, int32_t* order, int32_t* colour_off);
 
 /* whether GB_TABLE applies to this model, and the total number of tabulated configurations */
+/* hybrid mode: mask_out[n_vars] = 1 where the variable is sampled from a threshold table under GB_HYBRID */
+int gb_model_hybrid_mask(const gb_model* m, int32_t* mask_out);
 int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out);
 /* the tabulated thresholds of one sampled variable (builds the tables on first use): value 0 is
  * drawn iff the 32-bit draw <= threshold[configuration]; configuration = sum(state[nbr_i] * stride_i)

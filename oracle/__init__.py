@@ -442,14 +442,21 @@ class Sampler:
         n = lib().orc_collapsed_neighbors(self.h, int(var), _p(out, C.c_int))
         return out[:n].tolist()
 
-    def sweep_run(self, order, seed, chain0, states, sweep0, n_sweeps, bits=53, record=True, counts=None):
-        """Device-schedule sweeps (oracle/sweep.hpp).  states: [n_chains, n_vars] int32 (updated copy returned)."""
+    def sweep_run(self, order, seed, chain0, states, sweep0, n_sweeps, bits=53, record=True, counts=None, var_bits=None):
+        """Device-schedule sweeps (oracle/sweep.hpp).  states: [n_chains, n_vars] int32 (updated copy returned).
+        var_bits: optional per-variable draw widths (32 / 53) — the device's hybrid mode."""
         order = _ia(order)
         st = _ia(states).copy()
         n_chains = st.shape[0]
         if counts is None:
             counts = np.zeros(int(self.model.cards.sum()))
         counts = _da(counts).copy()
+        if var_bits is not None:
+            vb = _ia(var_bits)
+            _chk(lib().orc_sweep_run_mixed(self.h, _p(order, C.c_int), len(order), C.c_ulonglong(seed), C.c_uint(chain0),
+                                           n_chains, C.c_uint(sweep0), C.c_uint(n_sweeps), _p(vb, C.c_int), int(record),
+                                           _p(st, C.c_int), _p(counts, C.c_double)))
+            return st, counts
         _chk(lib().orc_sweep_run(self.h, _p(order, C.c_int), len(order), C.c_ulonglong(seed), C.c_uint(chain0),
                                  n_chains, C.c_uint(sweep0), C.c_uint(n_sweeps), bits, int(record),
                                  _p(st, C.c_int), _p(counts, C.c_double)))

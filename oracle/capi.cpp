@@ -596,6 +596,21 @@ int orc_sweep_run(void* sampler, const int* order, int n_order, unsigned long lo
     ORC_END
 }
 
+int orc_sweep_run_mixed(void* sampler, const int* order, int n_order, unsigned long long seed, unsigned chain0,
+                        int n_chains, unsigned sweep0, unsigned n_sweeps, const int* var_bits, int record, int* states,
+                        double* counts) {
+    ORC_TRY
+    auto* h = (SamplerH*)sampler;
+    std::vector<int> ord(order, order + n_order), off;
+    int acc = 0;
+    for (auto& v : h->model->vars) { off.push_back(acc); acc += v.card; }
+    size_t nv = h->model->vars.size();
+    for (int c = 0; c < n_chains; c++)
+        sweep_chain(*h->simple, ord, seed, chain0 + (unsigned)c, sweep0, n_sweeps, 53, record != 0,
+                    states + (size_t)c * nv, off, counts, var_bits);
+    ORC_END
+}
+
 int orc_scan_run(void* sampler, const int* order, int n_order, unsigned long long seed, unsigned chain0, int n_chains,
                  unsigned long long step0, long long n_steps, int record, int* states, double* counts) {
     ORC_TRY

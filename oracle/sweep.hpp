@@ -57,16 +57,18 @@ struct FixedUniform : Generator {
 
 // Runs `n_sweeps` systematic sweeps over `order` for one chain.  `state` is updated in
 // place; counts[off[v] + k] is incremented for every recorded draw when `record`.
+// var_bits (optional, per variable): draw width of that variable — the device's hybrid mode draws 32 bits
+// for tabulated variables and 53 bits for the others; nullptr = `bits` for every variable.
 inline void sweep_chain(GibbsSimple& gs, const std::vector<int>& order, uint64_t seed, uint32_t chain,
                         uint32_t sweep0, uint32_t n_sweeps, int bits, bool record, int* state,
-                        const std::vector<int>& count_off, double* counts) {
+                        const std::vector<int>& count_off, double* counts, const int* var_bits = nullptr) {
     FixedUniform fu;
     UniformSampler us(&fu, 1);
     std::vector<double> w;
     for (uint32_t s = 0; s < n_sweeps; s++) {
         for (int v : order) {
             gs.conditional(v, state, w);
-            fu.next = philox_uniform(seed, chain, sweep0 + s, (uint32_t)v, bits);
+            fu.next = philox_uniform(seed, chain, sweep0 + s, (uint32_t)v, var_bits ? var_bits[v] : bits);
             int k;
             try {
                 k = us.weighted_sample((int64_t)w.size(), w.data(), w.size());

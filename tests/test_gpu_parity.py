@@ -296,6 +296,38 @@ def test_resident_launch_chunking_keeps_the_window_schedule(res, monkeypatch):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
 
 
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+@pytest.mark.parametrize("name,evid,collapse", [("Pedigree_11.uai", True, None), ("Pedigree_11.uai", True, "random"),
+                                                ("Promedus_11.uai", True, "random"), ("Grids_11.uai", False, None),
+                                                ("dv-rel_1.uai", True, None), ("ObjectDetection_11.uai", False, None)])
+def test_hybrid_sweep_bitexact(res, name, evid, collapse, per_colour):
+    """GB_HYBRID: tabulated variables (32-bit draws against float64 thresholds) and log-sum-exp variables
+    (53-bit draws) in one sweep, on plain models and collapsed variants (wide blankets), both launch paths,
+    against the oracle with the same per-variable draw widths"""
+    dm, om = load_pair(res, name, evid)
+    samp = oracle.Sampler(oracle.Generator(1), om, collapsed=collapse is not None)
+    if collapse:
+        dm, v, _ = dm.collapse(-1, seed=11)
+        samp.collapse(v)
+    mask = dm.hybrid_mask()
+    order, _ = dm.schedule()
+    if name.startswith("ObjectDetection"):
+        assert not mask.any()  # cardinality 11: hybrid == f64
+    elif name.startswith("Grids"):
+        assert mask[order].all()
+    else:
+        assert mask[order].any()
+    if collapse:  # the variant's wide-blanket variables: more than 256 configurations still tabulated, or log-sum-exp
+        assert not dm.table_mode()[0] or mask[order].all()
+    seed, first, n_chains, n_sweeps = 23, 8, 24, 4
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.HYBRID, device=0, per_colour=per_colour)
+    st0 = ch.get_state(0, n_chains)
+    ch.sweep(n_sweeps, record=True)
+    ost, ocounts = samp.sweep_run(order, seed, first, st0, 0, n_sweeps, record=True, var_bits=np.where(mask, 32, 53))
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+
+
 def test_table_mode_rejects_unsuitable_models(res):
     dm, _ = load_pair(res, "ObjectDetection_11.uai", False)
     assert dm.table_mode()[0] is False

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import grample_b200 as gb
 res = os.path.join(ROOT, "tests", "golden", "res")
-prec = {"f32": gb.F32, "f64": gb.F64}[sys.argv[1] if len(sys.argv) > 1 else "f32"]
+prec = {"f32": gb.F32, "f64": gb.F64, "hybrid": gb.HYBRID}[sys.argv[1] if len(sys.argv) > 1 else "f32"]
 replicas, cw = 64, 200
 m = gb.Model.from_uai(os.path.join(res, "Pedigree_11.uai"), use_evidence=True, device=0)
 ch = gb.Chains([m, m], [replicas, replicas], seed=1, precision=prec, history=True, device=0)
