@@ -343,7 +343,8 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
 
 // Shared-memory-resident path for small models: all sweeps of one group in ONE launch.
 template <typename Real, int MAXC, int CW, bool TS>
-void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
+void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t hist_off, int32_t n_sweeps, int record, int32_t n_pre,
+                        int32_t n_half) {
     // block size >= work items of the largest colour of one CTA (one item per thread keeps the
     // per-colour critical path at a single update), capped at 256
     const gb::HostModel& hm = g.model->h;
@@ -360,7 +361,7 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t n_s
     const gb::HostModel& h = g.model->h;
     gb::k_sweep_resident<Real, MAXC, CW, TS><<<g.n_pad / ch, threads, smem, c->stream>>>(
         g.model->dev, g.dev, g.model->d_order, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, ch, g.sweep, n_sweeps,
-        record, n_pre, n_half, g.model->tab, (int)(c->precision == GB_HYBRID && g.model->hybrid_tables()));
+        record, n_pre, n_half, g.model->tab, (int)(c->precision == GB_HYBRID && g.model->hybrid_tables()), hist_off);
     c->launches++;
 }
 
@@ -371,6 +372,19 @@ struct ResidentPlan {
     size_t smem = 0;
     bool ts = false;
 };
+
+// Where the CTA's per-chain half-window histograms ([2][total_card][ch] u16) go for a launch that records
+// them: appended to the resident layout when that still fits (returns the byte offset and grows *smem),
+// else -1 = updated in global memory.
+int32_t place_histograms(const gb_chains* c, const Group& g, const ResidentPlan& p, int32_t n_half, size_t* smem) {
+    *smem = p.smem;
+    if (!(c->flags & GB_CHAINS_HISTORY) || n_half < 0 || !g.d_hist) return -1;
+    const size_t off = (p.smem + 15) & ~(size_t)15;
+    const size_t bytes = (size_t)2 * g.model->h.total_card * p.ch * sizeof(uint16_t);
+    if (off + bytes > (p.ts ? 160 : 100) * 1024) return -1;
+    *smem = off + bytes;
+    return (int32_t)off;
+}
 
 ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     static int disabled = -1, no_ts = -1;
@@ -426,8 +440,10 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
 
 template <typename Real, int MAXC, int CW>
 void launch_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
-    if (p.ts) launch_resident_ts<Real, MAXC, CW, true>(c, g, p.ch, p.smem, n_sweeps, record, n_pre, n_half);
-    else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, p.smem, n_sweeps, record, n_pre, n_half);
+    size_t smem = 0;
+    const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
+    if (p.ts) launch_resident_ts<Real, MAXC, CW, true>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
+    else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
 }
 
 void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
@@ -436,15 +452,17 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     for (size_t i = 0; i + 1 < h.colour_off.size(); i++) max_col = std::max(max_col, h.colour_off[i + 1] - h.colour_off[i]);
     const int64_t items = (int64_t)max_col * (p.ch / 8);
     const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
+    size_t smem = 0;
+    const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
     static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
     size_t& configured = configured_dev[c->device % kMaxDevices];
-    if (p.smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_tab_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        configured = p.smem;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_tab_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
-    gb::k_sweep_tab_resident<<<g.n_pad / p.ch, threads, p.smem, c->stream>>>(
+    gb::k_sweep_tab_resident<<<g.n_pad / p.ch, threads, smem, c->stream>>>(
         g.model->dev, g.model->tab, g.dev, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, p.ch, g.sweep, n_sweeps, record,
-        n_pre, n_half);
+        n_pre, n_half, hist_off);
     c->launches++;
 }
 

@@ -30,7 +30,7 @@ struct Err : std::runtime_error {
 constexpr int kNeighborVarMax = 12;
 constexpr int64_t kMaxTabSize = 1 << 23;
 constexpr int kMaxCard = 64;
-constexpr int64_t kTabWideCfg = 4096;  // hybrid mode tabulates binary variables with up to this many neighbour configurations
+constexpr int64_t kTabWideCfg = 65536;  // hybrid mode tabulates binary variables with up to this many neighbour configurations
 constexpr int kTabTile = 64;  // sweep positions per CTA tile of k_sweep_tab (<= 4 neighbours); the locality order groups by it
 
 struct Factor {

@@ -406,6 +406,34 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
     }
 }
 
+// chain.go:237 (ChainHistory[v].Add(value)) as per-chain half-window histograms: in the CTA's shared memory
+// when the launch keeps them there (s_hist = [2][total_card][CH] u16, flushed once at the end of the
+// launch), else read-modify-write in global memory.  entry = card_off[v] + value; cc = chain within the CTA.
+__device__ __forceinline__ void hist_add(uint16_t* s_hist, const DevGroup& g, const int total_card, const int half,
+                                         const int entry, const int CH, const int cc, const int lchain) {
+    uint16_t* h = s_hist ? s_hist + ((size_t)half * total_card + entry) * CH + cc
+                         : g.hist + ((size_t)half * total_card + entry) * g.n_pad + lchain;
+    *h = (uint16_t)(*h + 1);
+}
+__device__ __forceinline__ uint16_t* hist_begin(uint8_t* smem, const int32_t hist_off, const DevGroup& g, const int total_card,
+                                                const int CH) {
+    if (hist_off < 0 || !g.hist) return nullptr;
+    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + hist_off);
+    for (int i = threadIdx.x; i < 2 * total_card * CH; i += blockDim.x) s_hist[i] = 0;
+    return s_hist;
+}
+__device__ __forceinline__ void hist_flush(const uint16_t* s_hist, const DevGroup& g, const int total_card, const int CH,
+                                           const int cta_chain) {
+    if (!s_hist) return;
+    for (int i = threadIdx.x; i < 2 * total_card * CH; i += blockDim.x) {
+        const int e = i / CH, c = i - e * CH;
+        if (s_hist[i] && cta_chain + c < g.n_chains) {
+            uint16_t* h = g.hist + (size_t)e * g.n_pad + cta_chain + c;
+            *h = (uint16_t)(*h + s_hist[i]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ K1/K2 resident
 // Small models (the bundled UAI problems): the whole state of CH chains fits in shared memory, so
 // ONE launch runs many sweeps — every colour of every sweep — with __syncthreads() between
@@ -448,7 +476,7 @@ __global__ void __launch_bounds__(256)
 k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
-                 const int32_t n_half, const DevTab t, const int hybrid) {
+                 const int32_t n_half, const DevTab t, const int hybrid, const int32_t hist_off) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     uint8_t* s_state = smem;                                                                  // [n_vars][CH]
@@ -479,6 +507,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
             *reinterpret_cast<const uint32_t*>(g.state + (size_t)v * g.n_pad + cta_chain + 4 * q);
     }
     for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
+    uint16_t* s_hist = hist_begin(smem, n_half >= 0 ? hist_off : -1, g, m.total_card, ch_per_cta);
     if constexpr (TS) mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0);  // the tables have landed
     __syncthreads();
     for (int s = 0; s < n_sweeps; s++) {
@@ -498,10 +527,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     if (record && lchain < g.n_chains) {
                         const int32_t coff = __ldg(m.card_off + v);
                         atomicAdd(&s_counts[coff + x], 1u);
-                        if (hist_half >= 0 && g.hist) {
-                            uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + x) * g.n_pad + lchain;
-                            *h = (uint16_t)(*h + 1);
-                        }
+                        if (hist_half >= 0 && g.hist) hist_add(s_hist, g, m.total_card, hist_half, coff + x, CH, cc, lchain);
                     }
                 }
             } else {
@@ -529,10 +555,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                         if (hist_half >= 0 && g.hist) {
 #pragma unroll
                             for (int ci = 0; ci < 4; ci++)
-                                if (ci < nvalid) {
-                                    uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + x[ci]) * g.n_pad + lchain + ci;
-                                    *h = (uint16_t)(*h + 1);
-                                }
+                                if (ci < nvalid) hist_add(s_hist, g, m.total_card, hist_half, coff + x[ci], CH, 4 * q + ci, lchain + ci);
                         }
                     }
                 }
@@ -549,6 +572,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
     if (record)
         for (int i = threadIdx.x; i < m.total_card; i += blockDim.x)
             if (s_counts[i]) atomicAdd(g.counts + i, (unsigned long long)s_counts[i]);
+    hist_flush(s_hist, g, m.total_card, CH, cta_chain);
 }
 
 // ------------------------------------------------------------------ K1-table
@@ -858,7 +882,7 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
 __global__ void __launch_bounds__(256)
 k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ colour_off,
                      const int32_t n_colours, const int32_t ch_per_cta, const uint32_t sweep0, const int32_t n_sweeps,
-                     const int record, const int32_t n_pre, const int32_t n_half) {
+                     const int record, const int32_t n_pre, const int32_t n_half, const int32_t hist_off) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* s_state = smem;  // [n_vars][CH]
     unsigned int* s_counts = reinterpret_cast<unsigned int*>(smem + (((size_t)m.n_vars * ch_per_cta + 15) & ~(size_t)15));  // [total_card]
@@ -871,6 +895,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
             *reinterpret_cast<const uint2*>(g.state + (size_t)v * g.n_pad + cta_chain + 8 * q);
     }
     for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
+    uint16_t* s_hist = hist_begin(smem, n_half >= 0 ? hist_off : -1, g, m.total_card, ch_per_cta);
     __syncthreads();
     for (int s = 0; s < n_sweeps; s++) {
         const uint32_t sweep = sweep0 + (uint32_t)s;
@@ -939,10 +964,8 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                     if (hist_half >= 0 && g.hist) {
 #pragma unroll
                         for (int i = 0; i < 8; i++)
-                            if (i < nvalid) {
-                                uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + hd.w + ((xbits >> i) & 1u)) * g.n_pad + lchain + i;
-                                *h = (uint16_t)(*h + 1);
-                            }
+                            if (i < nvalid)
+                                hist_add(s_hist, g, m.total_card, hist_half, hd.w + (int)((xbits >> i) & 1u), CH, 8 * q + i, lchain + i);
                     }
                 }
             }
@@ -957,6 +980,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
     if (record)
         for (int i = threadIdx.x; i < m.total_card; i += blockDim.x)
             if (s_counts[i]) atomicAdd(g.counts + i, (unsigned long long)s_counts[i]);
+    hist_flush(s_hist, g, m.total_card, CH, cta_chain);
 }
 
 // ------------------------------------------------------------------ K6

@@ -47,7 +47,7 @@ enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 }
  *            stored as 32-bit inverse-CDF thresholds; the sweep is integer work (gather, index,
  *            compare) with 32-bit draws.  Applies when every sampled variable is binary with at
  *            most 256 joint configurations of its free neighbours (gb_model_table_mode). */
-/*   GB_HYBRID per variable: binary variables with at most 4096 joint configurations of their free
+/*   GB_HYBRID per variable: binary variables with at most 65536 joint configurations of their free
  *            neighbours are sampled from threshold tables as in GB_TABLE (float64 conditional per
  *            configuration, 32-bit draws), every other variable by the GB_F64 path (53-bit draws) —
  *            reference float64 arithmetic throughout, for models GB_TABLE rejects (collapsed variants
