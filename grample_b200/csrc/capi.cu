@@ -136,14 +136,25 @@ struct gb_model {
     }
     // table mode proper: every sampled variable tabulated with <= 256 configurations, fixed-size records
     void ensure_tab() {
-        if (tab_built) return;
         if (!h.tab_ok) throw gb::Err("table mode does not apply to this model: " + h.tab_why);
+        if (tab_built) return;
         ensure_thresholds();
         tab.trec = up(h.trec);
         tab_built = true;
     }
-    // hybrid mode tabulates what qualifies (binary, <= 4096 configurations) in models whose cardinalities are <= 4
+    // hybrid mode tabulates what qualifies (binary, <= 65536 configurations) in models whose cardinalities are <= 4
     bool hybrid_tables() const { return h.max_card <= 4 && h.n_tab_vars > 0; }
+    // hybrid mode on a model where EVERY sampled variable got a table (plain binary models and their
+    // single-collapsed variants): the resident table kernel runs it, wide variables through their tprog entry
+    bool hybrid_all_tables() const { return hybrid_tables() && h.tab_all; }
+    void ensure_hybrid() {
+        if (!hybrid_tables()) return;
+        ensure_thresholds();
+        if (h.tab_all && !tab_built) {
+            tab.trec = up(h.trec);
+            tab_built = true;
+        }
+    }
 };
 
 namespace {
@@ -224,7 +235,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     if (n_chains < 1) throw gb::Err("a chain group needs at least 1 chain");
     if (first_chain % 8) throw gb::Err("first_chain_id must be a multiple of 8 (chains share Philox calls in blocks of 8)");
     if (c->precision == GB_TABLE) model->ensure_tab();
-    if (c->precision == GB_HYBRID && model->hybrid_tables()) model->ensure_thresholds();
+    if (c->precision == GB_HYBRID) model->ensure_hybrid();
     if (!c->groups.empty() && (model->h.n_vars != c->base().n_vars || model->h.card != c->base().card))
         throw gb::Err("Cannot merge chain with different variables");
     if (model->h.order.empty()) throw gb::Err("No Variables to select");
@@ -386,6 +397,12 @@ int32_t place_histograms(const gb_chains* c, const Group& g, const ResidentPlan&
     return (int32_t)off;
 }
 
+// the resident table kernel runs table mode, and hybrid mode when every sampled variable has a table
+bool tab_resident(const gb_chains* c, const Group& g) {
+    const bool no_hy = std::getenv("GB_HYBRID_NO_TAB_KERNEL") != nullptr;  // A/B and test knob: hybrid stays on the LSE kernels
+    return c->precision == GB_TABLE || (c->precision == GB_HYBRID && !no_hy && g.model->hybrid_all_tables());
+}
+
 ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     static int disabled = -1, no_ts = -1;
     if (disabled < 0) disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
@@ -395,7 +412,7 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     const gb::HostModel& h = g.model->h;
     if (h.n_vars > 4096) return p;
     auto base = [&](int ch) { return (((size_t)h.n_vars * ch + 15) & ~(size_t)15) + (size_t)h.total_card * 4; };
-    if (c->precision == GB_TABLE) {  // units of 8 chains; thresholds and records stay in L1
+    if (tab_resident(c, g)) {  // units of 8 chains; thresholds and records stay in L1
         int sms_t = 148;
         cudaDeviceGetAttribute(&sms_t, cudaDevAttrMultiProcessorCount, c->device);
         for (int ch : {8, 16, 32, 64}) {
@@ -482,7 +499,7 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
         for (int64_t s0 = 0; s0 < n_sweeps; s0 += kMaxSweepsPerLaunch) {
             const int32_t ns = (int32_t)std::min<int64_t>(kMaxSweepsPerLaunch, n_sweeps - s0);
             const int32_t pre = (int32_t)std::max<int64_t>((int64_t)n_pre - s0, -(1ll << 30));
-            if (c->precision == GB_TABLE) {
+            if (tab_resident(c, g)) {
                 launch_tab_resident(c, g, plan, ns, record, pre, n_half);
             } else if (c->precision == GB_F32) {
                 if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, pre, n_half);

@@ -57,7 +57,7 @@ struct HostModel {
     std::vector<int32_t> order, colour_off;        // colour-sorted sweep schedule
     std::vector<int32_t> prog_off, prog;           // per-variable update program (see kernels.cuh)
     // ---- tabulated-conditional fast path (binary sampled variables, <= 256 neighbour configurations)
-    bool tab_ok = false;
+    bool tab_ok = false, tab_all = false;
     std::string tab_why;                           // why the fast path does not apply
     std::vector<int32_t> tp_off, tprog;            // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
     std::vector<int32_t> trec;                     // per sweep position: kTabRec words (see kernels.cuh)
@@ -167,7 +167,10 @@ struct HostModel {
             n_thresholds += cfgs;
             n_tab_vars++;
         }
-        if (!tab_ok) return;
+        // tab_all: every sampled variable has a table (any width) — the resident table kernel can run the whole
+        // model (wide variables through their variable-length tprog entry); tab_ok additionally has them all narrow
+        tab_all = n_tab_vars == (int32_t)order.size() && n_tab_vars > 0;
+        if (!tab_all) return;
         // fixed-size record per sweep position: {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
         // (2^n_nbr <= 256 configurations => n_nbr <= 8)
         trec.assign(order.size() * 20, 0);
@@ -180,6 +183,10 @@ struct HostModel {
             r[2] = tp[0];
             tab_max_nbr = std::max(tab_max_nbr, (int)tp[0]);
             r[3] = card_off[v];
+            if (tp[0] > 8) {  // wide variable: the record only points at its tprog entry
+                r[4] = tp_off[v];
+                continue;
+            }
             for (int i = 0; i < 8; i++) {
                 r[4 + i] = i < tp[0] ? tp[2 + 2 * i] : v;
                 r[12 + i] = i < tp[0] ? tp[3 + 2 * i] : 0;

@@ -906,37 +906,58 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                 const int j = item / units, q = item - j * units;
                 const int4* r = reinterpret_cast<const int4*>(t.trec + (size_t)(c0 + j) * kTabRec);
                 const int4 hd = __ldg(r);  // v, thr_off, n_nbr, card_off
-                uint32_t cfg_lo = 0, cfg_hi = 0;
-                {
-                    const int4 na = __ldg(r + 1), sa = __ldg(r + 3);
-                    const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
+                uint32_t T[8];
+                if (hd.z > 8) {
+                    // wide variable (more than 8 free neighbours, e.g. the neighbours of a collapsed variable): the
+                    // record points at its variable-length tprog entry and the configuration index needs 32 bits
+                    const int32_t* __restrict__ tp = t.tprog + __ldg(&r[1].x) + 2;
+                    uint32_t idx[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    for (int i = 0; i < hd.z; i++) {
+                        const int ov = __ldg(tp + 2 * i);
+                        const uint32_t os = (uint32_t)__ldg(tp + 2 * i + 1);
+                        const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)ov * CH + 8 * q);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {  // slots past n_nbr hold the variable itself at stride 0
-                        const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)nb[i] * CH + 8 * q);
-                        cfg_lo += w.x * (uint32_t)sb[i];
-                        cfg_hi += w.y * (uint32_t)sb[i];
+                        for (int ci = 0; ci < 4; ci++) {
+                            idx[ci] += ((w.x >> (8 * ci)) & 0xffu) * os;
+                            idx[4 + ci] += ((w.y >> (8 * ci)) & 0xffu) * os;
+                        }
                     }
-                }
-                if (hd.z > 4) {
-                    const int4 na = __ldg(r + 2), sa = __ldg(r + 4);
-                    const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)nb[i] * CH + 8 * q);
-                        cfg_lo += w.x * (uint32_t)sb[i];
-                        cfg_hi += w.y * (uint32_t)sb[i];
+                    for (int i = 0; i < 8; i++) T[i] = __ldg(t.thr + hd.y + idx[i]);
+                } else {
+                    uint32_t cfg_lo = 0, cfg_hi = 0;
+                    {
+                        const int4 na = __ldg(r + 1), sa = __ldg(r + 3);
+                        const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {  // slots past n_nbr hold the variable itself at stride 0
+                            const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)nb[i] * CH + 8 * q);
+                            cfg_lo += w.x * (uint32_t)sb[i];
+                            cfg_hi += w.y * (uint32_t)sb[i];
+                        }
                     }
+                    if (hd.z > 4) {
+                        const int4 na = __ldg(r + 2), sa = __ldg(r + 4);
+                        const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)nb[i] * CH + 8 * q);
+                            cfg_lo += w.x * (uint32_t)sb[i];
+                            cfg_hi += w.y * (uint32_t)sb[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        T[i] = __ldg(t.thr + hd.y + (((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu));
                 }
                 const int lchain = cta_chain + 8 * q;
                 const uint32_t chain_blk = (uint32_t)((g.first_chain + (uint64_t)lchain) >> 3);
                 const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
-                uint32_t T[8], xbits = 0;
+                uint32_t xbits = 0;
                 bool tie = false;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
-                    T[i] = __ldg(t.thr + hd.y + idx);
                     const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
                     xbits |= (hi > (T[i] >> 16) ? 1u : 0u) << i;
                     tie |= hi == (T[i] >> 16);

@@ -328,6 +328,43 @@ def test_hybrid_sweep_bitexact(res, name, evid, collapse, per_colour):
     assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
 
 
+def test_hybrid_all_table_variants_run_on_the_table_kernel(res, monkeypatch):
+    """a single-collapsed variant of an all-binary model: the collapsed variable's neighbours have more than
+    8 free neighbours (wide records, 32-bit configuration indices); hybrid mode runs the whole variant on the
+    resident table kernel and must give the states, counts and half-window histograms of the hybrid
+    log-sum-exp kernels (same tables, same Philox fields) and of the oracle"""
+    dm0, om = load_pair(res, "Promedus_11.uai", True)
+    fixed = dm0.fixed
+    cands = sorted(((dm0.blanket_size(v), v) for v in range(dm0.n_vars) if fixed[v] < 0), reverse=True)
+    for b, v in cands:  # the widest variant whose variables all still get a table (<= 65536 configurations)
+        if b > 12:
+            continue
+        dm, _, _ = dm0.collapse(v)
+        mask = dm.hybrid_mask()
+        order, _ = dm.schedule()
+        if mask[order].all() and not dm.table_mode()[0]:
+            break
+    else:
+        pytest.fail("no single-collapsed variant with only tabulated, partly wide variables")
+    assert max(len(dm.thresholds(u)) for u in order) > 256
+    samp = oracle.Sampler(oracle.Generator(1), om, collapsed=True)
+    samp.collapse(v)
+    out = []
+    for knob in (None, "1"):
+        if knob:
+            monkeypatch.setenv("GB_HYBRID_NO_TAB_KERNEL", knob)
+        ch = gb.Chains(dm, 40, seed=77, first_chain_id=16, precision=gb.HYBRID, history=True, device=0)
+        st0 = ch.get_state(0, 40)
+        ch.advance(6)
+        out.append((st0, ch.get_state(0, 40), ch.group_counts(0), ch.group_history(0, 40), ch.total_samples))
+    monkeypatch.delenv("GB_HYBRID_NO_TAB_KERNEL")
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    ost, ocounts = samp.sweep_run(order, 77, 16, out[0][0], 0, 7, record=True, var_bits=np.where(mask, 32, 53))
+    assert np.array_equal(ost, out[0][1])
+    assert np.array_equal(ocounts, out[0][2].astype(np.float64))
+
+
 def test_table_mode_rejects_unsuitable_models(res):
     dm, _ = load_pair(res, "ObjectDetection_11.uai", False)
     assert dm.table_mode()[0] is False
