@@ -361,8 +361,13 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t his
     const gb::HostModel& hm = g.model->h;
     int max_col = 1;
     for (size_t i = 0; i + 1 < hm.colour_off.size(); i++) max_col = std::max(max_col, hm.colour_off[i + 1] - hm.colour_off[i]);
+    // the largest colour's items are spread evenly over the fewest passes a CTA of <= cap threads needs (whole warps).
+    // One thread per chain (CW == 0, cardinality >= 8): a warp holds 32 chains of one variable, and these models have
+    // few variables per colour, so the cap is 512 threads to keep a colour at one pass.
+    // (Quad kernels keep 256 threads and a short last pass: balancing their passes measured slower.)
     const int64_t items = (int64_t)max_col * (CW == 0 ? ch : ch / 4);
-    const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
+    const int64_t passes = (items + 511) / 512;
+    const int threads = CW == 0 ? (int)(((items + passes - 1) / passes + 31) / 32 * 32) : (int)std::min<int64_t>(256, (items + 31) / 32 * 32);
     static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
     size_t& configured = configured_dev[c->device % kMaxDevices];
     if (smem > configured) {

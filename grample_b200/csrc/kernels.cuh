@@ -472,7 +472,7 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 constexpr uint32_t kBulkChunk = 32768;  // bytes per cp.async.bulk (multiple of 16)
 
 template <typename Real, int MAXC, int CW, bool TS>  // CW = 0: one thread per chain (lse_update_one)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CW == 0 ? 512 : 256)
 k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
