@@ -106,6 +106,8 @@ struct gb_model {
         dev.fixed = up(h.fixed);
         dev.prog_off = up(h.prog_off);
         dev.prog = up(h.prog);
+        dev.pw_off = up(h.pw_off);
+        dev.pw_rec = reinterpret_cast<const int4*>(up(h.pw_rec));
         dev.tab64 = up(tab64);
         dev.tab32 = up(tab32);
         dev.entry_var = up(entry_var);

@@ -56,6 +56,7 @@ struct HostModel {
     std::vector<int32_t> colour;                   // per var, -1 if never sampled
     std::vector<int32_t> order, colour_off;        // colour-sorted sweep schedule
     std::vector<int32_t> prog_off, prog;           // per-variable update program (see kernels.cuh)
+    std::vector<int32_t> pw_off, pw_rec;           // pairwise fast path: per variable 4-word records, pw_off = -1 when a factor has arity > 2
     // ---- tabulated-conditional fast path (binary sampled variables, <= 256 neighbour configurations)
     bool tab_ok = false, tab_all = false;
     std::string tab_why;                           // why the fast path does not apply
@@ -302,6 +303,28 @@ struct HostModel {
                 }
             }
         }
+        // Pairwise fast path (grids, ObjectDetection-style MRFs): a variable whose factors all have arity <= 2
+        // gets one 16-byte record per factor {tab_off, stride of v, other variable, stride of the other} in
+        // m.Funcs order, so the device walks its blanket with one vector load per factor.  A unary factor names
+        // the variable itself at stride 0.
+        pw_off.assign(n_vars, -1);
+        pw_rec.clear();
+        for (int v = 0; v < n_vars; v++) {
+            if (prog_off[v] < 0) continue;
+            bool ok = true;
+            for (int32_t fi : var_funcs[v]) ok = ok && funcs[fi].vars.size() <= 2;
+            if (!ok) continue;
+            pw_off[v] = (int32_t)pw_rec.size() / 4;
+            for (int32_t fi : var_funcs[v]) {
+                const Factor& f = funcs[fi];
+                const int pos = f.vars[0] == v ? 0 : 1;
+                pw_rec.push_back((int32_t)f.off);
+                pw_rec.push_back((int32_t)f.strides[pos]);
+                pw_rec.push_back(f.vars.size() == 2 ? f.vars[1 - pos] : v);
+                pw_rec.push_back(f.vars.size() == 2 ? (int32_t)f.strides[1 - pos] : 0);
+            }
+        }
+        if (pw_rec.empty()) pw_rec.assign(4, 0);
     }
 };
 

@@ -33,6 +33,8 @@ struct DevModel {
     const int32_t* fixed;       // [n_vars]
     const int32_t* prog_off;    // [n_vars], -1 when the variable has no program
     const int32_t* prog;        // update programs (host_model.hpp::build_programs)
+    const int32_t* pw_off;      // [n_vars] first pairwise record of the variable, -1 = none (a factor of arity > 2)
+    const int4* pw_rec;         // {tab_off, stride of v, other variable, its stride} per factor
     const double* tab64;        // log-space tables
     const float* tab32;
     int32_t n_tab;              // table entries, padded to a multiple of 4 (16-byte bulk-copy granularity)
@@ -91,6 +93,13 @@ __device__ __forceinline__ Real ld_tab(const Real* p) {
 // would overflow float32 for wide conditionals) and a multiply in place of the divide.
 // `card` may be smaller than MAXC (entries past it are ignored); callers that know card == MAXC pass it
 // as a constant so that the `k < card` predicates fold away.
+//
+// The float64 floor test `e[k] / tot < 1e-6` (gibbs-simple.go:249) is evaluated without the division
+// whenever that is provably the same decision: the running total only grows during the floor loop, by
+// less than (1 + 1e-6)^64 < 1 + 1e-4, so an e[k] outside [1e-6 tot0 (1 - 1e-4), 1e-6 tot0 (1 + 1e-4)]
+// (tot0 = total before the loop) compares the same way against every running total, correctly rounded
+// quotient included.  Only a weight inside that band (or a non-finite total) takes the literal loop with the
+// division.  The fast loop is branch-free: adding d = 0.0 to a non-negative double leaves it unchanged.
 template <typename Real, int MAXC>
 __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int card) {
     if constexpr (std::is_same<Real, double>::value) {
@@ -111,18 +120,34 @@ __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int c
                 tot += e;
                 w[k] = e;
             }
+        const double lo = tot * (1e-6 * (1.0 - 1e-4)), hi = tot * (1e-6 * (1.0 + 1e-4));
+        bool literal = !(tot < 1.7e308);
 #pragma unroll
         for (int k = 0; k < MAXC; k++)
-            if (k < card && w[k] / tot < 1e-6) {
-                const double d = tot * 1e-6;
-                tot += d;
-                w[k] += d;
-            }
+            if (k < card) literal |= (w[k] >= lo) & (w[k] <= hi);
+        if (!literal) {
+            const double mid = tot * 1e-6;
+#pragma unroll
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) {
+                    const double d = w[k] < mid ? tot * 1e-6 : 0.0;
+                    tot += d;
+                    w[k] += d;
+                }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < MAXC; k++)
+                if (k < card && w[k] / tot < 1e-6) {
+                    const double d = tot * 1e-6;
+                    tot += d;
+                    w[k] += d;
+                }
+        }
     } else {
         float mx = w[0];
 #pragma unroll
         for (int k = 1; k < MAXC; k++)
-            if (k < card && w[k] > mx) mx = w[k];
+            if (k < card) mx = fmaxf(mx, w[k]);
         float tot = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; k++)
@@ -133,8 +158,8 @@ __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int c
             }
 #pragma unroll
         for (int k = 0; k < MAXC; k++)
-            if (k < card && w[k] < tot * 1e-6f) {
-                const float d = tot * 1e-6f;
+            if (k < card) {
+                const float d = w[k] < tot * 1e-6f ? tot * 1e-6f : 0.f;
                 tot += d;
                 w[k] += d;
             }
@@ -143,6 +168,9 @@ __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int c
 
 // sampler.go:107-123: re-sum, r = U * tot, first k with r <= w[k].  The (measure-zero)
 // fall-through that the reference turns into an error selects the last value here.
+// float64: the reference's sequential subtraction, branch-free (r keeps being reduced after the hit; it is
+// not used any more).  float32: value = number of prefix sums the draw exceeds (same law, no dependent
+// subtract-compare chain).
 template <typename Real, int MAXC>
 __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real u) {
     Real tot = 0;
@@ -150,19 +178,29 @@ __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real
     for (int k = 0; k < MAXC; k++)
         if (k < card) tot += w[k];
     Real r = u * tot;
-    int sel = card - 1;
-    bool done = false;
+    if constexpr (std::is_same<Real, double>::value) {
+        int sel = card - 1;
+        bool done = false;
 #pragma unroll
-    for (int k = 0; k < MAXC; k++)
-        if (k < card && !done) {
-            if (r <= w[k]) {
-                sel = k;
-                done = true;
-            } else {
+        for (int k = 0; k < MAXC; k++)
+            if (k < card) {
+                const bool le = r <= w[k];
+                sel = (le && !done) ? k : sel;
+                done |= le;
                 r -= w[k];
             }
-        }
-    return sel;
+        return sel;
+    } else {
+        int sel = 0;
+        float c = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC - 1; k++)
+            if (k < card - 1) {
+                c += w[k];
+                sel += r > c ? 1 : 0;
+            }
+        return sel;
+    }
 }
 
 // ------------------------------------------------------------------ K1/K2
@@ -285,7 +323,50 @@ __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real
     return inverse_cdf<Real, MAXC>(w, card, u);
 }
 
-// cardinality buckets of the one-thread-per-chain body: exact unrolls for 2, 3, 11 (ObjectDetection) and MAXC
+// Pairwise fast path of the one-thread-per-chain body (host_model.hpp::build_programs, pw_rec): one 16-byte
+// record per factor; the two strides a dense pairwise table can give the updated variable (1 = last in the
+// scope, MAXC = first in the scope of an equal-cardinality pair) are compile-time, so the row's loads carry
+// immediate offsets.  Same factor order and arithmetic as lse_update_one_impl: identical results.
+template <typename Real, int MAXC, bool GT>
+__device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
+                                                 const uint32_t stride, const int v, const int32_t pw, const uint32_t chain,
+                                                 const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+    const int4* __restrict__ rec = m.pw_rec + pw;
+    const int nf = __ldg(m.prog + __ldg(m.prog_off + v));
+    Real u;
+    if constexpr (std::is_same<Real, double>::value) {
+        const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain >> 1, kTagDraw53, seed_lo, seed_hi);
+        u = (chain & 1u) ? u53(a.z, a.w) : u53(a.x, a.y);
+    } else {
+        const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain >> 2, kTagDraw24, seed_lo, seed_hi);
+        const uint32_t wsel = (chain & 2u) ? ((chain & 1u) ? a.w : a.z) : ((chain & 1u) ? a.y : a.x);
+        u = (float)(wsel >> 8) * (1.0f / 16777216.0f);
+    }
+    Real w[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) w[k] = 0;
+    int4 r = __ldg(rec);
+    for (int f = 0; f < nf; f++) {
+        const int4 nx = __ldg(rec + min(f + 1, nf - 1));  // next record in flight while this row is summed
+        const Real* __restrict__ row = tab + (r.x + (int)cell[(size_t)(uint32_t)r.z * stride] * r.w);
+        if (r.y == 1) {
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k);
+        } else if (r.y == MAXC) {
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k * MAXC);
+        } else {
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k * r.y);
+        }
+        r = nx;
+    }
+    stabilise_exp_floor<Real, MAXC>(w, MAXC);
+    return inverse_cdf<Real, MAXC>(w, MAXC, u);
+}
+
+// cardinality buckets of the one-thread-per-chain body: exact unrolls for 2, 3, 11 (ObjectDetection) and MAXC;
+// variables with only unary and pairwise factors take the record-driven fast path
 template <typename Real, int MAXC, bool GT = true>
 __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                               const uint32_t stride, const int v, const int card, const uint32_t chain,
@@ -296,10 +377,17 @@ __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __r
     if constexpr (MAXC > 3) {
         if (card == 3) return lse_update_one_impl<Real, 3, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
     }
+    const int32_t pw = __ldg(m.pw_off + v);
     if constexpr (MAXC > 11) {
-        if (card == 11) return lse_update_one_impl<Real, 11, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+        if (card == 11) {
+            if (pw >= 0) return lse_update_one_pw<Real, 11, GT>(m, tab, cell, stride, v, pw, chain, sweep, seed_lo, seed_hi);
+            return lse_update_one_impl<Real, 11, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+        }
     }
-    if (card == MAXC) return lse_update_one_impl<Real, MAXC, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    if (card == MAXC) {
+        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT>(m, tab, cell, stride, v, pw, chain, sweep, seed_lo, seed_hi);
+        return lse_update_one_impl<Real, MAXC, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    }
     return lse_update_one_impl<Real, MAXC, GT, false>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
 }
 
