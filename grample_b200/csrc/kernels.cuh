@@ -120,11 +120,14 @@ __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int c
                 tot += e;
                 w[k] = e;
             }
-        const double lo = tot * (1e-6 * (1.0 - 1e-4)), hi = tot * (1e-6 * (1.0 + 1e-4));
-        bool literal = !(tot < 1.7e308);
+        // (binary .. quaternary variables keep the literal loop: two to four divisions cost less than the band test)
+        bool literal = MAXC < 8 || !(tot < 1.7e308);
+        if constexpr (MAXC >= 8) {
+            const double lo = tot * (1e-6 * (1.0 - 1e-4)), hi = tot * (1e-6 * (1.0 + 1e-4));
 #pragma unroll
-        for (int k = 0; k < MAXC; k++)
-            if (k < card) literal |= (w[k] >= lo) & (w[k] <= hi);
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) literal |= (w[k] >= lo) & (w[k] <= hi);
+        }
         if (!literal) {
             const double mid = tot * 1e-6;
 #pragma unroll
@@ -135,7 +138,7 @@ __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int c
                     w[k] += d;
                 }
         } else {
-#pragma unroll 1
+#pragma unroll (MAXC < 8 ? MAXC : 1)
             for (int k = 0; k < MAXC; k++)
                 if (k < card && w[k] / tot < 1e-6) {
                     const double d = tot * 1e-6;
@@ -178,7 +181,21 @@ __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real
     for (int k = 0; k < MAXC; k++)
         if (k < card) tot += w[k];
     Real r = u * tot;
-    if constexpr (std::is_same<Real, double>::value) {
+    if constexpr (std::is_same<Real, double>::value && MAXC < 8) {
+        int sel = card - 1;
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < card && !done) {
+                if (r <= w[k]) {
+                    sel = k;
+                    done = true;
+                } else {
+                    r -= w[k];
+                }
+            }
+        return sel;
+    } else if constexpr (std::is_same<Real, double>::value) {
         int sel = card - 1;
         bool done = false;
 #pragma unroll
