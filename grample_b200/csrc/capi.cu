@@ -112,6 +112,15 @@ struct gb_model {
         dev.tab32 = up(tab32);
         dev.entry_var = up(entry_var);
         d_order = up(h.order);
+        std::vector<int32_t> pos_rec(std::max<size_t>(1, h.order.size()) * 4, 0);
+        for (size_t j = 0; j < h.order.size(); j++) {
+            const int v = h.order[j];
+            pos_rec[4 * j] = v;
+            pos_rec[4 * j + 1] = h.card[v];
+            pos_rec[4 * j + 2] = h.pw_off[v];
+            pos_rec[4 * j + 3] = h.prog[h.prog_off[v]];
+        }
+        dev.pos_rec = reinterpret_cast<const int4*>(up(pos_rec));
         d_colour_off = up(h.colour_off);
     }
     // thresholds: evaluate every (tabulated variable, neighbour configuration) conditional once on the device

@@ -35,6 +35,7 @@ struct DevModel {
     const int32_t* prog;        // update programs (host_model.hpp::build_programs)
     const int32_t* pw_off;      // [n_vars] first pairwise record of the variable, -1 = none (a factor of arity > 2)
     const int4* pw_rec;         // {tab_off, stride of v, other variable, its stride} per factor
+    const int4* pos_rec;        // [n_order] per sweep position {variable, cardinality, pw_off, number of factors}
     const double* tab64;        // log-space tables
     const float* tab32;
     int32_t n_tab;              // table entries, padded to a multiple of 4 (16-byte bulk-copy granularity)
@@ -151,21 +152,24 @@ __device__ __forceinline__ void stabilise_exp_floor(Real (&w)[MAXC], const int c
 #pragma unroll
         for (int k = 1; k < MAXC; k++)
             if (k < card) mx = fmaxf(mx, w[k]);
+        // exp(w - mx) as one FFMA + ex2.approx.ftz: arguments are <= 0 and a result flushed to zero is far below
+        // the floor anyway.  The floor adds 1e-6 * (total before the loop) to every weight below it: the
+        // reference's running total differs from that by a factor < (1 + 1e-6)^card, three orders of magnitude
+        // inside the float32 tolerance of the conditional (1e-4 relative).
+        const float nmx = -mx * 1.4426950408889634f;
         float tot = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; k++)
             if (k < card) {
-                const float e = __expf(w[k] - mx);
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(w[k], 1.4426950408889634f, nmx)));
                 tot += e;
                 w[k] = e;
             }
+        const float lim = tot * 1e-6f;
 #pragma unroll
         for (int k = 0; k < MAXC; k++)
-            if (k < card) {
-                const float d = w[k] < tot * 1e-6f ? tot * 1e-6f : 0.f;
-                tot += d;
-                w[k] += d;
-            }
+            if (k < card) w[k] += w[k] < lim ? lim : 0.f;
     }
 }
 
@@ -346,10 +350,10 @@ __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real
 // immediate offsets.  Same factor order and arithmetic as lse_update_one_impl: identical results.
 template <typename Real, int MAXC, bool GT>
 __device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
-                                                 const uint32_t stride, const int v, const int32_t pw, const uint32_t chain,
-                                                 const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+                                                 const uint32_t stride, const int v, const int32_t pw, const int nf,
+                                                 const uint32_t chain, const uint32_t sweep, const uint32_t seed_lo,
+                                                 const uint32_t seed_hi) {
     const int4* __restrict__ rec = m.pw_rec + pw;
-    const int nf = __ldg(m.prog + __ldg(m.prog_off + v));
     Real u;
     if constexpr (std::is_same<Real, double>::value) {
         const Philox4 a = philox4x32_10((uint32_t)v, sweep, chain >> 1, kTagDraw53, seed_lo, seed_hi);
@@ -386,23 +390,23 @@ __device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* 
 // variables with only unary and pairwise factors take the record-driven fast path
 template <typename Real, int MAXC, bool GT = true>
 __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
-                                              const uint32_t stride, const int v, const int card, const uint32_t chain,
-                                              const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+                                              const uint32_t stride, const int v, const int card, const int32_t pw, const int nf,
+                                              const uint32_t chain, const uint32_t sweep, const uint32_t seed_lo,
+                                              const uint32_t seed_hi) {
     if constexpr (MAXC > 2) {
         if (card == 2) return lse_update_one_impl<Real, 2, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
     }
     if constexpr (MAXC > 3) {
         if (card == 3) return lse_update_one_impl<Real, 3, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
     }
-    const int32_t pw = __ldg(m.pw_off + v);
     if constexpr (MAXC > 11) {
         if (card == 11) {
-            if (pw >= 0) return lse_update_one_pw<Real, 11, GT>(m, tab, cell, stride, v, pw, chain, sweep, seed_lo, seed_hi);
+            if (pw >= 0) return lse_update_one_pw<Real, 11, GT>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi);
             return lse_update_one_impl<Real, 11, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
         }
     }
     if (card == MAXC) {
-        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT>(m, tab, cell, stride, v, pw, chain, sweep, seed_lo, seed_hi);
+        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi);
         return lse_update_one_impl<Real, MAXC, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
     }
     return lse_update_one_impl<Real, MAXC, GT, false>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
@@ -621,13 +625,15 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
         for (int col = 0; col < n_colours; col++) {
             const int c0 = __ldg(colour_off + col), nvc = __ldg(colour_off + col + 1) - c0;
             if constexpr (CW == 0) {
+                const int ch_shift = 31 - __clz(CH);  // CH is a power of two (8..64)
                 for (int item = threadIdx.x; item < nvc * CH; item += blockDim.x) {
-                    const int j = item / CH, cc = item - j * CH;
-                    const int v = __ldg(order + c0 + j);
-                    const int card = __ldg(m.card + v);
+                    const int j = item >> ch_shift, cc = item & (CH - 1);
+                    const int4 pr = __ldg(m.pos_rec + c0 + j);  // variable, cardinality, pairwise records, factors
+                    const int v = pr.x;
                     const int lchain = cta_chain + cc;
                     const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)lchain);
-                    const int x = lse_update_one<Real, MAXC, !TS>(m, tab, s_state + cc, (uint32_t)CH, v, card, chain, sweep, g.seed_lo, g.seed_hi);
+                    const int x = lse_update_one<Real, MAXC, !TS>(m, tab, s_state + cc, (uint32_t)CH, v, pr.y, pr.z, pr.w, chain, sweep,
+                                                                  g.seed_lo, g.seed_hi);
                     s_state[(size_t)v * CH + cc] = (uint8_t)x;
                     if (record && lchain < g.n_chains) {
                         const int32_t coff = __ldg(m.card_off + v);
