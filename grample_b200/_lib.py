@@ -15,6 +15,8 @@ F64, F32, TABLE, HYBRID = 0, 1, 2, 3
 MAX_ABS, MEAN_ABS, HELLINGER, JS = 0, 1, 2, 3
 CHAINS_HISTORY = 1
 CHAINS_PER_COLOUR = 2
+CHAINS_RAO_BLACKWELL = 4
+RB_UNIT = 2.0 ** -24  # one Rao-Blackwell bin unit (gb_chains_group_counts under CHAINS_RAO_BLACKWELL)
 NEIGHBOR_VAR_MAX = 12
 MAX_CARD = 64
 

@@ -160,6 +160,8 @@ def build_parser():
     s.add_argument("--replicas", type=int, default=1024, help="device chains behind each reference chain")
     s.add_argument("--precision", default="f32", choices=["f64", "f32", "table", "hybrid"])
     s.add_argument("--device", type=int, default=0)
+    s.add_argument("--rao-blackwell", action="store_true",
+                   help="marginals accumulate the sampled conditionals instead of counts (f32 / f64; not the reference's estimator)")
     s.add_argument("--addr", default="", help="ip:port for the expvar-style monitor (cmd/monitor.go); empty = no HTTP server")
     return ap
 
@@ -286,7 +288,8 @@ def _sample(args, out, mon, start, dist=None, rank=0, world=1):
             models.append(mod)
         mon.add("Base-Chain-Count", 1)  # cmd/root.go:428-429
         mon.add("Total-Chain-Count", 1)
-    chains = core.Chains(models[0], n_local, seed=seed, first_chain_id=shard_first, precision=prec, history=True, device=args.device)
+    chains = core.Chains(models[0], n_local, seed=seed, first_chain_id=shard_first, precision=prec, history=True, device=args.device,
+                         rao_blackwell=args.rao_blackwell)
     for idx in range(1, base):
         chains.add_group(models[idx], n_local, idx * per + shard_first)
     chains.burnin((burn + n_free - 1) // max(n_free, 1))

@@ -167,14 +167,15 @@ class Chains:
     """All chains of one device, grouped by model (one group per collapsed variant)."""
 
     def __init__(self, models, chains_per_model, seed=1, first_chain_id=0, precision=F64, history=False, device=0,
-                 per_colour=False):
+                 per_colour=False, rao_blackwell=False):
         if isinstance(models, Model):
             models, chains_per_model = [models], [chains_per_model]
         self.models = list(models)
         arr = (C.c_void_p * len(models))(*[m.h.value if isinstance(m.h, C.c_void_p) else m.h for m in models])
         cpm = _i32(chains_per_model)
         self.h = C.c_void_p()
-        flags = (_lib.CHAINS_HISTORY if history else 0) | (_lib.CHAINS_PER_COLOUR if per_colour else 0)
+        flags = ((_lib.CHAINS_HISTORY if history else 0) | (_lib.CHAINS_PER_COLOUR if per_colour else 0)
+                 | (_lib.CHAINS_RAO_BLACKWELL if rao_blackwell else 0))
         check(lib().gb_chains_create(len(models), arr, _ptr(cpm, _i32p), C.c_uint64(seed), C.c_uint64(first_chain_id),
                                      precision, flags, device, C.byref(self.h)))
         self.base = self.models[0]

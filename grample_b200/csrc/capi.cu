@@ -273,6 +273,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     g.dev.first_chain = first_chain;
     g.dev.seed_lo = (uint32_t)c->seed;
     g.dev.seed_hi = (uint32_t)(c->seed >> 32);
+    g.dev.rb = (c->flags & GB_CHAINS_RAO_BLACKWELL) ? 1 : 0;
     const int64_t items = (int64_t)h.n_vars * (g.n_pad / 4);
     gb::k_init_state<<<grid_for(items, 256), 256, 0, c->stream>>>(model->dev, g.dev);
     c->launches++;
@@ -286,8 +287,12 @@ template <typename Real, int MAXC, int CW>
 void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half) {
     const int64_t items = (int64_t)n * (g.n_pad / 4);
     const int hybrid = c->precision == GB_HYBRID && g.model->hybrid_tables();
-    gb::k_sweep_colour<Real, MAXC, CW><<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, d_vars, n,
-                                                                                   g.sweep, record, hist_half, g.model->tab, hybrid);
+    if (g.dev.rb)
+        gb::k_sweep_colour<Real, MAXC, CW, true><<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, d_vars, n, g.sweep,
+                                                                                             record, hist_half, g.model->tab, hybrid);
+    else
+        gb::k_sweep_colour<Real, MAXC, CW, false><<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, d_vars, n, g.sweep,
+                                                                                              record, hist_half, g.model->tab, hybrid);
     c->launches++;
 }
 
@@ -364,8 +369,8 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
 }
 
 // Shared-memory-resident path for small models: all sweeps of one group in ONE launch.
-template <typename Real, int MAXC, int CW, bool TS>
-void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t hist_off, int32_t n_sweeps, int record, int32_t n_pre,
+template <typename Real, int MAXC, int CW, bool TS, bool RB>
+void launch_resident_rb(gb_chains* c, Group& g, int ch, size_t smem, int32_t hist_off, int32_t n_sweeps, int record, int32_t n_pre,
                         int32_t n_half) {
     // block size >= work items of the largest colour of one CTA (one item per thread keeps the
     // per-colour critical path at a single update), capped at 256
@@ -382,14 +387,21 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t his
     static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
     size_t& configured = configured_dev[c->device % kMaxDevices];
     if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW, TS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const gb::HostModel& h = g.model->h;
-    gb::k_sweep_resident<Real, MAXC, CW, TS><<<g.n_pad / ch, threads, smem, c->stream>>>(
+    gb::k_sweep_resident<Real, MAXC, CW, TS, RB><<<g.n_pad / ch, threads, smem, c->stream>>>(
         g.model->dev, g.dev, g.model->d_order, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, ch, g.sweep, n_sweeps,
         record, n_pre, n_half, g.model->tab, (int)(c->precision == GB_HYBRID && g.model->hybrid_tables()), hist_off);
     c->launches++;
+}
+
+template <typename Real, int MAXC, int CW, bool TS>
+void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t hist_off, int32_t n_sweeps, int record, int32_t n_pre,
+                        int32_t n_half) {
+    if (g.dev.rb) launch_resident_rb<Real, MAXC, CW, TS, true>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
+    else launch_resident_rb<Real, MAXC, CW, TS, false>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
 }
 
 // Resident-path launch plan: chains per CTA, dynamic shared memory, and whether the log-space tables are
@@ -656,7 +668,8 @@ void merge_partial(gb_chains* c) {
     CUDA_CHECK(cudaMemsetAsync(c->d_merge, 0, (size_t)h.total_card * sizeof(double), c->stream));
     for (auto& g : c->groups)
         gb::k_merge_partial<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(g.model->dev, g.d_counts,
-                                                                              (double)g.n_chains, c->d_skip, c->d_merge);
+                                                                              (double)g.n_chains, c->d_skip, c->d_merge,
+                                                                              g.dev.rb ? 1.0 / gb::kRbScale : 1.0);
     c->launches += (int64_t)c->groups.size();
     CUDA_CHECK(cudaGetLastError());
 }
@@ -993,6 +1006,8 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
     GB_TRY
     if (n_groups < 1) throw gb::Err("at least one chain group is required");
     if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE && precision != GB_HYBRID) throw gb::Err("unknown precision");
+    if ((flags & GB_CHAINS_RAO_BLACKWELL) && precision != GB_F64 && precision != GB_F32)
+        throw gb::Err("GB_CHAINS_RAO_BLACKWELL needs precision GB_F64 or GB_F32 (the estimator accumulates the log-sum-exp conditionals)");
     require_device(device);
     auto c = std::make_unique<gb_chains>();
     c->device = device;
@@ -1046,6 +1061,7 @@ int gb_chains_launch_count(const gb_chains* c, int64_t* out) { *out = c->launche
 int gb_chains_scan(gb_chains* c, int64_t n_steps, int record) {
     GB_TRY
     if (n_steps < 0) throw gb::Err("Invalid step count");
+    if (c->flags & GB_CHAINS_RAO_BLACKWELL) throw gb::Err("the random-scan parity mode records plain counts (no GB_CHAINS_RAO_BLACKWELL)");
     CUDA_CHECK(cudaSetDevice(c->device));
     for (auto& g : c->groups) {
         const gb::HostModel& h = g.model->h;

@@ -49,6 +49,7 @@ struct DevGroup {
     int32_t n_chains, n_pad;
     uint64_t first_chain;        // global id of local chain 0 (multiple of 4)
     uint32_t seed_lo, seed_hi;
+    int32_t rb;                  // GB_CHAINS_RAO_BLACKWELL: counts hold fixed-point conditional probabilities (units of 2^-24)
 };
 
 struct DevTab {
@@ -224,16 +225,52 @@ __device__ __forceinline__ int inverse_cdf(const Real (&w)[MAXC], int card, Real
     }
 }
 
+// Rao-Blackwell estimator (GB_CHAINS_RAO_BLACKWELL): instead of Marginal[value] += 1 (chain.go:235)
+// every recorded update adds the conditional it sampled from, p_k = e[k] / sum(e), to ALL bins of the variable —
+// the same expectation with less variance, at no extra memory traffic because the weights are already in
+// registers.  Bins are 64-bit fixed point in units of 2^-24 (an integer sum: independent of the order in which
+// chains arrive, so the merged estimate does not depend on scheduling or on the number of GPUs).  Lanes of a
+// warp that update the same variable add up their contributions with a warp reduction first.
+constexpr double kRbScale = 16777216.0;
+struct NoRecord {  // plain counts: nothing to do inside the update (kernels without the estimator compile to the same code as before)
+    __device__ __forceinline__ NoRecord(unsigned long long*, int) {}
+    template <typename Real, int M>
+    __device__ __forceinline__ void operator()(const int, const Real (&)[M], const int) const {}
+};
+struct RbRecord {
+    unsigned long long* bins;  // counts + card_off[v]; nullptr = not recording
+    int nvalid;                // chains of this work item that exist (the rest are padding)
+    __device__ __forceinline__ RbRecord(unsigned long long* b, int n) : bins(b), nvalid(n) {}
+    template <typename Real, int M>
+    __device__ __forceinline__ void operator()(const int ci, const Real (&w)[M], const int card) const {
+        if (bins == nullptr) return;
+        Real tot = 0;
+#pragma unroll
+        for (int k = 0; k < M; k++)
+            if (k < card) tot += w[k];
+        const Real scale = ci < nvalid ? (Real)kRbScale / tot : (Real)0;
+        const unsigned peers = __match_any_sync(__activemask(), reinterpret_cast<unsigned long long>(bins));
+        const bool leader = (int)(threadIdx.x & 31u) == __ffs(peers) - 1;
+#pragma unroll
+        for (int k = 0; k < M; k++)
+            if (k < card) {
+                const unsigned q = (unsigned)(w[k] * scale + (Real)0.5);
+                const unsigned sum = __reduce_add_sync(peers, q);
+                if (leader && sum) atomicAdd(bins + k, (unsigned long long)sum);
+            }
+    }
+};
+
 // ------------------------------------------------------------------ K1/K2
 // One variable x 4 consecutive chains: gather the Markov-blanket factor rows, stabilise,
 // exponentiate, floor, inverse CDF.  `row` points at the first of the 4 chains in the row of
 // variable 0, `stride` is the row stride in bytes (global layout: n_pad; shared-memory-resident
 // layout: chains per CTA).  CW = chains whose weight vectors are held in registers at once.
-template <typename Real, int MAXC, int CW, bool GT, bool EXACT>
+template <typename Real, int MAXC, int CW, bool GT, bool EXACT, typename Rec>
 __device__ __forceinline__ void lse_update_quad_impl(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
                                                      const uint32_t stride, const int v, const int card_rt, const uint32_t chain0,
                                                      const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
-                                                     int (&x)[4]) {
+                                                     int (&x)[4], const Rec& rb) {
     const int card = EXACT ? MAXC : card_rt;  // EXACT: the cardinality is the compile-time bound, predicates fold
     const int32_t* __restrict__ prog = m.prog + __ldg(m.prog_off + v);
     const int nf = __ldg(prog);
@@ -280,6 +317,7 @@ __device__ __forceinline__ void lse_update_quad_impl(const DevModel& m, const Re
 #pragma unroll
         for (int ci = 0; ci < CW; ci++) {
             stabilise_exp_floor<Real, MAXC>(w[ci], card);
+            rb(cb + ci, w[ci], card);
             x[cb + ci] = inverse_cdf<Real, MAXC>(w[ci], card, u[cb + ci]);
         }
     }
@@ -288,34 +326,35 @@ __device__ __forceinline__ void lse_update_quad_impl(const DevModel& m, const Re
 // Dispatch on the variable's cardinality: binary and ternary variables (the bulk of the UAI problems) run
 // bodies unrolled to exactly their cardinality instead of predicated-off iterations up to MAXC.  Same
 // arithmetic in the same order, so trajectories do not change.
-template <typename Real, int MAXC, int CW, bool GT = true>
+template <typename Real, int MAXC, int CW, bool GT = true, typename Rec = NoRecord>
 __device__ __forceinline__ void lse_update_quad(const DevModel& m, const Real* __restrict__ tab, const uint8_t* row,
                                                 const uint32_t stride, const int v, const int card, const uint32_t chain0,
                                                 const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
-                                                int (&x)[4]) {
+                                                int (&x)[4], const Rec& rb) {
     if constexpr (MAXC > 2) {
         if (card == 2) {
-            lse_update_quad_impl<Real, 2, CW, GT, true>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+            lse_update_quad_impl<Real, 2, CW, GT, true, Rec>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x, rb);
             return;
         }
     }
     if constexpr (MAXC > 3) {
         if (card == 3) {
-            lse_update_quad_impl<Real, 3, CW, GT, true>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+            lse_update_quad_impl<Real, 3, CW, GT, true, Rec>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x, rb);
             return;
         }
     }
-    if (card == MAXC) lse_update_quad_impl<Real, MAXC, CW, GT, true>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
-    else lse_update_quad_impl<Real, MAXC, CW, GT, false>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x);
+    if (card == MAXC) lse_update_quad_impl<Real, MAXC, CW, GT, true, Rec>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x, rb);
+    else lse_update_quad_impl<Real, MAXC, CW, GT, false, Rec>(m, tab, row, stride, v, card, chain0, sweep, seed_lo, seed_hi, x, rb);
 }
 
 // One variable x ONE chain (same arithmetic and draws as lse_update_quad for that chain): used by the
 // resident kernel for high-cardinality models, where one thread per chain gives 4x the parallelism
 // and a quarter of the registers.  `cell` points at this chain's byte in the row of variable 0.
-template <typename Real, int MAXC, bool GT, bool EXACT>
+template <typename Real, int MAXC, bool GT, bool EXACT, typename Rec>
 __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                                    const uint32_t stride, const int v, const int card_rt, const uint32_t chain,
-                                                   const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi) {
+                                                   const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
+                                                   const Rec& rb) {
     const int card = EXACT ? MAXC : card_rt;
     const int32_t* __restrict__ p = m.prog + __ldg(m.prog_off + v);
     const int nf = __ldg(p++);
@@ -341,6 +380,7 @@ __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real
             if (k < card) w[k] += ld_tab<GT>(tab + b + k * sv);
     }
     stabilise_exp_floor<Real, MAXC>(w, card);
+    rb(0, w, card);
     return inverse_cdf<Real, MAXC>(w, card, u);
 }
 
@@ -348,11 +388,11 @@ __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real
 // record per factor; the two strides a dense pairwise table can give the updated variable (1 = last in the
 // scope, MAXC = first in the scope of an equal-cardinality pair) are compile-time, so the row's loads carry
 // immediate offsets.  Same factor order and arithmetic as lse_update_one_impl: identical results.
-template <typename Real, int MAXC, bool GT>
+template <typename Real, int MAXC, bool GT, typename Rec>
 __device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                                  const uint32_t stride, const int v, const int32_t pw, const int nf,
                                                  const uint32_t chain, const uint32_t sweep, const uint32_t seed_lo,
-                                                 const uint32_t seed_hi) {
+                                                 const uint32_t seed_hi, const Rec& rb) {
     const int4* __restrict__ rec = m.pw_rec + pw;
     Real u;
     if constexpr (std::is_same<Real, double>::value) {
@@ -383,33 +423,34 @@ __device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* 
         r = nx;
     }
     stabilise_exp_floor<Real, MAXC>(w, MAXC);
+    rb(0, w, MAXC);
     return inverse_cdf<Real, MAXC>(w, MAXC, u);
 }
 
 // cardinality buckets of the one-thread-per-chain body: exact unrolls for 2, 3, 11 (ObjectDetection) and MAXC;
 // variables with only unary and pairwise factors take the record-driven fast path
-template <typename Real, int MAXC, bool GT = true>
+template <typename Real, int MAXC, bool GT = true, typename Rec = NoRecord>
 __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                               const uint32_t stride, const int v, const int card, const int32_t pw, const int nf,
                                               const uint32_t chain, const uint32_t sweep, const uint32_t seed_lo,
-                                              const uint32_t seed_hi) {
+                                              const uint32_t seed_hi, const Rec& rb) {
     if constexpr (MAXC > 2) {
-        if (card == 2) return lse_update_one_impl<Real, 2, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+        if (card == 2) return lse_update_one_impl<Real, 2, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
     }
     if constexpr (MAXC > 3) {
-        if (card == 3) return lse_update_one_impl<Real, 3, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+        if (card == 3) return lse_update_one_impl<Real, 3, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
     }
     if constexpr (MAXC > 11) {
         if (card == 11) {
-            if (pw >= 0) return lse_update_one_pw<Real, 11, GT>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi);
-            return lse_update_one_impl<Real, 11, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+            if (pw >= 0) return lse_update_one_pw<Real, 11, GT, Rec>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi, rb);
+            return lse_update_one_impl<Real, 11, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
         }
     }
     if (card == MAXC) {
-        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi);
-        return lse_update_one_impl<Real, MAXC, GT, true>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT, Rec>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi, rb);
+        return lse_update_one_impl<Real, MAXC, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
     }
-    return lse_update_one_impl<Real, MAXC, GT, false>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi);
+    return lse_update_one_impl<Real, MAXC, GT, false, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
 }
 
 // Hybrid mode (GB_HYBRID): a binary variable with a threshold table (<= 4096 configurations of its free
@@ -455,10 +496,11 @@ __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t t
 
 // One launch = one colour of one group.  Work item = (variable of the colour, quad of 4 chains);
 // consecutive threads take consecutive quads of the same variable.
-template <typename Real, int MAXC, int CW>
+template <typename Real, int MAXC, int CW, bool RB = false>  // RB: Rao-Blackwell bins instead of counts (g.rb is set)
 __global__ void __launch_bounds__(256)
 k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ vars, const int32_t n_vars_c,
                const uint32_t sweep, const int record, const int hist_half, const DevTab t, const int hybrid) {
+    using Rec = typename std::conditional<RB, RbRecord, NoRecord>::type;
     const Real* __restrict__ tab = tables_of<Real>(m);
     const int32_t n_quads = g.n_pad >> 2;
     const int64_t total = (int64_t)n_vars_c * n_quads;
@@ -478,8 +520,9 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
         if (tpo >= 0)
             tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
         else
-            lse_update_quad<Real, MAXC, CW>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo,
-                                            g.seed_hi, x);
+            lse_update_quad<Real, MAXC, CW, true, Rec>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep,
+                                                       g.seed_lo, g.seed_hi, x,
+                                                       Rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - 4 * q));
         const uint32_t packed = (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
         *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + 4 * q) = packed;
 
@@ -489,7 +532,9 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
             // chain.go:231-236: Marginal[value] += 1 — aggregated over the warp when it holds one variable
             const int v0 = __shfl_sync(mask, v, __ffs(mask) - 1);
             const bool uniform = __all_sync(mask, v == v0);
-            if (uniform) {
+            if constexpr (RB) {
+                // Rao-Blackwell estimator: the conditional was added to the bins inside the update
+            } else if (uniform) {
                 for (int k = 0; k < card; k++) {
                     int c = 0;
 #pragma unroll
@@ -580,12 +625,13 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 
 constexpr uint32_t kBulkChunk = 32768;  // bytes per cp.async.bulk (multiple of 16)
 
-template <typename Real, int MAXC, int CW, bool TS>  // CW = 0: one thread per chain (lse_update_one)
+template <typename Real, int MAXC, int CW, bool TS, bool RB = false>  // CW = 0: one thread per chain (lse_update_one)
 __global__ void __launch_bounds__(CW == 0 ? 512 : 256)
 k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
                  const int32_t n_half, const DevTab t, const int hybrid, const int32_t hist_off) {
+    using Rec = typename std::conditional<RB, RbRecord, NoRecord>::type;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     uint8_t* s_state = smem;                                                                  // [n_vars][CH]
@@ -632,12 +678,13 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const int v = pr.x;
                     const int lchain = cta_chain + cc;
                     const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)lchain);
-                    const int x = lse_update_one<Real, MAXC, !TS>(m, tab, s_state + cc, (uint32_t)CH, v, pr.y, pr.z, pr.w, chain, sweep,
-                                                                  g.seed_lo, g.seed_hi);
+                    const int x = lse_update_one<Real, MAXC, !TS, Rec>(
+                        m, tab, s_state + cc, (uint32_t)CH, v, pr.y, pr.z, pr.w, chain, sweep, g.seed_lo, g.seed_hi,
+                        Rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain));
                     s_state[(size_t)v * CH + cc] = (uint8_t)x;
                     if (record && lchain < g.n_chains) {
                         const int32_t coff = __ldg(m.card_off + v);
-                        atomicAdd(&s_counts[coff + x], 1u);
+                        if constexpr (!RB) atomicAdd(&s_counts[coff + x], 1u);
                         if (hist_half >= 0 && g.hist) hist_add(s_hist, g, m.total_card, hist_half, coff + x, CH, cc, lchain);
                     }
                 }
@@ -653,8 +700,9 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     if (tpo >= 0)
                         tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
                     else
-                        lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep,
-                                                                        g.seed_lo, g.seed_hi, x);
+                        lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS, Rec>(
+                            m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x,
+                            Rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain));
                     *reinterpret_cast<uint32_t*>(s_state + (size_t)v * CH + 4 * q) =
                         (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
                     if (record) {
@@ -662,7 +710,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                         const int32_t coff = __ldg(m.card_off + v);
 #pragma unroll
                         for (int ci = 0; ci < 4; ci++)
-                            if (ci < nvalid) atomicAdd(&s_counts[coff + x[ci]], 1u);
+                            if (ci < nvalid && !RB) atomicAdd(&s_counts[coff + x[ci]], 1u);
                         if (hist_half >= 0 && g.hist) {
 #pragma unroll
                             for (int ci = 0; ci < 4; ci++)
@@ -1323,12 +1371,12 @@ k_chain_dist(const DevModel m, const DevGroup g, const double* __restrict__ merg
 // uniform marginal 1/card (model/variable.go:45) and adds its counts
 __global__ void __launch_bounds__(256)
 k_merge_partial(const DevModel m, const unsigned long long* __restrict__ counts, const double n_chains,
-                const uint8_t* __restrict__ skip, double* __restrict__ out) {
+                const uint8_t* __restrict__ skip, double* __restrict__ out, const double count_unit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.total_card) return;
     const int v = m.entry_var[i];
     if (skip[v] & 1) return;
-    out[i] += n_chains * (1.0 / (double)m.card[v]) + (double)counts[i];
+    out[i] += n_chains * (1.0 / (double)m.card[v]) + (double)counts[i] * count_unit;  // 1, or 2^-24 for the Rao-Blackwell bins
 }
 
 }  // namespace gb

@@ -56,6 +56,12 @@ enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2, GB_HYBRID = 3 };
 /* gb_chains_create flags */
 #define GB_CHAINS_HISTORY 1u /* keep per-chain half-window histograms (needed by gb_chains_convergence*) */
 #define GB_CHAINS_PER_COLOUR 2u /* always launch one kernel per colour (disables the shared-memory-resident multi-sweep kernels small models use; same results) */
+/* Rao-Blackwell marginal estimator (NOT the reference's estimator, hence a flag): a recorded update adds
+ * the conditional it sampled from, p_k = e[k] / sum(e) (gibbs-simple.go:239-258 weights), to every bin of the variable
+ * instead of Marginal[value] += 1 (chain.go:235).  Same expectation, lower variance.  Bins are 64-bit fixed point in
+ * units of 2^-24 (gb_chains_group_counts returns them raw); merged marginals, TotalSampleCount, histories and
+ * convergence scores keep their meaning.  GB_F64 / GB_F32 only. */
+#define GB_CHAINS_RAO_BLACKWELL 4u
 
 const char* gb_last_error(void);
 int gb_version(void);

@@ -592,7 +592,7 @@ int orc_sweep_run(void* sampler, const int* order, int n_order, unsigned long lo
     size_t nv = h->model->vars.size();
     for (int c = 0; c < n_chains; c++)
         sweep_chain(*h->simple, ord, seed, chain0 + (unsigned)c, sweep0, n_sweeps, bits, record != 0,
-                    states + (size_t)c * nv, off, counts);
+                    states + (size_t)c * nv, off, counts, nullptr, record == 2);  // record 2 = Rao-Blackwell bins
     ORC_END
 }
 

@@ -13,6 +13,8 @@
 // the device trajectory validates gathers, index math, floor, inverse CDF, Philox,
 // counting AND the colouring.
 #pragma once
+#include <cmath>
+
 #include "sampler.hpp"
 
 namespace oracle {
@@ -61,7 +63,8 @@ struct FixedUniform : Generator {
 // for tabulated variables and 53 bits for the others; nullptr = `bits` for every variable.
 inline void sweep_chain(GibbsSimple& gs, const std::vector<int>& order, uint64_t seed, uint32_t chain,
                         uint32_t sweep0, uint32_t n_sweeps, int bits, bool record, int* state,
-                        const std::vector<int>& count_off, double* counts, const int* var_bits = nullptr) {
+                        const std::vector<int>& count_off, double* counts, const int* var_bits = nullptr,
+                        bool rao_blackwell = false) {
     FixedUniform fu;
     UniformSampler us(&fu, 1);
     std::vector<double> w;
@@ -76,7 +79,16 @@ inline void sweep_chain(GibbsSimple& gs, const std::vector<int>& order, uint64_t
                 k = (int)w.size() - 1;  // device convention for the (measure-zero) fall-through
             }
             state[v] = k;
-            if (record && !gs.pgm->vars[v].collapsed) counts[count_off[v] + k] += 1.0;
+            if (record && !gs.pgm->vars[v].collapsed) {
+                if (rao_blackwell) {  // the device's GB_CHAINS_RAO_BLACKWELL bins: round(p_k * 2^24) for every value
+                    double tot = 0.0;
+                    for (double e : w) tot += e;
+                    const double scale = 16777216.0 / tot;
+                    for (size_t i = 0; i < w.size(); i++) counts[count_off[v] + i] += std::floor(w[i] * scale + 0.5);
+                } else {
+                    counts[count_off[v] + k] += 1.0;
+                }
+            }
         }
     }
 }
