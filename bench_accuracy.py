@@ -55,8 +55,9 @@ def first_below(samples, values, thr=0.01):
 
 
 def device_curve(gb, model, mar_cards, mar, n_chains, burn_sweeps, sweeps_per_point, points, precision, seed,
-                 fixed=None, adaptive=None):
-    ch = gb.Chains(model, n_chains, seed=seed, precision=precision, history=adaptive is not None, device=0)
+                 fixed=None, adaptive=None, rao_blackwell=False):
+    ch = gb.Chains(model, n_chains, seed=seed, precision=precision, history=adaptive is not None, device=0,
+                   rao_blackwell=rao_blackwell)
     ch.burnin(burn_sweeps)
     out = {"samples": [], "with_prior": [], "counts_only": [], "groups": []}
     cards = model.cards
@@ -90,102 +91,113 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--configs", default="0,1,2,3", help="comma-separated BASELINE config numbers to run")
     args = ap.parse_args()
+    sel = {int(x) for x in args.configs.split(",")}
     import grample_b200 as gb
     import oracle
 
     q = 4 if args.quick else 1
     doc = {"note": "equal recorded single-variable updates; errors vs res/*.uai.MAR; 'not reached' = None", "configs": {}}
 
-    # ---- config 0: Grids_11, oracle 4 chains (reference curve) + device table mode
-    name = "Grids_11.uai"
-    cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
-    ref = oracle_curve(name, False, oracle.SIMPLE, 4, 2000 * 100 // q, 2000, 20000 * 100 // q, seed=1)
-    dm = gb.Model.from_uai(os.path.join(RES, name), device=0)
-    dev = device_curve(gb, dm, cards, mar, 64, 2000 // q, 40 // q or 1, 8, gb.TABLE, seed=1)
-    doc["configs"]["0_Grids_11_simple"] = {"oracle_4_chains_random_scan": ref, "device_64_chains_table": dev}
+    if 0 in sel:
+        # ---- config 0: Grids_11, oracle 4 chains (reference curve) + device table mode
+        name = "Grids_11.uai"
+        cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
+        ref = oracle_curve(name, False, oracle.SIMPLE, 4, 2000 * 100 // q, 2000, 20000 * 100 // q, seed=1)
+        dm = gb.Model.from_uai(os.path.join(RES, name), device=0)
+        dev = device_curve(gb, dm, cards, mar, 64, 2000 // q, 40 // q or 1, 8, gb.TABLE, seed=1)
+        doc["configs"]["0_Grids_11_simple"] = {"oracle_4_chains_random_scan": ref, "device_64_chains_table": dev}
 
-    # ---- config 1: Promedus_11 + evidence
-    name = "Promedus_11.uai"
-    cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
-    dm = gb.Model.from_uai(os.path.join(RES, name), use_evidence=True, device=0)
-    fixed = dm.fixed
-    ref = oracle_curve(name, True, oracle.SIMPLE, 4, 2000 * 461 // q, 2000, 16_000_000 // q, seed=1)
-    dev = {}
-    for label, prec in (("f64", gb.F64), ("f32", gb.F32)):
-        dev[label] = device_curve(gb, dm, cards, mar, 4096, 2000 // q, 1, 8, prec, seed=42, fixed=fixed)
-    doc["configs"]["1_Promedus_11_evid_simple_4096_chains"] = {"oracle_4_chains_random_scan": ref, "device": dev,
-                                                               "table_mode_applies": dm.table_mode()[0]}
+    if 1 in sel:
+        # ---- config 1: Promedus_11 + evidence
+        name = "Promedus_11.uai"
+        cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
+        dm = gb.Model.from_uai(os.path.join(RES, name), use_evidence=True, device=0)
+        fixed = dm.fixed
+        ref = oracle_curve(name, True, oracle.SIMPLE, 4, 2000 * 461 // q, 2000, 16_000_000 // q, seed=1)
+        dev = {}
+        for label, prec in (("f64", gb.F64), ("f32", gb.F32)):
+            dev[label] = device_curve(gb, dm, cards, mar, 4096, 2000 // q, 1, 8, prec, seed=42, fixed=fixed)
+        doc["configs"]["1_Promedus_11_evid_simple_4096_chains"] = {"oracle_4_chains_random_scan": ref, "device": dev,
+                                                                   "table_mode_applies": dm.table_mode()[0]}
 
-    # ---- config 2: Pedigree_11 + evidence, adaptive
-    name = "Pedigree_11.uai"
-    cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
-    dm = gb.Model.from_uai(os.path.join(RES, name), use_evidence=True, device=0)
-    fixed = dm.fixed
-    ref = oracle_curve(name, True, oracle.ADAPTIVE, 2, 2000, 2000, 40_000_000 // q, seed=1, chain_adds=4)
-    # device: base group + up to 127 single-collapsed variants x 64 replicas = 8192 chains (MaxChains = 128)
-    dev = device_curve(gb, dm, cards, mar, 64, 2000 // q, 0, 34 // q or 2, gb.F32, seed=7, fixed=fixed,
-                       adaptive={"cw": 200, "chain_adds": 4, "per_group": 64, "adapt_rounds": 32 // q})
-    doc["configs"]["2_Pedigree_11_evid_adaptive"] = {"oracle_adaptive_2_start_chains_plus_4": ref, "device_64_per_variant": dev}
+    if 2 in sel:
+        # ---- config 2: Pedigree_11 + evidence, adaptive
+        name = "Pedigree_11.uai"
+        cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
+        dm = gb.Model.from_uai(os.path.join(RES, name), use_evidence=True, device=0)
+        fixed = dm.fixed
+        ref = oracle_curve(name, True, oracle.ADAPTIVE, 2, 2000, 2000, 40_000_000 // q, seed=1, chain_adds=4)
+        # device: base group + up to 127 single-collapsed variants x 64 replicas = 8192 chains (MaxChains = 128)
+        dev = device_curve(gb, dm, cards, mar, 64, 2000 // q, 0, 34 // q or 2, gb.F32, seed=7, fixed=fixed,
+                           adaptive={"cw": 200, "chain_adds": 4, "per_group": 64, "adapt_rounds": 32 // q})
+        doc["configs"]["2_Pedigree_11_evid_adaptive"] = {"oracle_adaptive_2_start_chains_plus_4": ref, "device_64_per_variant": dev}
 
-    # ---- config 3: ObjectDetection_11
-    name = "ObjectDetection_11.uai"
-    cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
-    offs = np.concatenate([[0], np.cumsum(cards)])
-    dm = gb.Model.from_uai(os.path.join(RES, name), device=0)
-    tractable = [v for v in range(dm.n_vars) if dm.blanket_size(v) <= 7]
-    # (a) simple sampler: the one configuration where mean Hellinger < 0.01 is reachable
-    ref_simple = oracle_curve(name, False, oracle.SIMPLE, 4, 2000 * 60 // q, 2000, 3_000_000 // q, seed=3)
-    dev_simple = device_curve(gb, dm, cards, mar, 16, 2000 // q, 160 // q or 1, 20, gb.F32, seed=2024)
-    # (b) collapsed: one collapsed variable per variant.  The reference's Collapse(-1) only checks the
-    # blanket COUNT and then aborts on the 2^23 table cap for 19 of the 60 variables, so both sides
-    # collapse the same 8 tractable variables.  A collapsed variable is REPORTED with its local blanket
-    # marginal (chain.go:113-129), which is not its exact marginal: that bias is the algorithm's.
-    chosen = sorted(int(v) for v in np.random.default_rng(5).choice(tractable, size=8, replace=False))
-    om = oracle.Model.load(os.path.join(RES, name))
-    sol = oracle.solution_load(os.path.join(RES, name + ".MAR"))
-    gen = oracle.Generator(3)
-    keep, ochains = [], []
-    for v in chosen:
-        m = om.clone()
-        sp = oracle.Sampler(gen, m, collapsed=True, lean=True)
-        sp.collapse(v)
-        c = oracle.Chain(m, sp, cw=2000, burn_in=2000 * 60 // q)
-        keep.append((m, sp))
-        ochains.append(c)
-    ref_col = {"samples": [], "mean_hellinger": [], "max_hellinger": [], "mean_abs": []}
-    for _ in range(6):
-        for c in ochains:
-            c.advance()
-        merged, _ = oracle.merge_chains(ochains, int(cards.sum()), dm.n_vars)
-        e = hel(gb, cards, mar, merged)
-        ref_col["samples"].append(sum(c.total_sample_count for c in ochains))
-        for k in ("mean_hellinger", "max_hellinger", "mean_abs"):
-            ref_col[k].append(e[k])
-    variants = [dm.collapse(v)[0] for v in chosen]
-    t = time.time()
-    ch = gb.Chains(variants, [8] * len(variants), seed=9, precision=gb.F32, device=0)
-    ch.burnin(2000 // q)
-    dev_col = {"samples": [], "with_prior": [], "counts_only": []}
-    for p in range(16):
-        ch.sweep(200 // q or 1)
-        merged, col = ch.merged_marginals()
-        prior = np.concatenate([np.full(c, ch.n_chains / c) for c in cards])
-        counts = merged - prior
-        for v in np.nonzero(col)[0]:
-            counts[offs[v]:offs[v + 1]] = merged[offs[v]:offs[v + 1]]
-        dev_col["samples"].append(ch.total_samples)
-        dev_col["with_prior"].append(hel(gb, cards, mar, merged))
-        dev_col["counts_only"].append(hel(gb, cards, mar, np.maximum(counts, 0) + 1e-9))
-    dev_col["seconds"] = time.time() - t
-    doc["configs"]["3_ObjectDetection_11"] = {
-        "tractable_variables": len(tractable), "collapsed_variables": chosen,
-        "simple": {"oracle_4_chains_random_scan": ref_simple, "device_16_chains_f32": dev_simple,
-                   "samples_to_mean_hellinger_below_0.01": {
-                       "oracle": first_below(ref_simple["samples"], ref_simple["mean_hellinger"]),
-                       "device_with_prior": first_below(dev_simple["samples"], [x["mean_hellinger"] for x in dev_simple["with_prior"]]),
-                       "device_counts_only": first_below(dev_simple["samples"], [x["mean_hellinger"] for x in dev_simple["counts_only"]])}},
-        "collapsed": {"oracle_8_chains_same_variables": ref_col, "device_8_variants_x_8_chains_f32": dev_col}}
+    if 3 in sel:
+        # ---- config 3: ObjectDetection_11
+        name = "ObjectDetection_11.uai"
+        cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
+        offs = np.concatenate([[0], np.cumsum(cards)])
+        dm = gb.Model.from_uai(os.path.join(RES, name), device=0)
+        tractable = [v for v in range(dm.n_vars) if dm.blanket_size(v) <= 7]
+        # (a) simple sampler: the one configuration where mean Hellinger < 0.01 is reachable
+        ref_simple = oracle_curve(name, False, oracle.SIMPLE, 4, 2000 * 60 // q, 2000, 3_000_000 // q, seed=3)
+        dev_simple = device_curve(gb, dm, cards, mar, 16, 2000 // q, 40 // q or 1, 80, gb.F32, seed=2024)
+        # same trajectory, Rao-Blackwell bins instead of counts (GB_CHAINS_RAO_BLACKWELL; not the reference's estimator)
+        dev_rb = device_curve(gb, dm, cards, mar, 16, 2000 // q, 40 // q or 1, 80, gb.F32, seed=2024, rao_blackwell=True)
+        # (b) collapsed: one collapsed variable per variant.  The reference's Collapse(-1) only checks the
+        # blanket COUNT and then aborts on the 2^23 table cap for 19 of the 60 variables, so both sides
+        # collapse the same 8 tractable variables.  A collapsed variable is REPORTED with its local blanket
+        # marginal (chain.go:113-129), which is not its exact marginal: that bias is the algorithm's.
+        chosen = sorted(int(v) for v in np.random.default_rng(5).choice(tractable, size=8, replace=False))
+        om = oracle.Model.load(os.path.join(RES, name))
+        sol = oracle.solution_load(os.path.join(RES, name + ".MAR"))
+        gen = oracle.Generator(3)
+        keep, ochains = [], []
+        for v in chosen:
+            m = om.clone()
+            sp = oracle.Sampler(gen, m, collapsed=True, lean=True)
+            sp.collapse(v)
+            c = oracle.Chain(m, sp, cw=2000, burn_in=2000 * 60 // q)
+            keep.append((m, sp))
+            ochains.append(c)
+        ref_col = {"samples": [], "mean_hellinger": [], "max_hellinger": [], "mean_abs": []}
+        for _ in range(6):
+            for c in ochains:
+                c.advance()
+            merged, _ = oracle.merge_chains(ochains, int(cards.sum()), dm.n_vars)
+            e = hel(gb, cards, mar, merged)
+            ref_col["samples"].append(sum(c.total_sample_count for c in ochains))
+            for k in ("mean_hellinger", "max_hellinger", "mean_abs"):
+                ref_col[k].append(e[k])
+        variants = [dm.collapse(v)[0] for v in chosen]
+        t = time.time()
+        ch = gb.Chains(variants, [8] * len(variants), seed=9, precision=gb.F32, device=0)
+        ch.burnin(2000 // q)
+        dev_col = {"samples": [], "with_prior": [], "counts_only": []}
+        for p in range(16):
+            ch.sweep(200 // q or 1)
+            merged, col = ch.merged_marginals()
+            prior = np.concatenate([np.full(c, ch.n_chains / c) for c in cards])
+            counts = merged - prior
+            for v in np.nonzero(col)[0]:
+                counts[offs[v]:offs[v + 1]] = merged[offs[v]:offs[v + 1]]
+            dev_col["samples"].append(ch.total_samples)
+            dev_col["with_prior"].append(hel(gb, cards, mar, merged))
+            dev_col["counts_only"].append(hel(gb, cards, mar, np.maximum(counts, 0) + 1e-9))
+        dev_col["seconds"] = time.time() - t
+        doc["configs"]["3_ObjectDetection_11"] = {
+            "tractable_variables": len(tractable), "collapsed_variables": chosen,
+            "simple": {"oracle_4_chains_random_scan": ref_simple, "device_16_chains_f32": dev_simple,
+                       "device_16_chains_f32_rao_blackwell": dev_rb,
+                       "samples_to_mean_hellinger_below_0.01": {
+                           "oracle": first_below(ref_simple["samples"], ref_simple["mean_hellinger"]),
+                           "device_with_prior": first_below(dev_simple["samples"], [x["mean_hellinger"] for x in dev_simple["with_prior"]]),
+                           "device_counts_only": first_below(dev_simple["samples"], [x["mean_hellinger"] for x in dev_simple["counts_only"]]),
+                           "device_rao_blackwell_with_prior": first_below(dev_rb["samples"], [x["mean_hellinger"] for x in dev_rb["with_prior"]]),
+                           "device_rao_blackwell_no_prior": first_below(dev_rb["samples"], [x["mean_hellinger"] for x in dev_rb["counts_only"]])}},
+            "collapsed": {"oracle_8_chains_same_variables": ref_col, "device_8_variants_x_8_chains_f32": dev_col}}
 
     text = json.dumps(doc, indent=1)
     if args.out:

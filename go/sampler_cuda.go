@@ -43,7 +43,18 @@ var (
 	Precision = C.GB_F32
 	// Device is the CUDA device the process drives (one process per GPU).
 	Device = 0
+	// RaoBlackwell makes recorded updates add the sampled conditional to every bin of the variable instead of
+	// Marginal[value] += 1 (chain.go:235); lower variance, NOT the reference's estimator (GB_F32 / GB_F64 only).
+	RaoBlackwell = false
 )
+
+func chainFlags() C.uint32_t {
+	f := C.uint32_t(C.GB_CHAINS_HISTORY)
+	if RaoBlackwell {
+		f |= C.GB_CHAINS_RAO_BLACKWELL
+	}
+	return f
+}
 
 func lastErr(what string) error { return errors.Errorf("%s: %s", what, C.GoString(C.gb_last_error())) }
 
@@ -229,7 +240,7 @@ func NewChain(mod *model.Model, samp FullSampler, cw int, burnIn int64) (*Chain,
 		models := []*C.gb_model{base.dev.h}
 		counts := []C.int32_t{C.int32_t(Replicas)}
 		seed := C.uint64_t(uint64(base.gen.Int63()))
-		if C.gb_chains_create(1, &models[0], &counts[0], seed, first, C.int(Precision), C.GB_CHAINS_HISTORY,
+		if C.gb_chains_create(1, &models[0], &counts[0], seed, first, C.int(Precision), chainFlags(),
 			C.int(Device), &thePool.h) != 0 {
 			return nil, lastErr("Could not create initial chain")
 		}

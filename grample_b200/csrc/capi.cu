@@ -499,15 +499,17 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
     size_t smem = 0;
     const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
-    static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
-    size_t& configured = configured_dev[c->device % kMaxDevices];
+    static size_t configured_dev[2][kMaxDevices] = {};  // function attributes are per device
+    const bool wide = h.tab_max_nbr > 8;
+    size_t& configured = configured_dev[wide][c->device % kMaxDevices];
+    auto kernel = wide ? gb::k_sweep_tab_resident<true> : gb::k_sweep_tab_resident<false>;
     if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_tab_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    gb::k_sweep_tab_resident<<<g.n_pad / p.ch, threads, smem, c->stream>>>(
-        g.model->dev, g.model->tab, g.dev, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, p.ch, g.sweep, n_sweeps, record,
-        n_pre, n_half, hist_off);
+    kernel<<<g.n_pad / p.ch, threads, smem, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.model->d_colour_off,
+                                                         (int32_t)h.colour_off.size() - 1, p.ch, g.sweep, n_sweeps, record, n_pre, n_half,
+                                                         hist_off);
     c->launches++;
 }
 

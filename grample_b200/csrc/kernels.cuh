@@ -236,26 +236,40 @@ struct NoRecord {  // plain counts: nothing to do inside the update (kernels wit
     __device__ __forceinline__ NoRecord(unsigned long long*, int) {}
     template <typename Real, int M>
     __device__ __forceinline__ void operator()(const int, const Real (&)[M], const int) const {}
+    __device__ __forceinline__ void flush(const int) const {}
 };
+template <int MAXC>
 struct RbRecord {
     unsigned long long* bins;  // counts + card_off[v]; nullptr = not recording
     int nvalid;                // chains of this work item that exist (the rest are padding)
-    __device__ __forceinline__ RbRecord(unsigned long long* b, int n) : bins(b), nvalid(n) {}
+    mutable unsigned acc[MAXC];  // this work item's fixed-point conditionals, summed over its chains (<= 4 x 2^24)
+    __device__ __forceinline__ RbRecord(unsigned long long* b, int n) : bins(b), nvalid(n) {
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) acc[k] = 0;
+    }
+    // called by the update with the floored weights of chain ci of the work item
     template <typename Real, int M>
     __device__ __forceinline__ void operator()(const int ci, const Real (&w)[M], const int card) const {
-        if (bins == nullptr) return;
+        static_assert(M <= MAXC, "weight vector longer than the accumulator");
+        if (bins == nullptr || ci >= nvalid) return;
         Real tot = 0;
 #pragma unroll
         for (int k = 0; k < M; k++)
             if (k < card) tot += w[k];
-        const Real scale = ci < nvalid ? (Real)kRbScale / tot : (Real)0;
+        const Real scale = (Real)kRbScale / tot;
+#pragma unroll
+        for (int k = 0; k < M; k++)
+            if (k < card) acc[k] += (unsigned)(w[k] * scale + (Real)0.5);
+    }
+    // once per work item: lanes of the warp that updated the same variable reduce first, one atomic per bin
+    __device__ __forceinline__ void flush(const int card) const {
+        if (bins == nullptr) return;
         const unsigned peers = __match_any_sync(__activemask(), reinterpret_cast<unsigned long long>(bins));
         const bool leader = (int)(threadIdx.x & 31u) == __ffs(peers) - 1;
 #pragma unroll
-        for (int k = 0; k < M; k++)
+        for (int k = 0; k < MAXC; k++)
             if (k < card) {
-                const unsigned q = (unsigned)(w[k] * scale + (Real)0.5);
-                const unsigned sum = __reduce_add_sync(peers, q);
+                const unsigned sum = __reduce_add_sync(peers, acc[k]);
                 if (leader && sum) atomicAdd(bins + k, (unsigned long long)sum);
             }
     }
@@ -500,7 +514,7 @@ template <typename Real, int MAXC, int CW, bool RB = false>  // RB: Rao-Blackwel
 __global__ void __launch_bounds__(256)
 k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ vars, const int32_t n_vars_c,
                const uint32_t sweep, const int record, const int hist_half, const DevTab t, const int hybrid) {
-    using Rec = typename std::conditional<RB, RbRecord, NoRecord>::type;
+    using Rec = typename std::conditional<RB, RbRecord<MAXC>, NoRecord>::type;
     const Real* __restrict__ tab = tables_of<Real>(m);
     const int32_t n_quads = g.n_pad >> 2;
     const int64_t total = (int64_t)n_vars_c * n_quads;
@@ -519,10 +533,12 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
         const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
         if (tpo >= 0)
             tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
-        else
+        else {
+            const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - 4 * q);
             lse_update_quad<Real, MAXC, CW, true, Rec>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep,
-                                                       g.seed_lo, g.seed_hi, x,
-                                                       Rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - 4 * q));
+                                                       g.seed_lo, g.seed_hi, x, rec);
+            rec.flush(card);
+        }
         const uint32_t packed = (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
         *reinterpret_cast<uint32_t*>(g.state + (size_t)v * g.n_pad + 4 * q) = packed;
 
@@ -631,7 +647,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
                  const int32_t n_half, const DevTab t, const int hybrid, const int32_t hist_off) {
-    using Rec = typename std::conditional<RB, RbRecord, NoRecord>::type;
+    using Rec = typename std::conditional<RB, RbRecord<MAXC>, NoRecord>::type;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     uint8_t* s_state = smem;                                                                  // [n_vars][CH]
@@ -678,9 +694,10 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const int v = pr.x;
                     const int lchain = cta_chain + cc;
                     const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)lchain);
-                    const int x = lse_update_one<Real, MAXC, !TS, Rec>(
-                        m, tab, s_state + cc, (uint32_t)CH, v, pr.y, pr.z, pr.w, chain, sweep, g.seed_lo, g.seed_hi,
-                        Rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain));
+                    const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain);
+                    const int x = lse_update_one<Real, MAXC, !TS, Rec>(m, tab, s_state + cc, (uint32_t)CH, v, pr.y, pr.z, pr.w, chain,
+                                                                       sweep, g.seed_lo, g.seed_hi, rec);
+                    rec.flush(pr.y);
                     s_state[(size_t)v * CH + cc] = (uint8_t)x;
                     if (record && lchain < g.n_chains) {
                         const int32_t coff = __ldg(m.card_off + v);
@@ -699,10 +716,12 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
                     if (tpo >= 0)
                         tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
-                    else
-                        lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS, Rec>(
-                            m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x,
-                            Rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain));
+                    else {
+                        const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain);
+                        lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS, Rec>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0,
+                                                                                  sweep, g.seed_lo, g.seed_hi, x, rec);
+                        rec.flush(card);
+                    }
                     *reinterpret_cast<uint32_t*>(s_state + (size_t)v * CH + 4 * q) =
                         (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
                     if (record) {
@@ -1038,6 +1057,7 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
 // Work item = (sweep position, unit of 8 chains); same records, thresholds, Philox stream and tie rule
 // as k_sweep_tab, so the two paths produce identical trajectories.  Records and thresholds are read
 // through L1 (they are a few KB and shared by every CTA).
+template <bool WIDE>  // WIDE: some variable has more than 8 free neighbours (variable-length records, 32-bit configuration indices)
 __global__ void __launch_bounds__(256)
 k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ colour_off,
                      const int32_t n_colours, const int32_t ch_per_cta, const uint32_t sweep0, const int32_t n_sweeps,
@@ -1048,6 +1068,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
     const int CH = ch_per_cta;
     const int cta_chain = blockIdx.x * CH;
     const int units = CH >> 3;
+    const int unit_shift = 31 - __clz(units);
     for (int i = threadIdx.x; i < m.n_vars * units; i += blockDim.x) {
         const int v = i / units, q = i - v * units;
         *reinterpret_cast<uint2*>(s_state + (size_t)v * CH + 8 * q) =
@@ -1062,29 +1083,27 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
         for (int col = 0; col < n_colours; col++) {
             const int c0 = __ldg(colour_off + col), nvc = __ldg(colour_off + col + 1) - c0;
             for (int item = threadIdx.x; item < nvc * units; item += blockDim.x) {
-                const int j = item / units, q = item - j * units;
+                const int j = item >> unit_shift, q = item & (units - 1);  // units is a power of two (CH = 8..64)
                 const int4* r = reinterpret_cast<const int4*>(t.trec + (size_t)(c0 + j) * kTabRec);
                 const int4 hd = __ldg(r);  // v, thr_off, n_nbr, card_off
-                uint32_t T[8];
-                if (hd.z > 8) {
+                uint32_t cfg_lo = 0, cfg_hi = 0;
+                [[maybe_unused]] uint32_t idxw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                const bool wide = WIDE && hd.z > 8;
+                if (wide) {
                     // wide variable (more than 8 free neighbours, e.g. the neighbours of a collapsed variable): the
                     // record points at its variable-length tprog entry and the configuration index needs 32 bits
                     const int32_t* __restrict__ tp = t.tprog + __ldg(&r[1].x) + 2;
-                    uint32_t idx[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                     for (int i = 0; i < hd.z; i++) {
                         const int ov = __ldg(tp + 2 * i);
                         const uint32_t os = (uint32_t)__ldg(tp + 2 * i + 1);
                         const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)ov * CH + 8 * q);
 #pragma unroll
                         for (int ci = 0; ci < 4; ci++) {
-                            idx[ci] += ((w.x >> (8 * ci)) & 0xffu) * os;
-                            idx[4 + ci] += ((w.y >> (8 * ci)) & 0xffu) * os;
+                            idxw[ci] += ((w.x >> (8 * ci)) & 0xffu) * os;
+                            idxw[4 + ci] += ((w.y >> (8 * ci)) & 0xffu) * os;
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) T[i] = __ldg(t.thr + hd.y + idx[i]);
                 } else {
-                    uint32_t cfg_lo = 0, cfg_hi = 0;
                     {
                         const int4 na = __ldg(r + 1), sa = __ldg(r + 3);
                         const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
@@ -1105,18 +1124,18 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                             cfg_hi += w.y * (uint32_t)sb[i];
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        T[i] = __ldg(t.thr + hd.y + (((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu));
                 }
                 const int lchain = cta_chain + 8 * q;
                 const uint32_t chain_blk = (uint32_t)((g.first_chain + (uint64_t)lchain) >> 3);
                 const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
-                uint32_t xbits = 0;
+                uint32_t T[8], xbits = 0;
                 bool tie = false;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
+                    uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+                    if constexpr (WIDE) idx = wide ? idxw[i] : idx;
+                    T[i] = __ldg(t.thr + hd.y + idx);
                     const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
                     xbits |= (hi > (T[i] >> 16) ? 1u : 0u) << i;
                     tie |= hi == (T[i] >> 16);

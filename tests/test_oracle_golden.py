@@ -86,3 +86,28 @@ def test_host_schedule_matches_golden_colouring(res):
         order, coff = m.schedule()
         got = [sorted(int(v) for v in order[coff[c]:coff[c + 1]]) for c in range(len(coff) - 1)]
         assert got == [sorted(c) for c in t["colours"]], t["model"]
+
+
+def test_oracle_rao_blackwell_bins(res):
+    """oracle replay of GB_CHAINS_RAO_BLACKWELL (sweep_run(record=2)): same trajectory as the counting run; every
+    recorded update spreads 2^24 units over the variable's bins in proportion to the floored weights of
+    gibbs-simple.go:239-258 — re-derived here from the golden initial state for the first update of a trajectory"""
+    for t in _load("trajectories.json"):
+        order = [v for c in t["colours"] for v in c]
+        s = oracle.Sampler(oracle.Generator(1), oracle.Model.load(res(t["model"]), use_evidence=t["evidence"]))
+        init = np.asarray(t["initial"], dtype=np.int32)
+        st_c, counts = s.sweep_run(order, t["seed"], t["first_chain"], init, 0, t["n_sweeps"], bits=53, record=True)
+        st_r, bins = s.sweep_run(order, t["seed"], t["first_chain"], init, 0, t["n_sweeps"], bits=53, record=2)
+        assert np.array_equal(st_c, st_r)
+        cards = s.model.cards
+        off = np.concatenate([[0], np.cumsum(cards)])
+        n_chains = init.shape[0]
+        for v in order:
+            assert counts[off[v]:off[v + 1]].sum() == t["n_sweeps"] * n_chains
+            assert abs(bins[off[v]:off[v + 1]].sum() * 2.0 ** -24 - t["n_sweeps"] * n_chains) < 1e-4
+        # first update of chain 0 in isolation: one variable, one sweep, state = the initial state
+        v0 = order[0]
+        _, b1 = s.sweep_run([v0], t["seed"], t["first_chain"], init[:1], 0, 1, bits=53, record=2)
+        e = np.asarray(s.conditional(v0, init[0]), dtype=np.float64)
+        expect = np.floor(e * (16777216.0 / e.sum()) + 0.5)
+        assert np.array_equal(b1[off[v0]:off[v0 + 1]], expect), t["model"]
