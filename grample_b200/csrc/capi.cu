@@ -371,7 +371,7 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
 // Shared-memory-resident path for small models: all sweeps of one group in ONE launch.
 template <typename Real, int MAXC, int CW, bool TS, bool RB>
 void launch_resident_rb(gb_chains* c, Group& g, int ch, size_t smem, int32_t hist_off, int32_t n_sweeps, int record, int32_t n_pre,
-                        int32_t n_half) {
+                        int32_t n_half, int32_t n_stage) {
     // block size >= work items of the largest colour of one CTA (one item per thread keeps the
     // per-colour critical path at a single update), capped at 256
     const gb::HostModel& hm = g.model->h;
@@ -393,15 +393,15 @@ void launch_resident_rb(gb_chains* c, Group& g, int ch, size_t smem, int32_t his
     const gb::HostModel& h = g.model->h;
     gb::k_sweep_resident<Real, MAXC, CW, TS, RB><<<g.n_pad / ch, threads, smem, c->stream>>>(
         g.model->dev, g.dev, g.model->d_order, g.model->d_colour_off, (int32_t)h.colour_off.size() - 1, ch, g.sweep, n_sweeps,
-        record, n_pre, n_half, g.model->tab, (int)(c->precision == GB_HYBRID && g.model->hybrid_tables()), hist_off);
+        record, n_pre, n_half, g.model->tab, (int)(c->precision == GB_HYBRID && g.model->hybrid_tables()), hist_off, n_stage);
     c->launches++;
 }
 
 template <typename Real, int MAXC, int CW, bool TS>
 void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t hist_off, int32_t n_sweeps, int record, int32_t n_pre,
-                        int32_t n_half) {
-    if (g.dev.rb) launch_resident_rb<Real, MAXC, CW, TS, true>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
-    else launch_resident_rb<Real, MAXC, CW, TS, false>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
+                        int32_t n_half, int32_t n_stage) {
+    if (g.dev.rb) launch_resident_rb<Real, MAXC, CW, TS, true>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half, n_stage);
+    else launch_resident_rb<Real, MAXC, CW, TS, false>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half, n_stage);
 }
 
 // Resident-path launch plan: chains per CTA, dynamic shared memory, and whether the log-space tables are
@@ -410,6 +410,7 @@ struct ResidentPlan {
     int ch = 0;
     size_t smem = 0;
     bool ts = false;
+    int32_t n_stage = 0;  // table entries staged in shared memory: all of them (ts) or a prefix ending on a factor boundary
 };
 
 // Where the CTA's per-chain half-window histograms ([2][total_card][ch] u16) go for a launch that records
@@ -468,6 +469,29 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
             if (ch < 64 && (int64_t)(g.n_pad / ch) > per_sm * sms) continue;
             if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
             p.ch = ch; p.smem = smem; p.ts = true;
+            p.n_stage = (int32_t)(((size_t)h.log_tab.size() + 3) & ~(size_t)3);
+            return p;
+        }
+    // 1b) one-thread-per-chain kernels (cardinality >= 8): stage the longest PREFIX of the tables that fits and ends on
+    //     a factor boundary.  A collapsed variant keeps the model's small factors first and appends the large factor
+    //     over the collapsed variable's blanket (up to 11^6 entries on ObjectDetection_11), so every small factor is
+    //     served from shared memory and only the large one goes through L1/L2.
+    if (!no_ts && h.max_card >= 8)
+        for (int ch : {8, 16, 32, 64}) {
+            if (g.n_pad % ch) continue;
+            if (base(ch) + 4096 > kSmemPerCta) break;
+            const size_t budget = kSmemPerCta - base(ch) - 32;
+            int64_t n = 0;
+            for (const auto& f : h.funcs) {  // factors are laid out in this order
+                if ((size_t)((f.off + f.size + 3) & ~(int64_t)3) * real_bytes > budget) break;
+                n = f.off + f.size;
+            }
+            if (n == 0) break;
+            const size_t smem = base(ch) + 16 + (size_t)((n + 3) & ~(int64_t)3) * real_bytes;
+            const int64_t per_sm = std::min<int64_t>(8, (int64_t)(kSmemPerSm / (smem + 1024)));
+            if (ch < 64 && (int64_t)(g.n_pad / ch) > per_sm * sms) continue;
+            if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
+            p.ch = ch; p.smem = smem; p.n_stage = (int32_t)n;
             return p;
         }
     // 2) tables through L1: few chains per CTA = many CTAs = better SM fill and latency hiding; grow the
@@ -487,8 +511,8 @@ template <typename Real, int MAXC, int CW>
 void launch_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
     size_t smem = 0;
     const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
-    if (p.ts) launch_resident_ts<Real, MAXC, CW, true>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
-    else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half);
+    if (p.ts) launch_resident_ts<Real, MAXC, CW, true>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half, p.n_stage);
+    else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half, p.n_stage);
 }
 
 void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {

@@ -82,7 +82,16 @@ template <>
 __device__ __forceinline__ const float* tables_of<float>(const DevModel& m) { return m.tab32; }
 
 // Table reads: through the non-coherent global path (G = true) or plain loads when the tables have been
-// staged in shared memory (the compiler then emits LDS).
+// staged in shared memory (the compiler then emits LDS).  With G = true a PREFIX of the tables may still be
+// staged (StagedPrefix): a collapsed variant keeps the model's small factors first and appends the one large
+// factor over the collapsed variable's blanket (up to 11^6 entries on ObjectDetection_11), so the small factors
+// are served from shared memory and only the large one goes through L1/L2.  The prefix ends on a factor
+// boundary, hence the test is per factor (tab_off < n).
+template <typename Real>
+struct StagedPrefix {
+    const Real* s_tab;  // shared-memory copy of tab[0 .. n)
+    int32_t n;          // entries staged (0 = none)
+};
 template <bool G, typename Real>
 __device__ __forceinline__ Real ld_tab(const Real* p) {
     if constexpr (G) return __ldg(p);
@@ -368,7 +377,7 @@ template <typename Real, int MAXC, bool GT, bool EXACT, typename Rec>
 __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                                    const uint32_t stride, const int v, const int card_rt, const uint32_t chain,
                                                    const uint32_t sweep, const uint32_t seed_lo, const uint32_t seed_hi,
-                                                   const Rec& rb) {
+                                                   const Rec& rb, const StagedPrefix<Real>& sp) {
     const int card = EXACT ? MAXC : card_rt;
     const int32_t* __restrict__ p = m.prog + __ldg(m.prog_off + v);
     const int nf = __ldg(p++);
@@ -389,9 +398,15 @@ __device__ __forceinline__ int lse_update_one_impl(const DevModel& m, const Real
         p += 3;
         int b = tab_off;
         for (int o = 0; o < no; o++, p += 2) b += (int)cell[(size_t)__ldg(p) * stride] * __ldg(p + 1);
+        if (GT && tab_off < sp.n) {
 #pragma unroll
-        for (int k = 0; k < MAXC; k++)
-            if (k < card) w[k] += ld_tab<GT>(tab + b + k * sv);
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) w[k] += sp.s_tab[b + k * sv];
+        } else {
+#pragma unroll
+            for (int k = 0; k < MAXC; k++)
+                if (k < card) w[k] += ld_tab<GT>(tab + b + k * sv);
+        }
     }
     stabilise_exp_floor<Real, MAXC>(w, card);
     rb(0, w, card);
@@ -406,7 +421,7 @@ template <typename Real, int MAXC, bool GT, typename Rec>
 __device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                                  const uint32_t stride, const int v, const int32_t pw, const int nf,
                                                  const uint32_t chain, const uint32_t sweep, const uint32_t seed_lo,
-                                                 const uint32_t seed_hi, const Rec& rb) {
+                                                 const uint32_t seed_hi, const Rec& rb, const StagedPrefix<Real>& sp) {
     const int4* __restrict__ rec = m.pw_rec + pw;
     Real u;
     if constexpr (std::is_same<Real, double>::value) {
@@ -423,16 +438,31 @@ __device__ __forceinline__ int lse_update_one_pw(const DevModel& m, const Real* 
     int4 r = __ldg(rec);
     for (int f = 0; f < nf; f++) {
         const int4 nx = __ldg(rec + min(f + 1, nf - 1));  // next record in flight while this row is summed
-        const Real* __restrict__ row = tab + (r.x + (int)cell[(size_t)(uint32_t)r.z * stride] * r.w);
-        if (r.y == 1) {
+        const int b = r.x + (int)cell[(size_t)(uint32_t)r.z * stride] * r.w;
+        if (GT && r.x < sp.n) {  // factor inside the staged prefix: shared-memory row
+            const Real* __restrict__ row = sp.s_tab + b;
+            if (r.y == 1) {
 #pragma unroll
-            for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k);
-        } else if (r.y == MAXC) {
+                for (int k = 0; k < MAXC; k++) w[k] += row[k];
+            } else if (r.y == MAXC) {
 #pragma unroll
-            for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k * MAXC);
+                for (int k = 0; k < MAXC; k++) w[k] += row[k * MAXC];
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) w[k] += row[k * r.y];
+            }
         } else {
+            const Real* __restrict__ row = tab + b;
+            if (r.y == 1) {
 #pragma unroll
-            for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k * r.y);
+                for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k);
+            } else if (r.y == MAXC) {
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k * MAXC);
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) w[k] += ld_tab<GT>(row + k * r.y);
+            }
         }
         r = nx;
     }
@@ -447,24 +477,24 @@ template <typename Real, int MAXC, bool GT = true, typename Rec = NoRecord>
 __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __restrict__ tab, const uint8_t* cell,
                                               const uint32_t stride, const int v, const int card, const int32_t pw, const int nf,
                                               const uint32_t chain, const uint32_t sweep, const uint32_t seed_lo,
-                                              const uint32_t seed_hi, const Rec& rb) {
+                                              const uint32_t seed_hi, const Rec& rb, const StagedPrefix<Real>& sp) {
     if constexpr (MAXC > 2) {
-        if (card == 2) return lse_update_one_impl<Real, 2, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
+        if (card == 2) return lse_update_one_impl<Real, 2, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb, sp);
     }
     if constexpr (MAXC > 3) {
-        if (card == 3) return lse_update_one_impl<Real, 3, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
+        if (card == 3) return lse_update_one_impl<Real, 3, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb, sp);
     }
     if constexpr (MAXC > 11) {
         if (card == 11) {
-            if (pw >= 0) return lse_update_one_pw<Real, 11, GT, Rec>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi, rb);
-            return lse_update_one_impl<Real, 11, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
+            if (pw >= 0) return lse_update_one_pw<Real, 11, GT, Rec>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi, rb, sp);
+            return lse_update_one_impl<Real, 11, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb, sp);
         }
     }
     if (card == MAXC) {
-        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT, Rec>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi, rb);
-        return lse_update_one_impl<Real, MAXC, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
+        if (pw >= 0) return lse_update_one_pw<Real, MAXC, GT, Rec>(m, tab, cell, stride, v, pw, nf, chain, sweep, seed_lo, seed_hi, rb, sp);
+        return lse_update_one_impl<Real, MAXC, GT, true, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb, sp);
     }
-    return lse_update_one_impl<Real, MAXC, GT, false, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb);
+    return lse_update_one_impl<Real, MAXC, GT, false, Rec>(m, tab, cell, stride, v, card, chain, sweep, seed_lo, seed_hi, rb, sp);
 }
 
 // Hybrid mode (GB_HYBRID): a binary variable with a threshold table (<= 4096 configurations of its free
@@ -646,7 +676,9 @@ __global__ void __launch_bounds__(CW == 0 ? 512 : 256)
 k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ colour_off, const int32_t n_colours, const int32_t ch_per_cta,
                  const uint32_t sweep0, const int32_t n_sweeps, const int record, const int32_t n_pre,
-                 const int32_t n_half, const DevTab t, const int hybrid, const int32_t hist_off) {
+                 const int32_t n_half, const DevTab t, const int hybrid, const int32_t hist_off, const int32_t n_stage) {
+    // n_stage = table entries staged in shared memory (multiple of 4): all of them when TS, else a prefix that ends on
+    // a factor boundary (possibly empty) — see StagedPrefix
     using Rec = typename std::conditional<RB, RbRecord<MAXC>, NoRecord>::type;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -654,19 +686,22 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
     const size_t counts_off = ((size_t)m.n_vars * ch_per_cta + 15) & ~(size_t)15;
     unsigned int* s_counts = reinterpret_cast<unsigned int*>(smem + counts_off);              // [total_card]
     const Real* __restrict__ tab = tables_of<Real>(m);
-    if constexpr (TS) {
-        Real* s_tab = reinterpret_cast<Real*>(smem + ((counts_off + (size_t)m.total_card * 4 + 15) & ~(size_t)15));  // [n_tab]
+    StagedPrefix<Real> sp{nullptr, 0};
+    const bool staged = TS || n_stage > 0;
+    if (staged) {
+        Real* s_tab = reinterpret_cast<Real*>(smem + ((counts_off + (size_t)m.total_card * 4 + 15) & ~(size_t)15));  // [n_stage]
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t bytes = (uint32_t)m.n_tab * (uint32_t)sizeof(Real);
+            const uint32_t bytes = (uint32_t)((n_stage + 3) & ~3) * (uint32_t)sizeof(Real);  // 16-byte granules (the device tables are padded)
             mbar_expect_tx(bar, bytes);
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab);
             for (uint32_t off = 0; off < bytes; off += kBulkChunk)
                 tma_bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(tab) + off, min(kBulkChunk, bytes - off), bar);
         }
-        tab = s_tab;
+        if constexpr (TS) tab = s_tab;
+        else sp = StagedPrefix<Real>{s_tab, n_stage};
     }
     const int CH = ch_per_cta;
     const int cta_chain = blockIdx.x * CH;  // local index of this CTA's first chain
@@ -679,7 +714,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
     }
     for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
     uint16_t* s_hist = hist_begin(smem, n_half >= 0 ? hist_off : -1, g, m.total_card, ch_per_cta);
-    if constexpr (TS) mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0);  // the tables have landed
+    if (staged) mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0);  // the tables have landed
     __syncthreads();
     for (int s = 0; s < n_sweeps; s++) {
         const uint32_t sweep = sweep0 + (uint32_t)s;
@@ -696,7 +731,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     const uint32_t chain = (uint32_t)(g.first_chain + (uint64_t)lchain);
                     const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain);
                     const int x = lse_update_one<Real, MAXC, !TS, Rec>(m, tab, s_state + cc, (uint32_t)CH, v, pr.y, pr.z, pr.w, chain,
-                                                                       sweep, g.seed_lo, g.seed_hi, rec);
+                                                                       sweep, g.seed_lo, g.seed_hi, rec, sp);
                     rec.flush(pr.y);
                     s_state[(size_t)v * CH + cc] = (uint8_t)x;
                     if (record && lchain < g.n_chains) {
