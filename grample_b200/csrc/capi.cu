@@ -413,14 +413,19 @@ struct ResidentPlan {
     int32_t n_stage = 0;  // table entries staged in shared memory: all of them (ts) or a prefix ending on a factor boundary
 };
 
+bool tab_resident(const gb_chains* c, const Group& g);
+
 // Where the CTA's per-chain half-window histograms ([2][total_card][ch] u16) go for a launch that records
 // them: appended to the resident layout when that still fits (returns the byte offset and grows *smem),
 // else -1 = updated in global memory.
 int32_t place_histograms(const gb_chains* c, const Group& g, const ResidentPlan& p, int32_t n_half, size_t* smem) {
     *smem = p.smem;
     if (!(c->flags & GB_CHAINS_HISTORY) || n_half < 0 || !g.d_hist) return -1;
+    if (std::getenv("GB_HIST_GLOBAL")) return -1;  // A/B knob: histograms updated in global memory
     const size_t off = (p.smem + 15) & ~(size_t)15;
-    const size_t bytes = (size_t)2 * g.model->h.total_card * p.ch * sizeof(uint16_t);
+    // the resident table kernel keeps only the ones of its (binary) variables: [2][n_vars][ch]; the others [2][total_card][ch]
+    const size_t rows = tab_resident(c, g) ? (size_t)g.model->h.n_vars : (size_t)g.model->h.total_card;
+    const size_t bytes = (size_t)2 * rows * p.ch * sizeof(uint16_t);
     if (off + bytes > (p.ts ? 160 : 100) * 1024) return -1;
     *smem = off + bytes;
     return (int32_t)off;

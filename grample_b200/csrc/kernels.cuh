@@ -611,9 +611,43 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
 // launch), else read-modify-write in global memory.  entry = card_off[v] + value; cc = chain within the CTA.
 __device__ __forceinline__ void hist_add(uint16_t* s_hist, const DevGroup& g, const int total_card, const int half,
                                          const int entry, const int CH, const int cc, const int lchain) {
-    uint16_t* h = s_hist ? s_hist + ((size_t)half * total_card + entry) * CH + cc
-                         : g.hist + ((size_t)half * total_card + entry) * g.n_pad + lchain;
-    *h = (uint16_t)(*h + 1);
+    if (s_hist) {  // two code paths instead of one generic pointer: LDS/STS or LDG/STG
+        uint16_t* h = s_hist + ((size_t)half * total_card + entry) * CH + cc;
+        *h = (uint16_t)(*h + 1);
+    } else {
+        uint16_t* h = g.hist + ((size_t)half * total_card + entry) * g.n_pad + lchain;
+        *h = (uint16_t)(*h + 1);
+    }
+}
+// Table kernels: the 8 chains of a work unit are contiguous, and a binary variable has two histogram rows, so the 16
+// read-modify-writes of 2 bytes become two 16-byte ones: bit i of `ones` / `zeros` is added to the 16-bit lane of
+// chain i (lanes cannot carry into each other: a half window holds < 65536 samples).  Rows are 16-byte aligned
+// (CH, n_pad and the unit's first chain are multiples of 8).
+__device__ __forceinline__ uint4 spread_bits16(const uint32_t b) {  // bit i -> 16-bit lane i of a uint4
+    uint4 r;
+    r.x = ((b & 3u) | ((b & 3u) << 15)) & 0x00010001u;
+    r.y = (((b >> 2) & 3u) | (((b >> 2) & 3u) << 15)) & 0x00010001u;
+    r.z = (((b >> 4) & 3u) | (((b >> 4) & 3u) << 15)) & 0x00010001u;
+    r.w = (((b >> 6) & 3u) | (((b >> 6) & 3u) << 15)) & 0x00010001u;
+    return r;
+}
+__device__ __forceinline__ void add_row16(uint4* row, const uint4 inc) {
+    uint4 h = *row;
+    h.x += inc.x; h.y += inc.y; h.z += inc.z; h.w += inc.w;
+    *row = h;
+}
+__device__ __forceinline__ void hist_add8_binary(uint16_t* s_hist, const DevGroup& g, const int total_card, const int half,
+                                                 const int coff, const int CH, const int cc0, const int lchain0,
+                                                 const uint32_t ones, const uint32_t zeros) {
+    if (s_hist) {
+        uint16_t* r0 = s_hist + ((size_t)half * total_card + coff) * CH + cc0;
+        add_row16(reinterpret_cast<uint4*>(r0), spread_bits16(zeros));
+        add_row16(reinterpret_cast<uint4*>(r0 + CH), spread_bits16(ones));
+    } else {
+        uint16_t* r0 = g.hist + ((size_t)half * total_card + coff) * g.n_pad + lchain0;
+        add_row16(reinterpret_cast<uint4*>(r0), spread_bits16(zeros));
+        add_row16(reinterpret_cast<uint4*>(r0 + g.n_pad), spread_bits16(ones));
+    }
 }
 __device__ __forceinline__ uint16_t* hist_begin(uint8_t* smem, const int32_t hist_off, const DevGroup& g, const int total_card,
                                                 const int CH) {
@@ -986,14 +1020,8 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
                 outw.y = (((xbits >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
                 if (lane_valid) st_state8(my + (uint64_t)(uint32_t)hd.x * n_pad, outw);
                 if constexpr (HIST) {
-                    if (record && hist_half >= 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            if (i < nvalid) {
-                                uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + hd.w + ((xbits >> i) & 1u)) * g.n_pad + 8 * (size_t)unit + i;
-                                *h = (uint16_t)(*h + 1);
-                            }
-                    }
+                    if (record && hist_half >= 0 && lane_valid)
+                        hist_add8_binary(nullptr, g, m.total_card, hist_half, hd.w, 0, 0, 8 * unit, xbits & vmask, ~xbits & vmask);
                 }
                 // chain.go:231-236: this thread's ones of the variable go into nibble `slot` of the group accumulator
                 acc += (uint32_t)__popc(xbits & vmask) << (4 * slot);
@@ -1110,7 +1138,14 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
             *reinterpret_cast<const uint2*>(g.state + (size_t)v * g.n_pad + cta_chain + 8 * q);
     }
     for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
-    uint16_t* s_hist = hist_begin(smem, n_half >= 0 ? hist_off : -1, g, m.total_card, ch_per_cta);
+    // Shared-memory histograms of this kernel hold only the ONES of every (binary) variable, [2][n_vars][CH] u16 — half the
+    // footprint, so twice the CTAs stay co-resident; the zeros are (recorded sweeps of the half) - ones, added at the flush.
+    uint16_t* s_hist = nullptr;
+    if (n_half >= 0 && hist_off >= 0 && g.hist) {
+        s_hist = reinterpret_cast<uint16_t*>(smem + hist_off);
+        for (int i = threadIdx.x; i < 2 * m.n_vars * (ch_per_cta >> 3); i += blockDim.x)
+            reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     for (int s = 0; s < n_sweeps; s++) {
         const uint32_t sweep = sweep0 + (uint32_t)s;
@@ -1196,10 +1231,11 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                     if (ones) atomicAdd(&s_counts[hd.w + 1], (unsigned)ones);
                     if (nvalid - ones) atomicAdd(&s_counts[hd.w], (unsigned)(nvalid - ones));
                     if (hist_half >= 0 && g.hist) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            if (i < nvalid)
-                                hist_add(s_hist, g, m.total_card, hist_half, hd.w + (int)((xbits >> i) & 1u), CH, 8 * q + i, lchain + i);
+                        if (s_hist)
+                            add_row16(reinterpret_cast<uint4*>(s_hist + ((size_t)hist_half * m.n_vars + hd.x) * CH + 8 * q),
+                                      spread_bits16(xbits & vmask));
+                        else
+                            hist_add8_binary(nullptr, g, m.total_card, hist_half, hd.w, CH, 8 * q, lchain, xbits & vmask, ~xbits & vmask);
                     }
                 }
             }
@@ -1214,7 +1250,25 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
     if (record)
         for (int i = threadIdx.x; i < m.total_card; i += blockDim.x)
             if (s_counts[i]) atomicAdd(g.counts + i, (unsigned long long)s_counts[i]);
-    hist_flush(s_hist, g, m.total_card, CH, cta_chain);
+    if (s_hist && record) {
+        // recorded sweeps of this launch that fell into each half window (the schedule of the sweep loop above)
+        const int b0 = max(0, n_pre), e0 = min(n_sweeps, n_pre + n_half);
+        const int n_rec[2] = {max(0, e0 - b0), max(0, n_sweeps - max(0, n_pre + n_half))};
+        for (int i = threadIdx.x; i < 2 * m.n_vars * units; i += blockDim.x) {  // (half, variable, unit of 8 chains): 16-byte rows
+            const int e = i >> unit_shift, u = i & (units - 1);
+            const int half = e >= m.n_vars ? 1 : 0, v = e - half * m.n_vars;
+            const int nvalid = min(8, g.n_chains - (cta_chain + 8 * u));
+            if (n_rec[half] == 0 || nvalid <= 0 || __ldg(t.tp_off + v) < 0) continue;  // nothing recorded / padding / not sampled
+            const uint4 ones = *reinterpret_cast<const uint4*>(s_hist + (size_t)e * CH + 8 * u);
+            const uint4 lanes = spread_bits16(nvalid >= 8 ? 0xffu : ((1u << nvalid) - 1u));  // 1 in the lanes of existing chains
+            const uint32_t nr = (uint32_t)n_rec[half];
+            uint4 zeros;  // per 16-bit lane: recorded sweeps - ones (no borrow: ones <= recorded sweeps)
+            zeros.x = lanes.x * nr - ones.x; zeros.y = lanes.y * nr - ones.y; zeros.z = lanes.z * nr - ones.z; zeros.w = lanes.w * nr - ones.w;
+            uint16_t* h = g.hist + ((size_t)half * m.total_card + __ldg(m.card_off + v)) * g.n_pad + cta_chain + 8 * u;
+            add_row16(reinterpret_cast<uint4*>(h), zeros);
+            add_row16(reinterpret_cast<uint4*>(h + g.n_pad), ones);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ K6
