@@ -158,7 +158,9 @@ def build_parser():
     s.add_argument("-x", "--maxsecs", type=int, default=300)
     s.add_argument("-p", "--experiment", action="store_true")
     s.add_argument("--replicas", type=int, default=1024, help="device chains behind each reference chain")
-    s.add_argument("--precision", default="f32", choices=["f64", "f32", "table", "hybrid"])
+    s.add_argument("--precision", default="auto", choices=["auto", "f64", "f32", "table", "hybrid"],
+                   help="auto: hybrid (exact float64 conditionals from threshold tables) when every sampled variable of the "
+                        "model gets a table, else f32; the Rao-Blackwell estimator implies f32")
     s.add_argument("--device", type=int, default=0)
     s.add_argument("--rao-blackwell", action="store_true",
                    help="marginals accumulate the sampled conditionals instead of counts (f32 / f64; not the reference's estimator)")
@@ -237,9 +239,16 @@ def _agree(dist, device, *flags):
 
 def _sample(args, out, mon, start, dist=None, rank=0, world=1):
     from . import distributed as gbd
-    prec = {"f64": F64, "f32": F32, "table": TABLE, "hybrid": HYBRID}[args.precision]
     out.write("Reading model from %s\n" % args.model)
     mod = core.Model.from_uai(args.model, use_evidence=args.evidence, device=args.device)
+    if args.precision == "auto":
+        # all-table models (binary variables, <= 65536 neighbour configurations) and their single-collapsed variants run
+        # on the resident table kernel under hybrid mode; anything else takes the float32 log-sum-exp kernels
+        order, _ = mod.schedule()
+        all_tables = len(order) > 0 and bool(mod.hybrid_mask()[order].all())
+        args.precision = "hybrid" if all_tables and not args.rao_blackwell else "f32"
+        out.write("Precision: %s\n" % args.precision)
+    prec = {"f64": F64, "f32": F32, "table": TABLE, "hybrid": HYBRID}[args.precision]
     n, cards, fixed = mod.n_vars, mod.cards, mod.fixed
     offs = np.concatenate([[0], np.cumsum(cards)])
     out.write("Model has %d vars and %d functions\n" % (n, mod.n_funcs))

@@ -14,6 +14,17 @@
 #include "host_model.hpp"
 #include "kernels.cuh"
 
+// Build partition (see __graft_entry__.build): the log-sum-exp sweep kernels are ~70 heavy template instantiations, so the
+// library is compiled as three translation units in parallel from this one source — GB_PART 1 = everything but the LSE
+// kernels, 2 = the float32 LSE kernels, 3 = the float64 ones (0 / undefined = all in one unit).  The LSE launches sit
+// behind four plain functions (gbh::lse_*), defined in the unit that instantiates their kernels.
+#ifndef GB_PART
+#define GB_PART 0
+#endif
+#define GB_MAIN (GB_PART == 0 || GB_PART == 1)
+#define GB_LSE_F32 (GB_PART == 0 || GB_PART == 2)
+#define GB_LSE_F64 (GB_PART == 0 || GB_PART == 3)
+
 namespace {
 
 thread_local std::string g_err;
@@ -168,7 +179,7 @@ struct gb_model {
     }
 };
 
-namespace {
+namespace gbh {  // host-side types shared by the translation units
 
 struct Group {
     gb_model* model = nullptr;
@@ -184,7 +195,18 @@ struct Group {
     gb::DevGroup dev{};
 };
 
-}  // namespace
+// Resident-path launch plan: chains per CTA, dynamic shared memory, and whether the log-space tables are
+// staged in shared memory by TMA bulk copies (ts).  ch == 0: the model does not qualify.
+struct ResidentPlan {
+    int ch = 0;
+    size_t smem = 0;
+    bool ts = false;
+    int32_t n_stage = 0;  // table entries staged in shared memory: all of them (ts) or a prefix ending on a factor boundary
+};
+
+}  // namespace gbh
+using gbh::Group;
+using gbh::ResidentPlan;
 
 struct gb_chains {
     int device = 0;
@@ -238,8 +260,17 @@ struct gb_chains {
     const gb::HostModel& base() const { return groups[0].model->h; }
 };
 
+namespace gbh {
+// one colour of one group / n_sweeps sweeps of one group on the resident path, log-sum-exp kernels of one precision
+void lse_colour_f32(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half);
+void lse_colour_f64(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half);
+void lse_resident_f32(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half);
+void lse_resident_f64(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half);
+}  // namespace gbh
+
 namespace {
 
+#if GB_MAIN
 void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_chain, bool owns) {
     if (!model) throw gb::Err("No model supplied");
     if (model->device != c->device) throw gb::Err("model lives on a different device than the chains");
@@ -283,6 +314,8 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     c->skip_uploaded = false;
 }
 
+#endif  // GB_MAIN
+
 template <typename Real, int MAXC, int CW>
 void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half) {
     const int64_t items = (int64_t)n * (g.n_pad / 4);
@@ -296,6 +329,7 @@ void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int
     c->launches++;
 }
 
+#if GB_MAIN
 template <int VB, int NN, bool HIST, int PF>
 void launch_tab_variant(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
     static int resident_dev[kMaxDevices] = {};  // per device: CTAs that fit at once (persistent tile loop)
@@ -338,7 +372,6 @@ void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist
 void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
     const gb::HostModel& h = g.model->h;
     const int n_col = (int)h.colour_off.size() - 1;
-    const int mc = h.max_card;
     for (int col = 0; col < n_col; col++) {
         const int32_t* dv = g.model->d_order + h.colour_off[col];
         const int32_t n = h.colour_off[col + 1] - h.colour_off[col];
@@ -346,19 +379,9 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         if (c->precision == GB_TABLE) {
             launch_tab(c, g, col, n, record, hist_half);
         } else if (c->precision == GB_F32) {
-            if (mc <= 2) launch_colour<float, 2, 4>(c, g, dv, n, record, hist_half);
-            else if (mc <= 4) launch_colour<float, 4, 4>(c, g, dv, n, record, hist_half);
-            else if (mc <= 8) launch_colour<float, 8, 4>(c, g, dv, n, record, hist_half);
-            else if (mc <= 16) launch_colour<float, 16, 4>(c, g, dv, n, record, hist_half);
-            else if (mc <= 32) launch_colour<float, 32, 1>(c, g, dv, n, record, hist_half);
-            else launch_colour<float, 64, 1>(c, g, dv, n, record, hist_half);
+            gbh::lse_colour_f32(c, g, dv, n, record, hist_half);
         } else {
-            if (mc <= 2) launch_colour<double, 2, 4>(c, g, dv, n, record, hist_half);
-            else if (mc <= 4) launch_colour<double, 4, 4>(c, g, dv, n, record, hist_half);
-            else if (mc <= 8) launch_colour<double, 8, 1>(c, g, dv, n, record, hist_half);
-            else if (mc <= 16) launch_colour<double, 16, 1>(c, g, dv, n, record, hist_half);
-            else if (mc <= 32) launch_colour<double, 32, 1>(c, g, dv, n, record, hist_half);
-            else launch_colour<double, 64, 1>(c, g, dv, n, record, hist_half);
+            gbh::lse_colour_f64(c, g, dv, n, record, hist_half);
         }
     }
     g.sweep++;
@@ -367,6 +390,8 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         g.total_samples += (int64_t)h.order.size() * g.n_chains;
     }
 }
+
+#endif  // GB_MAIN
 
 // Shared-memory-resident path for small models: all sweeps of one group in ONE launch.
 template <typename Real, int MAXC, int CW, bool TS, bool RB>
@@ -404,15 +429,6 @@ void launch_resident_ts(gb_chains* c, Group& g, int ch, size_t smem, int32_t his
     else launch_resident_rb<Real, MAXC, CW, TS, false>(c, g, ch, smem, hist_off, n_sweeps, record, n_pre, n_half, n_stage);
 }
 
-// Resident-path launch plan: chains per CTA, dynamic shared memory, and whether the log-space tables are
-// staged in shared memory by TMA bulk copies (ts).  ch == 0: the model does not qualify.
-struct ResidentPlan {
-    int ch = 0;
-    size_t smem = 0;
-    bool ts = false;
-    int32_t n_stage = 0;  // table entries staged in shared memory: all of them (ts) or a prefix ending on a factor boundary
-};
-
 bool tab_resident(const gb_chains* c, const Group& g);
 
 // Where the CTA's per-chain half-window histograms ([2][total_card][ch] u16) go for a launch that records
@@ -437,6 +453,7 @@ bool tab_resident(const gb_chains* c, const Group& g) {
     return c->precision == GB_TABLE || (c->precision == GB_HYBRID && !no_hy && g.model->hybrid_all_tables());
 }
 
+#if GB_MAIN
 ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     static int disabled = -1, no_ts = -1;
     if (disabled < 0) disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
@@ -512,6 +529,8 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     return p;
 }
 
+#endif  // GB_MAIN
+
 template <typename Real, int MAXC, int CW>
 void launch_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
     size_t smem = 0;
@@ -519,6 +538,54 @@ void launch_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sw
     if (p.ts) launch_resident_ts<Real, MAXC, CW, true>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half, p.n_stage);
     else launch_resident_ts<Real, MAXC, CW, false>(c, g, p.ch, smem, hist_off, n_sweeps, record, n_pre, n_half, p.n_stage);
 }
+
+}  // namespace
+
+namespace gbh {
+#if GB_LSE_F32
+void lse_colour_f32(gb_chains* c, Group& g, const int32_t* dv, int32_t n, int record, int hist_half) {
+    const int mc = g.model->h.max_card;
+    if (mc <= 2) launch_colour<float, 2, 4>(c, g, dv, n, record, hist_half);
+    else if (mc <= 4) launch_colour<float, 4, 4>(c, g, dv, n, record, hist_half);
+    else if (mc <= 8) launch_colour<float, 8, 4>(c, g, dv, n, record, hist_half);
+    else if (mc <= 16) launch_colour<float, 16, 4>(c, g, dv, n, record, hist_half);
+    else if (mc <= 32) launch_colour<float, 32, 1>(c, g, dv, n, record, hist_half);
+    else launch_colour<float, 64, 1>(c, g, dv, n, record, hist_half);
+}
+void lse_resident_f32(gb_chains* c, Group& g, const ResidentPlan& plan, int32_t ns, int record, int32_t pre, int32_t n_half) {
+    const int mc = g.model->h.max_card;
+    if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 4) launch_resident<float, 4, 4>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 8) launch_resident<float, 8, 0>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 16) launch_resident<float, 16, 0>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 32) launch_resident<float, 32, 0>(c, g, plan, ns, record, pre, n_half);
+    else launch_resident<float, 64, 0>(c, g, plan, ns, record, pre, n_half);
+}
+#endif
+#if GB_LSE_F64
+void lse_colour_f64(gb_chains* c, Group& g, const int32_t* dv, int32_t n, int record, int hist_half) {
+    const int mc = g.model->h.max_card;
+    if (mc <= 2) launch_colour<double, 2, 4>(c, g, dv, n, record, hist_half);
+    else if (mc <= 4) launch_colour<double, 4, 4>(c, g, dv, n, record, hist_half);
+    else if (mc <= 8) launch_colour<double, 8, 1>(c, g, dv, n, record, hist_half);
+    else if (mc <= 16) launch_colour<double, 16, 1>(c, g, dv, n, record, hist_half);
+    else if (mc <= 32) launch_colour<double, 32, 1>(c, g, dv, n, record, hist_half);
+    else launch_colour<double, 64, 1>(c, g, dv, n, record, hist_half);
+}
+void lse_resident_f64(gb_chains* c, Group& g, const ResidentPlan& plan, int32_t ns, int record, int32_t pre, int32_t n_half) {
+    const int mc = g.model->h.max_card;
+    if (mc <= 2) launch_resident<double, 2, 4>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 4) launch_resident<double, 4, 4>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 8) launch_resident<double, 8, 0>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 16) launch_resident<double, 16, 0>(c, g, plan, ns, record, pre, n_half);
+    else if (mc <= 32) launch_resident<double, 32, 0>(c, g, plan, ns, record, pre, n_half);
+    else launch_resident<double, 64, 0>(c, g, plan, ns, record, pre, n_half);
+}
+#endif
+}  // namespace gbh
+
+#if GB_MAIN
+namespace {
 
 void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t n_sweeps, int record, int32_t n_pre, int32_t n_half) {
     const gb::HostModel& h = g.model->h;
@@ -549,7 +616,6 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
     const ResidentPlan plan = resident_plan(c, g);
     const gb::HostModel& h = g.model->h;
     if (plan.ch) {
-        const int mc = h.max_card;
         // One launch runs at most kMaxSweepsPerLaunch sweeps: the CTA's shared-memory counters are 32-bit
         // (sweeps x chains per CTA must stay below 2^31) and a single kernel should not run for minutes.
         // A later launch continues the window schedule: its n_pre is shifted (it may go negative).
@@ -561,19 +627,9 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
             if (tab_resident(c, g)) {
                 launch_tab_resident(c, g, plan, ns, record, pre, n_half);
             } else if (c->precision == GB_F32) {
-                if (mc <= 2) launch_resident<float, 2, 4>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 4) launch_resident<float, 4, 4>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 8) launch_resident<float, 8, 0>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 16) launch_resident<float, 16, 0>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 32) launch_resident<float, 32, 0>(c, g, plan, ns, record, pre, n_half);
-                else launch_resident<float, 64, 0>(c, g, plan, ns, record, pre, n_half);
+                gbh::lse_resident_f32(c, g, plan, ns, record, pre, n_half);
             } else {
-                if (mc <= 2) launch_resident<double, 2, 4>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 4) launch_resident<double, 4, 4>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 8) launch_resident<double, 8, 0>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 16) launch_resident<double, 16, 0>(c, g, plan, ns, record, pre, n_half);
-                else if (mc <= 32) launch_resident<double, 32, 0>(c, g, plan, ns, record, pre, n_half);
-                else launch_resident<double, 64, 0>(c, g, plan, ns, record, pre, n_half);
+                gbh::lse_resident_f64(c, g, plan, ns, record, pre, n_half);
             }
             g.sweep += (uint32_t)ns;
         }
@@ -1391,3 +1447,4 @@ int gb_mar_load(const char* path, int32_t* n_vars_out, int32_t* total_card_out, 
 }
 
 }  // extern "C"
+#endif  // GB_MAIN

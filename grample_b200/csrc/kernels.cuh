@@ -829,7 +829,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
 // by k_build_thresholds and stored as the largest 32-bit draw that still selects value 0 under
 // the reference's inverse-CDF rule (sampler.go:115-123: r = U*tot, r <= e0).  The sweep itself is
 // integer work: gather neighbour bytes -> configuration index -> threshold -> compare.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__ order, const int32_t n_order) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_order; j += gridDim.x * blockDim.x) {
         const int v = order[j];
@@ -1272,7 +1272,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
 }
 
 // ------------------------------------------------------------------ K6
-__global__ void __launch_bounds__(256) k_init_state(const DevModel m, const DevGroup g) {
+static __global__ void __launch_bounds__(256) k_init_state(const DevModel m, const DevGroup g) {
     const int32_t n_quads = g.n_pad >> 2;
     const int64_t total = (int64_t)m.n_vars * n_quads;
     for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
@@ -1375,7 +1375,7 @@ struct CollapsePlan {
     const int32_t* f_stride_b;  // [n_f][n_b] stride of blanket position b in factor f (0 if absent)
 };
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_collapse(const CollapsePlan pl, const double* __restrict__ tab, double* __restrict__ new_tab,
            double* __restrict__ marg /*[card_v], pre-set to 1e-12*/) {
     __shared__ double s_marg[kMaxCardDev];
@@ -1451,7 +1451,7 @@ __device__ __forceinline__ double measure_dev(int which, int card, FA A, FB B) {
 
 // item = (variable, chain): within = d(hist1, hist2), between = d(merged, hist1 + hist2), every
 // histogram bin seeded with 1e-8 (chain.go:264-287); sums over chains into wb[v], wb[n_vars+v].
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_chain_dist(const DevModel m, const DevGroup g, const double* __restrict__ merged,
              const uint8_t* __restrict__ skip, const int which, double* __restrict__ wb) {
     const int64_t total = (int64_t)m.n_vars * g.n_chains;
@@ -1477,7 +1477,7 @@ k_chain_dist(const DevModel m, const DevGroup g, const double* __restrict__ merg
 
 // this device's contribution to MergeChains (chain.go:131-144): every chain starts at the
 // uniform marginal 1/card (model/variable.go:45) and adds its counts
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_merge_partial(const DevModel m, const unsigned long long* __restrict__ counts, const double n_chains,
                 const uint8_t* __restrict__ skip, double* __restrict__ out, const double count_unit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
