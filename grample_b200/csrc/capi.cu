@@ -477,6 +477,12 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     }
     const size_t real_bytes = c->precision == GB_F32 ? 4 : 8;
     const size_t tab_bytes = 16 + (((size_t)h.log_tab.size() + 3) & ~(size_t)3) * real_bytes;
+    // the groups of a handle run concurrently (side streams), so co-residency is judged on the CTAs of ALL of them
+    auto ctas = [&](int ch) {
+        int64_t n = 0;
+        for (const auto& gg : c->groups) n += (gg.n_pad + ch - 1) / ch;
+        return std::max<int64_t>(n, g.n_pad / ch);
+    };
     constexpr size_t kSmemPerSm = 220 * 1024, kSmemPerCta = 200 * 1024;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -488,7 +494,7 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
             const size_t smem = base(ch) + tab_bytes;
             if (smem > kSmemPerCta) break;
             const int64_t per_sm = std::min<int64_t>(8, (int64_t)(kSmemPerSm / (smem + 1024)));
-            if (ch < 64 && (int64_t)(g.n_pad / ch) > per_sm * sms) continue;
+            if (ch < 64 && ctas(ch) > per_sm * sms) continue;
             if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
             p.ch = ch; p.smem = smem; p.ts = true;
             p.n_stage = (int32_t)(((size_t)h.log_tab.size() + 3) & ~(size_t)3);
@@ -511,7 +517,7 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
             if (n == 0) break;
             const size_t smem = base(ch) + 16 + (size_t)((n + 3) & ~(int64_t)3) * real_bytes;
             const int64_t per_sm = std::min<int64_t>(8, (int64_t)(kSmemPerSm / (smem + 1024)));
-            if (ch < 64 && (int64_t)(g.n_pad / ch) > per_sm * sms) continue;
+            if (ch < 64 && ctas(ch) > per_sm * sms) continue;
             if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
             p.ch = ch; p.smem = smem; p.n_stage = (int32_t)n;
             return p;

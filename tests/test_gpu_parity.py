@@ -862,6 +862,21 @@ def test_cli_sample_adaptive(res, tmp_path):
     assert mon["Total-Samples"] > 0 and 0 < mon["Last-Mean-Hellinger"] < 1
 
 
+def test_cli_precision_auto(res):
+    """--precision auto: hybrid (exact float64 conditionals from threshold tables) when every sampled variable gets a
+    table, float32 log-sum-exp otherwise and with the Rao-Blackwell estimator"""
+    import io
+
+    from grample_b200 import cli
+    for argv, want in ((["-m", res("Grids_11.uai")], "hybrid"), (["-m", res("ObjectDetection_11.uai")], "f32"),
+                       (["-m", res("Grids_11.uai"), "--rao-blackwell"], "f32")):
+        args = cli.build_parser().parse_args(["sample"] + argv + ["-o", "-b", "200", "-w", "10", "-i", "20000", "--replicas", "8"])
+        out = io.StringIO()
+        final, _ = cli.sample(args, out)
+        assert "Precision: %s" % want in out.getvalue()
+        assert np.isfinite(final).all()
+
+
 def test_cli_errors(res):
     from grample_b200 import cli
     args = cli.build_parser().parse_args(["sample", "-m", res("one.uai"), "-s", "simple", "-a", "3"])
