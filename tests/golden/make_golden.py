@@ -6,7 +6,7 @@ not pin (SampleVar numerics, the sweep schedule, collapse, converg
                                    (gibbs-simple.go:171-258), float64, exact round trip through repr
   tests/golden/trajectories.json   (model, colour schedule, seed, initial states) -> states and marginal
                                    counts after n sweeps of the device schedule, for 53-bit (f64 kernels)
-                                   and 32-bit (table kernels) draws
+                                   and 32-bit (table kernels) draws, plus the Rao-Blackwell bins of the 53-bit run
 
 Source of truth: the CPU oracle (oracle/, pinned by the reference's known-answer tests).  Run from the
 repo root:  python tests/golden/make_golden.py      (no GPU needed; deterministic)
@@ -82,6 +82,10 @@ def main():
                 s = oracle.Sampler(oracle.Generator(1), oracle.Model.load(os.path.join(res, name), use_evidence=evid))
                 st, counts = s.sweep_run(order, seed, first, st0, 0, n_sweeps, bits=bits, record=True)
                 entry["bits%d" % bits] = {"final": st.tolist(), "counts": [int(c) for c in counts]}
+                if bits == 53:  # the Rao-Blackwell bins of the same trajectory (GB_CHAINS_RAO_BLACKWELL, units of 2^-24)
+                    s = oracle.Sampler(oracle.Generator(1), oracle.Model.load(os.path.join(res, name), use_evidence=evid))
+                    _, bins = s.sweep_run(order, seed, first, st0, 0, n_sweeps, bits=53, record=2)
+                    entry["bits53"]["rb_bins"] = [int(b) for b in bins]
             traj.append(entry)
     with open(os.path.join(HERE, "conditionals.json"), "w") as f:
         json.dump(cond, f, separators=(",", ":"))

@@ -135,6 +135,14 @@ def test_trajectories_match_golden_fixture(res, per_colour):
             ch.sweep(t["n_sweeps"], record=True)
             assert ch.get_state(0, st0.shape[0]).tolist() == g["final"], (t["model"], bits)
             assert ch.group_counts(0).tolist() == g["counts"], (t["model"], bits)
+            if "rb_bins" in g:  # Rao-Blackwell bins of the same trajectory (device exp vs libm exp: a few units of 2^-24)
+                rb = gb.Chains(dm, st0.shape[0], seed=t["seed"], first_chain_id=t["first_chain"], precision=prec, device=0,
+                               per_colour=per_colour, rao_blackwell=True)
+                rb.set_state(0, st0)
+                rb.sweep(t["n_sweeps"], record=True)
+                assert rb.get_state(0, st0.shape[0]).tolist() == g["final"], t["model"]
+                diff = np.abs(rb.group_counts(0).astype(np.int64) - np.asarray(g["rb_bins"], dtype=np.int64))
+                assert diff.max() <= 4, (t["model"], int(diff.max()))
 
 
 # ------------------------------------------------------------------ sweeps (K1): bit-exact trajectories

@@ -75,6 +75,10 @@ def test_oracle_trajectories_match_golden(res):
                                      t["n_sweeps"], bits=bits, record=True)
             assert st.tolist() == g["final"], (t["model"], bits)
             assert [int(c) for c in counts] == g["counts"], (t["model"], bits)
+            if "rb_bins" in g:
+                _, bins = s.sweep_run(order, t["seed"], t["first_chain"], np.asarray(t["initial"], dtype=np.int32), 0,
+                                      t["n_sweeps"], bits=bits, record=2)
+                assert [int(b) for b in bins] == g["rb_bins"], t["model"]
 
 
 def test_host_schedule_matches_golden_colouring(res):
