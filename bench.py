@@ -135,6 +135,33 @@ def small_model_rates(gb, dev, sweeps=500):
     return out
 
 
+def samples_to_hellinger(gb, dev, threshold=0.01):
+    """The second half of BASELINE.json's metric on the one bundled problem where it is finite:
+    recorded updates until the mean Hellinger distance of the merged marginals to ObjectDetection_11.uai.MAR first drops
+    below 0.01, checked every 38400 updates; 16 chains, float32, the reference's merge rule (per-chain uniform
+    pseudo-count included).  Counting estimator (the reference's) and the Rao-Blackwell estimator, same trajectory."""
+    res = os.path.join(ROOT, "tests", "golden", "res")
+    out = {"problem": "ObjectDetection_11", "chains": 16, "precision": "f32", "threshold": threshold, "check_every_updates": 16 * 40 * 60,
+           "reference_algorithm_cpu": {"value": 1017360, "source": "profiles/r01_accuracy_objectdetection_rao_blackwell.json (oracle, 4 chains, random scan)"}}
+    try:
+        m = gb.Model.from_uai(os.path.join(res, "ObjectDetection_11.uai"), device=dev)
+        cards, mar = gb.mar_load(os.path.join(res, "ObjectDetection_11.uai.MAR"))
+        for label, rb in (("counts", False), ("rao_blackwell", True)):
+            ch = gb.Chains(m, 16, seed=2024, precision=gb.F32, device=dev, rao_blackwell=rb)
+            ch.burnin(2000)
+            reached = None
+            for _ in range(80):
+                ch.sweep(40)
+                h = gb.error_suite(cards, mar, ch.merged_marginals()[0])["MeanHellinger"]
+                if h < threshold:
+                    reached = int(ch.total_samples)
+                    break
+            out[label] = {"samples": reached, "mean_hellinger_at_stop": h}
+    except Exception as e:  # never lose the headline line over a secondary number
+        out["error"] = str(e)[:200]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -279,6 +306,7 @@ def run_native(args):
     if world == 1 and not args.no_secondary:
         del chains
         secondary = small_model_rates(gb, dev)
+        secondary["samples_to_mean_hellinger_below_0.01"] = samples_to_hellinger(gb, dev)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
