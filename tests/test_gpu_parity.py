@@ -373,6 +373,95 @@ def test_hybrid_all_table_variants_run_on_the_table_kernel(res, monkeypatch):
     assert np.array_equal(ocounts, out[0][2].astype(np.float64))
 
 
+# ------------------------------------------------------------------ synthetic models: every cardinality bucket of the LSE kernels
+def synthetic_model(rng, cards, n_pair, n_triple, zero_frac=0.15, evidence=()):
+    """random UAI-style model: one unary factor per variable, random pairwise and ternary factors (mixed cardinalities,
+    the updated variable in every scope position), positive tables with a share of exact zeros (the 1e-6 eps rule and
+    the floor both fire)"""
+    n = len(cards)
+    scopes = [[v] for v in range(n)]
+    for k, cnt in ((2, n_pair), (3, n_triple)):
+        for _ in range(cnt):
+            scopes.append([int(v) for v in rng.choice(n, size=k, replace=False)])
+    scope_off, scope_vars, tab_off, tables = [0], [], [0], []
+    for sc in scopes:
+        size = int(np.prod([cards[v] for v in sc]))
+        t = rng.uniform(0.05, 3.0, size=size) * np.exp(rng.normal(0.0, 2.0, size=size))
+        t[rng.random(size) < zero_frac] = 0.0
+        if not t.any():
+            t[0] = 1.0
+        scope_vars += sc
+        scope_off.append(len(scope_vars))
+        tables.append(t)
+        tab_off.append(tab_off[-1] + size)
+    fixed = np.full(n, -1, dtype=np.int32)
+    for v, x in evidence:
+        fixed[v] = x
+    return (np.asarray(cards, dtype=np.int32), fixed, np.asarray(scope_off, dtype=np.int32), np.asarray(scope_vars, dtype=np.int32),
+            np.asarray(tab_off, dtype=np.int64), np.concatenate(tables))
+
+
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+@pytest.mark.parametrize("label,cards,n_pair,n_triple,evidence", [
+    ("card<=4", [2, 3, 4, 2, 3, 4, 4, 2, 3, 3, 4, 2], 14, 5, ((3, 1),)),
+    ("card<=8", [5, 8, 2, 7, 8, 3, 6, 8, 5, 2], 12, 3, ((0, 4),)),
+    ("card<=16", [16, 11, 9, 2, 16, 13, 3, 10, 16], 10, 2, ()),
+    ("pairwise-11", [11] * 10, 18, 0, ((2, 7),)),
+    ("card<=32", [32, 17, 2, 25, 32, 5], 6, 1, ()),
+    ("card<=64", [64, 40, 3, 64, 33], 5, 0, ((2, 2),)),
+])
+def test_synthetic_mixed_cardinalities_bitexact(label, cards, n_pair, n_triple, evidence, per_colour):
+    """float64 sweeps, conditional probe and Rao-Blackwell bins against the oracle on random models that exercise every
+    cardinality bucket of the log-sum-exp kernels (2, 4, 8, 16, 32, 64; exact-cardinality and predicated bodies), ternary
+    factors with the updated variable in every scope position, the pairwise fast path, zeros and evidence"""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(label.encode()))
+    arrays = synthetic_model(rng, cards, n_pair, n_triple, evidence=evidence)
+    dm = gb.Model.from_arrays(*arrays, device=0)
+    om = oracle.Model.create(*arrays)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    order, _ = dm.schedule()
+    cards_a, fixed = dm.cards, dm.fixed
+    # conditionals (K5)
+    states = random_states(rng, cards_a, fixed, 24)
+    vs = rng.choice(order, size=24)
+    got = dm.conditional(states, vs, precision=gb.F64)
+    for st, v, e in zip(states, vs, got):
+        ref = np.asarray(samp.conditional(int(v), st))
+        np.testing.assert_allclose(e / e.sum(), ref / ref.sum(), rtol=1e-9, atol=0)
+    # sweeps
+    seed, first, n_chains, n_sweeps = 77, 8, 37, 6
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0, per_colour=per_colour)
+    st0 = ch.get_state(0, n_chains)
+    ch.sweep(n_sweeps, record=True)
+    ost, ocounts = samp.sweep_run(order, seed, first, st0, 0, n_sweeps, bits=53, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains)), label
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64)), label
+    # Rao-Blackwell bins of the same trajectory
+    rb = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0, per_colour=per_colour,
+                   rao_blackwell=True)
+    rb.set_state(0, st0)
+    rb.sweep(n_sweeps, record=True)
+    _, obins = samp.sweep_run(order, seed, first, st0, 0, n_sweeps, bits=53, record=2)
+    assert np.array_equal(ost, rb.get_state(0, n_chains)), label
+    assert np.abs(rb.group_counts(0).astype(np.float64) - obins).max() <= 8.0, label
+    # float32 arithmetic on the same states: conditionals within 1e-4 relative of the float64 oracle (north_star's bound),
+    # and a float32 run keeps finite, normalisable marginals
+    got32 = dm.conditional(states, vs, precision=gb.F32)
+    for st, v, e in zip(states, vs, got32):
+        ref = np.asarray(samp.conditional(int(v), st))
+        p, q = e / e.sum(), ref / ref.sum()
+        near_floor = np.abs(q * (1 + 1e-6 * len(q)) / 1e-6 - 1.0) < 1e-2  # the floor is a discontinuity at e/tot = 1e-6
+        assert np.allclose(p[~near_floor], q[~near_floor], rtol=1e-4, atol=0), (label, int(v))
+    c32 = gb.Chains(dm, 64, seed=5, precision=gb.F32, device=0, per_colour=per_colour)
+    c32.burnin(5)
+    c32.sweep(20)
+    m32 = c32.merged_marginals()[0]
+    off = np.concatenate([[0], np.cumsum(cards_a)])
+    for v in order:
+        assert abs(m32[off[v]:off[v + 1]].sum() - (64 + 64 * 20)) < 1e-6, (label, int(v))
+
+
 # ------------------------------------------------------------------ Rao-Blackwell estimator (flag, SURVEY 8f)
 @pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
 @pytest.mark.parametrize("name,evid,n_chains", [("ObjectDetection_11.uai", False, 37), ("Pedigree_11.uai", True, 21),
