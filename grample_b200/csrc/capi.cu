@@ -771,10 +771,20 @@ void merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const gb::HostModel& h = c->base();
     const size_t bytes = (size_t)h.total_card * sizeof(double);
-    if (!c->h_merge) CUDA_CHECK(cudaMallocHost(&c->h_merge, bytes));
-    CUDA_CHECK(cudaMemcpyAsync(c->h_merge, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    std::memcpy(out, c->h_merge, bytes);
+    // a caller buffer that is page-locked (cudaHostAlloc / cudaHostRegister / a pinned torch tensor) receives the DMA
+    // directly; a pageable one goes through the handle's pinned staging buffer
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();  // (older drivers report an unregistered host pointer as an error)
+    if (pinned) {
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+        if (!c->h_merge) CUDA_CHECK(cudaMallocHost(&c->h_merge, bytes));
+        CUDA_CHECK(cudaMemcpyAsync(c->h_merge, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        std::memcpy(out, c->h_merge, bytes);
+    }
     refresh_collapsed_cache(c);
     if (collapsed_out) {
         upload_skip(c);

@@ -180,7 +180,9 @@ int gb_chains_synchronize(gb_chains* c);
 /* sampler.MergeChains (sampler/chain.go:96-148) over this device's chains: for every variable
  * the sum over chains of Marginal (each chain starts at uniform 1/card, model/variable.go:45,
  * plus its counts); a variable collapsed in ANY group is reported with that group's local
- * marginal and collapsed_out[v] = 1.  out[sum(card)], collapsed_out[n_vars] (may be NULL). */
+ * marginal and collapsed_out[v] = 1.  out[sum(card)], collapsed_out[n_vars] (may be NULL).
+ * `out` is host memory; when it is page-locked (cudaHostAlloc / cudaHostRegister) the device-to-host copy lands in it
+ * directly, otherwise it is staged through a pinned buffer of the handle. */
 int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out);
 /* Multi-device form: this device's un-merged contribution is written to a DEVICE buffer of
  * sum(card) doubles (collapsed variables zero) so the host plumbing can all-reduce it in
