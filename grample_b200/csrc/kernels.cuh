@@ -1199,17 +1199,21 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                 const uint32_t chain_blk = (uint32_t)((g.first_chain + (uint64_t)lchain) >> 3);
                 const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
-                uint32_t T[8], xbits = 0;
-                bool tie = false;
+                // same compare as k_sweep_tab: d = threshold high half - draw high half (both < 2^16), sign bit set <=> the
+                // draw is above the threshold; a zero d is a tie, found with 3-input unsigned minima
+                uint32_t T[8], dd[8], xbits = 0;
+                const uint32_t* __restrict__ thr_v = t.thr + hd.y;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+                for (int i = 7; i >= 0; i--) {
+                    uint32_t idx = __byte_perm(i < 4 ? cfg_lo : cfg_hi, 0, 0x4440 + (i & 3));
                     if constexpr (WIDE) idx = wide ? idxw[i] : idx;
-                    T[i] = __ldg(t.thr + hd.y + idx);
-                    const uint32_t hi = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-                    xbits |= (hi > (T[i] >> 16) ? 1u : 0u) << i;
-                    tie |= hi == (T[i] >> 16);
+                    T[i] = __ldg(thr_v + idx);
+                    const uint32_t hi = (i & 1) ? (wa[i >> 1] >> 16) : __byte_perm(wa[i >> 1], 0, 0x4410);
+                    const uint32_t d = (T[i] >> 16) - hi;
+                    xbits = __funnelshift_l(d, xbits, 1);  // xbits = (xbits << 1) | (hi > threshold)
+                    dd[i] = d;
                 }
+                const bool tie = __vimin3_u32(__vimin3_u32(dd[0], dd[1], dd[2]), __vimin3_u32(dd[3], dd[4], dd[5]), min(dd[6], dd[7])) == 0;
                 if (tie) {  // draw > threshold <=> high halves equal and lo16 > (T & 0xffff)
                     const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
                     const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
