@@ -439,8 +439,9 @@ int32_t place_histograms(const gb_chains* c, const Group& g, const ResidentPlan&
     if (!(c->flags & GB_CHAINS_HISTORY) || n_half < 0 || !g.d_hist) return -1;
     if (std::getenv("GB_HIST_GLOBAL")) return -1;  // A/B knob: histograms updated in global memory
     const size_t off = (p.smem + 15) & ~(size_t)15;
-    // the resident table kernel keeps only the ones of its (binary) variables: [2][n_vars][ch]; the others [2][total_card][ch]
-    const size_t rows = tab_resident(c, g) ? (size_t)g.model->h.n_vars : (size_t)g.model->h.total_card;
+    // the resident table kernel keeps only the ones of its (binary) variables, by sweep position: [2][n_order][ch];
+    // the others [2][total_card][ch]
+    const size_t rows = tab_resident(c, g) ? g.model->h.order.size() : (size_t)g.model->h.total_card;
     const size_t bytes = (size_t)2 * rows * p.ch * sizeof(uint16_t);
     if (off + bytes > (p.ts ? 160 : 100) * 1024) return -1;
     *smem = off + bytes;

@@ -1138,12 +1138,13 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
             *reinterpret_cast<const uint2*>(g.state + (size_t)v * g.n_pad + cta_chain + 8 * q);
     }
     for (int i = threadIdx.x; i < m.total_card; i += blockDim.x) s_counts[i] = 0;
-    // Shared-memory histograms of this kernel hold only the ONES of every (binary) variable, [2][n_vars][CH] u16 — half the
-    // footprint, so twice the CTAs stay co-resident; the zeros are (recorded sweeps of the half) - ones, added at the flush.
+    // Shared-memory histograms of this kernel hold only the ONES of every (binary) sampled variable, indexed by sweep
+    // position: [2][n_order][CH] u16 — half the footprint of both rows, and a warp's consecutive positions touch
+    // consecutive 16-byte rows.  The zeros are (recorded sweeps of the half) - ones, added at the flush.
     uint16_t* s_hist = nullptr;
     if (n_half >= 0 && hist_off >= 0 && g.hist) {
         s_hist = reinterpret_cast<uint16_t*>(smem + hist_off);
-        for (int i = threadIdx.x; i < 2 * m.n_vars * (ch_per_cta >> 3); i += blockDim.x)
+        for (int i = threadIdx.x; i < 2 * t.n_order * (ch_per_cta >> 3); i += blockDim.x)
             reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -1236,7 +1237,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                     if (nvalid - ones) atomicAdd(&s_counts[hd.w], (unsigned)(nvalid - ones));
                     if (hist_half >= 0 && g.hist) {
                         if (s_hist)
-                            add_row16(reinterpret_cast<uint4*>(s_hist + ((size_t)hist_half * m.n_vars + hd.x) * CH + 8 * q),
+                            add_row16(reinterpret_cast<uint4*>(s_hist + ((size_t)hist_half * t.n_order + c0 + j) * CH + 8 * q),
                                       spread_bits16(xbits & vmask));
                         else
                             hist_add8_binary(nullptr, g, m.total_card, hist_half, hd.w, CH, 8 * q, lchain, xbits & vmask, ~xbits & vmask);
@@ -1258,17 +1259,17 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
         // recorded sweeps of this launch that fell into each half window (the schedule of the sweep loop above)
         const int b0 = max(0, n_pre), e0 = min(n_sweeps, n_pre + n_half);
         const int n_rec[2] = {max(0, e0 - b0), max(0, n_sweeps - max(0, n_pre + n_half))};
-        for (int i = threadIdx.x; i < 2 * m.n_vars * units; i += blockDim.x) {  // (half, variable, unit of 8 chains): 16-byte rows
+        for (int i = threadIdx.x; i < 2 * t.n_order * units; i += blockDim.x) {  // (half, position, unit of 8 chains): 16-byte rows
             const int e = i >> unit_shift, u = i & (units - 1);
-            const int half = e >= m.n_vars ? 1 : 0, v = e - half * m.n_vars;
+            const int half = e >= t.n_order ? 1 : 0, pos = e - half * t.n_order;
             const int nvalid = min(8, g.n_chains - (cta_chain + 8 * u));
-            if (n_rec[half] == 0 || nvalid <= 0 || __ldg(t.tp_off + v) < 0) continue;  // nothing recorded / padding / not sampled
+            if (n_rec[half] == 0 || nvalid <= 0) continue;  // nothing recorded / padding
             const uint4 ones = *reinterpret_cast<const uint4*>(s_hist + (size_t)e * CH + 8 * u);
             const uint4 lanes = spread_bits16(nvalid >= 8 ? 0xffu : ((1u << nvalid) - 1u));  // 1 in the lanes of existing chains
             const uint32_t nr = (uint32_t)n_rec[half];
             uint4 zeros;  // per 16-bit lane: recorded sweeps - ones (no borrow: ones <= recorded sweeps)
             zeros.x = lanes.x * nr - ones.x; zeros.y = lanes.y * nr - ones.y; zeros.z = lanes.z * nr - ones.z; zeros.w = lanes.w * nr - ones.w;
-            uint16_t* h = g.hist + ((size_t)half * m.total_card + __ldg(m.card_off + v)) * g.n_pad + cta_chain + 8 * u;
+            uint16_t* h = g.hist + ((size_t)half * m.total_card + __ldg(t.trec + (size_t)pos * kTabRec + 3)) * g.n_pad + cta_chain + 8 * u;
             add_row16(reinterpret_cast<uint4*>(h), zeros);
             add_row16(reinterpret_cast<uint4*>(h + g.n_pad), ones);
         }
