@@ -260,6 +260,23 @@ struct gb_chains {
     const gb::HostModel& base() const { return groups[0].model->h; }
 };
 
+// The L1 / shared-memory split of a launch is the driver's choice; left alone it sizes the carve-out for the MOST CTAs that
+// could fit by shared memory (233 KB for a resident table kernel with histograms) even when two CTAs per SM exist, and the
+// records and thresholds then miss in what is left of L1 (ncu: L1 hit rate 99 % -> 69 %, long-scoreboard stall 0.6 -> 3.1
+// per issue).  Ask for the carve-out that holds the CTAs each SM really hosts — counted over all groups of the handle,
+// whose kernels run concurrently — and leave the rest to L1.  Table kernel only: the log-sum-exp resident kernels keep their
+// tables in shared memory and measured slower with the hint (ObjectDetection_11 f64 33.8 -> 39.5 us/sweep).
+template <typename K>
+void prefer_carveout(K kernel, const gb_chains* c, int ch, size_t smem_per_cta) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    int64_t ctas = 0;
+    for (const auto& gg : c->groups) ctas += (gg.n_pad + ch - 1) / ch;
+    const int64_t per_sm = (ctas + sms - 1) / sms + 1;  // one spare: block scheduling is not perfectly even
+    const int64_t pct = std::min<int64_t>(100, (100 * per_sm * (int64_t)(smem_per_cta + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::max<int64_t>(pct, 8));
+}
+
 namespace gbh {
 // one colour of one group / n_sweeps sweeps of one group on the resident path, log-sum-exp kernels of one precision
 void lse_colour_f32(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int record, int hist_half);
@@ -610,6 +627,7 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
         CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    prefer_carveout(kernel, c, p.ch, smem);
     kernel<<<g.n_pad / p.ch, threads, smem, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.model->d_colour_off,
                                                          (int32_t)h.colour_off.size() - 1, p.ch, g.sweep, n_sweeps, record, n_pre, n_half,
                                                          hist_off);
