@@ -2,12 +2,18 @@
 """bench.py — variable-updates/sec of the Gibbs sweep hot path (BASELINE.json metric).
 
 Workload (config.workload): BASELINE.json configs[4] — synthetic 1024x1024 binary Ising torus
-(1 M variables, 3 M factors), 2-colour sweep, float32 arithmetic, 65536 chains per GPU
-(64 GiB of uint8 state per GPU, so inputs are far larger than the 126 MB L2 and no flush is
-needed between timed steps).  One "step" = one systematic sweep of every chain
-(n_vars x chains recorded single-variable updates).  Chains shard across GPUs with no
-data-path collective (weak scaling: fixed chains per GPU); the only exchange is the all-reduce
-of the marginal counts at the monitor interval, which is part of the e2e figure.
+(1 M variables, 3 M factors), 2-colour sweep, 65536 chains per GPU (64 GiB of uint8 state per
+GPU, so inputs are far larger than the 126 MB L2 and no flush is needed between timed steps).
+Default arithmetic (`--precision table`, dtype "u32"): the reference's float64 conditional is
+evaluated once per (variable, neighbour configuration) and stored as a 32-bit inverse-CDF
+threshold; the sweep itself is integer work with 32-bit Philox draws.  `--precision f32|f64`
+run the per-update log-sum-exp kernels instead (also reported under `secondary.lse` at N = 1).
+One "step" = one systematic sweep of every chain (n_vars x chains recorded single-variable
+updates).  Chains shard across GPUs with no data-path collective.  `value` is the weak-scaling
+figure (fixed 65536 chains per GPU); at N > 1 the `strong` block adds SURVEY 8d's split of the
+same 65536 chains over the N GPUs.  The only exchange is the NCCL sum of the marginal counts at
+the monitor interval — inside the library (gb_comm_*), overlapped with the next sweep, and part
+of the e2e figure.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--chains C] [--side S]
 
@@ -33,6 +39,7 @@ import numpy as np
 METRIC = "variable_updates_per_sec"
 UNIT = "updates/s"
 GATHER_BYTES_PER_UPDATE = 5.0  # 4 distinct neighbours read + 1 state byte written (uint8 state)
+COMPULSORY_BYTES_PER_UPDATE = 2.0  # each state byte read once and written once per sweep (perfect neighbour reuse)
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -191,47 +198,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_native(args):
-    import torch
-    import grample_b200 as gb
-    from grample_b200 import distributed as gbd
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = local_rank
-    torch.cuda.set_device(dev)
-
+def measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, dev):
+    """(device ms of K sweeps, launches, clocks, e2e wall ms of K intervals, last merged marginals)"""
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    prec = {"table": gb.TABLE, "f32": gb.F32, "f64": gb.F64}[args.precision]
-    kernel = {"table": "k_sweep_tab<64,4,false,3>", "f32": "k_sweep_colour<float,2,4>", "f64": "k_sweep_colour<double,2,4>"}[args.precision]
-    dtype = {"table": "u32", "f32": "f32", "f64": "f64"}[args.precision]
-    t_setup = time.time()
-    arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)
-    model = gb.Model.from_arrays(*arrays, device=dev)
-    n_vars = model.n_vars
-    order, coff = model.schedule()
-    n_colours = len(coff) - 1
-    chains = gb.Chains(model, args.chains, seed=20260101, first_chain_id=rank * args.chains, precision=prec, device=dev)
-    chains.synchronize()
-    setup_s = time.time() - t_setup
-    updates_per_step = n_vars * args.chains  # per GPU
-    model_bytes = int(sum(a.nbytes for a in arrays))
-
     for _ in range(args.warmup):
         chains.sweep(1, record=True)
     chains.synchronize()
-
     # ---------------- timed region: exactly K steps, device time, max over ranks
     sampler = ClockSampler(dev)
     sampler.start()
@@ -248,67 +225,152 @@ def run_native(args):
         t = torch.tensor([ms], device=f"cuda:{dev}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * updates_per_step * args.steps / (ms * 1e-3)
 
-    # ---------------- e2e: the call a user makes each monitor interval (cmd/root.go:475-539):
-    # advance -> MergeChains read back to the host -> score.  D2H inside: the merged marginals
-    # (sum(card) float64) + the sample count; there is no per-interval host input (see e2e.note).
-    total_card = model.total_card
-    mar = np.full(total_card, 0.5)
-    cards = model.cards
-    # the caller's result buffers, reused per interval: page-locked host memory, so the library's device-to-host copy
-    # lands in them directly (a pageable buffer would be staged through the handle's own pinned buffer)
-    pinned_merge = torch.empty(total_card, dtype=torch.float64).pin_memory()
-    host_out = (pinned_merge.numpy(), np.empty(n_vars, dtype=np.int32))
-    for _ in range(args.warmup):  # warm the interval path too (first call allocates the pinned staging buffer)
+    # ---------------- e2e: the call sequence a user makes each monitor interval (cmd/root.go:475-539): advance ->
+    # MergeChains read back to the host -> score.  The merge of interval i (count sums, NCCL all-reduce over the ranks
+    # inside the library, float64 marginals, D2H into the caller's pinned buffer) runs on the handle's side stream
+    # while the sweep of interval i + 1 runs: gb_chains_merge_begin / gb_chains_merge_end.  Every interval's result is
+    # delivered inside the timed region (the last one after the last sweep).
+    total_card, n_vars = model.total_card, model.n_vars
+    bufs = [(torch.empty(total_card, dtype=torch.float64).pin_memory().numpy(), np.empty(n_vars, dtype=np.int32)) for _ in range(2)]
+    for i in range(args.warmup):  # warm the interval path too (first call creates the side stream and scratch)
         chains.sweep(1, record=True)
-        gbd.merged_marginals(chains, dist, out=host_out)
+        chains.merge_begin(bufs[i % 2])
+        chains.merge_end()
     barrier()
     e0 = time.time()
-    for _ in range(args.steps):
-        chains.sweep(1, record=True)
-        merged, _ = gbd.merged_marginals(chains, dist, out=host_out)  # all-reduce over NVLink when world > 1
-        _ = chains.total_samples
+    chains.sweep(1, record=True)
+    chains.merge_begin(bufs[0])
+    for i in range(1, args.steps):
+        chains.sweep(1, record=True)             # interval i is enqueued ...
+        merged, _, n_all, samples_all = chains.merge_end()   # ... while interval i - 1's merged marginals arrive
+        chains.merge_begin(bufs[i % 2])
+    merged, _, n_all, samples_all = chains.merge_end()
     barrier()
     e_ms = (time.time() - e0) * 1e3
     if dist is not None:
         t = torch.tensor([e_ms], device=f"cuda:{dev}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t.item())
+    assert n_all == world * chains.n_chains, (n_all, world, chains.n_chains)
+    return ms, launches, clocks, e_ms, merged
+
+
+def lse_rates(gb, model, args, dev, n_vars, peak):
+    """The general per-update log-sum-exp path (`k_sweep_colour<Real,2,4>`) on the SAME workload: everything table
+    mode rejects lands on these kernels, so the bench line carries them next to the headline (N = 1 only)."""
+    out = {}
+    for label, prec, steps in (("f32", gb.F32, 3), ("f64", gb.F64, 2)):
+        try:
+            ch = gb.Chains(model, args.chains, seed=20260101, precision=prec, device=dev)
+            ch.sweep(1, record=True)
+            ms = ch.sweep_timed(steps, record=True)
+            v = n_vars * args.chains * steps / (ms * 1e-3)
+            out[label] = {"kernel": "k_sweep_colour<%s,2,4>" % ("float" if label == "f32" else "double"), "value": v, "unit": UNIT,
+                          "ms_per_step": ms / steps, "steps": steps, "roofline_frac": GATHER_BYTES_PER_UPDATE * v / 1e9 / peak}
+            del ch
+        except Exception as e:  # never lose the headline line over a secondary number
+            out[label] = {"error": str(e)[:200]}
+    return out
+
+
+def run_native(args):
+    import torch
+    import grample_b200 as gb
+    from grample_b200 import distributed as gbd
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+
+    prec = {"table": gb.TABLE, "f32": gb.F32, "f64": gb.F64}[args.precision]
+    kernel = {"table": "k_sweep_tab<64,4,false,3>", "f32": "k_sweep_colour<float,2,4>", "f64": "k_sweep_colour<double,2,4>"}[args.precision]
+    dtype = {"table": "u32", "f32": "f32", "f64": "f64"}[args.precision]
+    t_setup = time.time()
+    arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)
+    model = gb.Model.from_arrays(*arrays, device=dev)
+    n_vars = model.n_vars
+    order, coff = model.schedule()
+    n_colours = len(coff) - 1
+    chains = gb.Chains(model, args.chains, seed=20260101, first_chain_id=rank * args.chains, precision=prec, device=dev)
+    gbd.attach(chains, dist)  # N > 1: the library's own NCCL communicator (torch.distributed only carries its 128-byte id)
+    chains.synchronize()
+    setup_s = time.time() - t_setup
+    updates_per_step = n_vars * args.chains  # per GPU
+    model_bytes = int(sum(a.nbytes for a in arrays))
+    total_card = model.total_card
+
+    ms, launches, clocks, e_ms, merged = measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, dev)
+    value = world * updates_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * updates_per_step * args.steps / (e_ms * 1e-3)
-    score = gb.error_suite(cards, mar, merged)  # host scoring of the read-back (untimed sanity use)
+    score = gb.error_suite(model.cards, np.full(total_card, 0.5), merged)  # host scoring of the read-back (untimed sanity use)
+
+    # ---------------- strong scaling (SURVEY 8d: the SAME 65536 chains split over the N GPUs), N > 1 only
+    strong = None
+    if world > 1:
+        del chains
+        per = args.chains // world // 8 * 8
+        sch = gb.Chains(model, per, seed=20260101, first_chain_id=rank * per, precision=prec, device=dev)
+        gbd.attach(sch, dist)
+        sch.synchronize()
+        s_ms, s_launches, s_clocks, s_e_ms, _ = measure(gb, gbd, torch, dist, sch, model, args, n_vars * per, world, dev)
+        s_updates = world * n_vars * per * args.steps
+        strong = {"chains_total": per * world, "chains_per_gpu": per, "value": s_updates / (s_ms * 1e-3), "unit": UNIT,
+                  "ms_per_step": s_ms / args.steps, "e2e": {"value": s_updates / (s_e_ms * 1e-3), "unit": UNIT, "ms_per_step": s_e_ms / args.steps,
+                                                             "d2h_bytes_per_step": int(total_card * 8 + 16)},
+                  "gpu_launches": int(s_launches), "clocks": s_clocks,
+                  "note": "efficiency = strong.value (or strong.e2e.value) / the N = 1 run's value (e2e.value): same total work"}
+        chains = sch
 
     # ---------------- roofline of the dominant kernel (one launch = one colour of one sweep)
     peak, peak_src = hbm_peak()
     launch_ms = ms / (args.steps * n_colours)
     updates_per_launch = updates_per_step / n_colours
     achieved = GATHER_BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "issue",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": kernel,
                 "algorithmic_bytes_per_update": GATHER_BYTES_PER_UPDATE, "updates_per_launch": updates_per_launch,
-                "launch_ms": launch_ms}
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
-    # bytes per update measured at the capture's chain count, scaled to this launch's update count)
+                "launch_ms": launch_ms,
+                "frac_of_compulsory_ceiling": COMPULSORY_BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9 / peak,
+                "compulsory_bytes_per_update": COMPULSORY_BYTES_PER_UPDATE,
+                "bound_note": "achieved / peak / frac are SURVEY 8d's gather-byte yardstick (5 B per update) over the measured HBM copy "
+                              "bandwidth; frac_of_compulsory_ceiling is the same rate against the 2 B per update a perfect-reuse "
+                              "uint8 sweep must move.  ncu (profiles/) shows the kernel bound by instruction issue on the ALU / FMA "
+                              "pipes, not by DRAM: see `issue`"}
+    # DRAM traffic and issue figures of the dominant kernel from the committed ncu --set full capture
+    # (profiles/traffic.json: per update at the capture's chain count, scaled to this launch's update count)
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr) and args.precision == "table":
         try:
             t = json.load(open(tr))
             roofline["traffic"] = t["dram_bytes_per_update"] * updates_per_launch
             roofline["traffic_source"] = t["source"]
+            if "issue" in t:
+                roofline["issue"] = t["issue"]
         except Exception:
             pass
 
     if rank != 0:
         if dist is not None:
+            del chains
             dist.destroy_process_group()
         return
 
-    # ---------------- secondary workloads (reported next to the headline, N = 1 only): the bundled UAI
-    # problems of BASELINE.json configs[1..3] at their chain counts, device time of one 500-sweep launch
+    # ---------------- secondary workloads (reported next to the headline, N = 1 only): the general log-sum-exp path on
+    # the same workload, and the bundled UAI problems of BASELINE.json configs[1..3] at their chain counts
     secondary = None
     if world == 1 and not args.no_secondary:
         del chains
-        secondary = small_model_rates(gb, dev)
+        secondary = {"lse": lse_rates(gb, model, args, dev, n_vars, peak)} if args.precision == "table" else {}
+        secondary.update(small_model_rates(gb, dev))
         secondary["samples_to_mean_hellinger_below_0.01"] = samples_to_hellinger(gb, dev)
 
     cpu = None
@@ -329,19 +391,23 @@ def run_native(args):
                        "setup_seconds": round(setup_s, 2)},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": int(total_card * 8 + 8), "ms_per_step": e_ms / args.steps,
-                    "path": "gb_chains_sweep + gb_chains_merged_marginals (pinned host result buffer) per step",
+                    "d2h_bytes_per_step": int(total_card * 8 + 16), "ms_per_step": e_ms / args.steps,
+                    "path": "per step: gb_chains_sweep, gb_chains_merge_end (the previous step's merged marginals, pinned host "
+                            "buffer), gb_chains_merge_begin; in-library NCCL sum of the uint64 counts when N > 1",
                     "note": "the interval loop of cmd/root.go has no per-interval host input: chain state is device-resident "
                             "(as each Go chain's state is resident in its goroutine); the model (CSR + tables, "
                             f"{model_bytes} bytes) is uploaded once from host arrays during setup_seconds, and the collapsed "
                             "flags the merge needs are uploaded once per change of the chain set"},
             "roofline": roofline, "sanity": {"mean_hellinger_vs_uniform": score["MeanHellinger"]}}
+    if strong is not None:
+        line["strong"] = strong
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if secondary is not None:
         line["secondary"] = secondary
     print(json.dumps(line), flush=True)
     if dist is not None:
+        del chains  # (and with it the library's communicator) before torch tears its own down
         dist.destroy_process_group()
 
 

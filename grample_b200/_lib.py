@@ -74,6 +74,26 @@ _SIGS = {
     "gb_chains_group_info": (C.c_int, [_vp, C.c_int32, _i32p, _i64p, C.POINTER(_vp)]),
     "gb_chains_synchronize": (C.c_int, [_vp]),
     "gb_chains_merged_marginals": (C.c_int, [_vp, _f64p, _i32p]),
+    "gb_chains_merge_begin": (C.c_int, [_vp, _f64p, _i32p]),
+    "gb_chains_merge_end": (C.c_int, [_vp, _i64p, _i64p]),
+    "gb_chains_global_totals": (C.c_int, [_vp, _i64p, _i64p]),
+    "gb_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "gb_comm_init_rank": (C.c_int, [C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int, C.POINTER(_vp)]),
+    "gb_comm_info": (C.c_int, [_vp, _i32p, _i32p, C.POINTER(C.c_int)]),
+    "gb_comm_destroy": (None, [_vp]),
+    "gb_chains_attach_comm": (C.c_int, [_vp, _vp]),
+    "gb_fleet_create": (C.c_int, [C.c_int32, C.POINTER(C.c_int), C.POINTER(_vp)]),
+    "gb_fleet_destroy": (None, [_vp]),
+    "gb_fleet_size": (C.c_int, [_vp, _i32p]),
+    "gb_fleet_attach": (C.c_int, [_vp, C.c_int32, _vp]),
+    "gb_fleet_sweep": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "gb_fleet_advance": (C.c_int, [_vp, C.c_int32]),
+    "gb_fleet_synchronize": (C.c_int, [_vp]),
+    "gb_fleet_merged_marginals": (C.c_int, [_vp, _f64p, _i32p]),
+    "gb_fleet_merge_begin": (C.c_int, [_vp, _f64p, _i32p]),
+    "gb_fleet_merge_end": (C.c_int, [_vp, _i64p, _i64p]),
+    "gb_fleet_convergence": (C.c_int, [_vp, C.c_int, _f64p, _f64p]),
+    "gb_fleet_adapt": (C.c_int, [_vp, C.POINTER(_vp), C.c_int32, C.c_int32, C.c_int, C.c_int32, C.c_int32, C.c_uint64, _i32p, _i32p]),
     "gb_chains_merge_partial_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     "gb_chains_merge_finalize": (C.c_int, [_vp, _f64p, _i32p]),
     "gb_chains_convergence": (C.c_int, [_vp, C.c_int, _f64p, _f64p]),

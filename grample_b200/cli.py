@@ -301,6 +301,7 @@ def _sample(args, out, mon, start, dist=None, rank=0, world=1):
                          rao_blackwell=args.rao_blackwell)
     for idx in range(1, base):
         chains.add_group(models[idx], n_local, idx * per + shard_first)
+    gbd.attach(chains, dist)  # multi-GPU: MergeChains / ChainConvergence / Adapt reduce inside the library (its own NCCL communicator)
     chains.burnin((burn + n_free - 1) // max(n_free, 1))
     next_id = base * per
     trace = open(args.trace, "w") if (args.trace and rank == 0) else (_Null() if args.trace else None)

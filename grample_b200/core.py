@@ -258,6 +258,30 @@ class Chains:
         check(lib().gb_chains_merged_marginals(self.h, _ptr(out, _f64p), _ptr(col, _i32p)))
         return out, col
 
+    def merge_begin(self, out=None):
+        """MergeChains off the sweep stream: snapshot now, reduce (NCCL when a communicator is attached) and copy to the
+        host on a side stream while later sweeps run.  `out` must stay alive until merge_end()."""
+        self._pending = self._merge_buffers(out)
+        check(lib().gb_chains_merge_begin(self.h, _ptr(self._pending[0], _f64p), _ptr(self._pending[1], _i32p)))
+
+    def merge_end(self):
+        """-> (merged, collapsed flags, chains over all ranks, TotalSampleCount over all ranks)"""
+        n, t = C.c_int64(), C.c_int64()
+        check(lib().gb_chains_merge_end(self.h, C.byref(n), C.byref(t)))
+        out, col = self._pending
+        self._pending = None
+        return out, col, n.value, t.value
+
+    def global_totals(self):
+        n, t = C.c_int64(), C.c_int64()
+        check(lib().gb_chains_global_totals(self.h, C.byref(n), C.byref(t)))
+        return n.value, t.value
+
+    def attach_comm(self, comm):
+        """in-library NCCL: merged_marginals / merge_begin / convergence / adapt become collective over the ranks"""
+        check(lib().gb_chains_attach_comm(self.h, comm.h if comm is not None else None))
+        self.comm = comm
+
     def merge_partial_dev(self):
         """(device pointer, n doubles) of this device's MergeChains contribution, for an all-reduce."""
         p, n = C.c_void_p(), C.c_int64()
@@ -328,6 +352,100 @@ class Chains:
         out = np.zeros((2, self.base.total_card, n_chains), dtype=np.uint16)
         check(lib().gb_chains_group_history(self.h, group, out.ctypes.data_as(C.POINTER(C.c_uint16))))
         return out
+
+
+class Comm:
+    """One rank of an NCCL communicator owned by the library (gb_comm_*)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().gb_comm_unique_id(buf))
+        return bytes(buf)
+
+    @staticmethod
+    def init_rank(unique_id, world, rank, device):
+        out = C.c_void_p()
+        buf = (C.c_uint8 * 128)(*unique_id) if unique_id is not None else None
+        check(lib().gb_comm_init_rank(buf, world, rank, device, C.byref(out)))
+        return Comm(out)
+
+    @property
+    def info(self):
+        w, r, d = C.c_int32(), C.c_int32(), C.c_int()
+        check(lib().gb_comm_info(self.h, C.byref(w), C.byref(r), C.byref(d)))
+        return w.value, r.value, d.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().gb_comm_destroy(self.h)
+            self.h = None
+
+
+class Fleet:
+    """The chain handles of one process's devices joined by a single-process communicator (gb_fleet_*)."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p()
+        check(lib().gb_fleet_create(len(devices), devs, C.byref(self.h)))
+        self.devices = list(devices)
+        self.chains = [None] * len(devices)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.chains = None  # (handles are destroyed by their owners; the fleet only borrows them)
+            lib().gb_fleet_destroy(self.h)
+            self.h = None
+
+    def attach(self, slot, chains):
+        check(lib().gb_fleet_attach(self.h, slot, chains.h))
+        self.chains[slot] = chains
+
+    def sweep(self, n_sweeps, record=True):
+        check(lib().gb_fleet_sweep(self.h, int(n_sweeps), int(record)))
+
+    def advance(self, cw):
+        check(lib().gb_fleet_advance(self.h, int(cw)))
+
+    def synchronize(self):
+        check(lib().gb_fleet_synchronize(self.h))
+
+    def merged_marginals(self, out=None):
+        out, col = self.chains[0]._merge_buffers(out)
+        check(lib().gb_fleet_merged_marginals(self.h, _ptr(out, _f64p), _ptr(col, _i32p)))
+        return out, col
+
+    def merge_begin(self, out=None):
+        self._pending = self.chains[0]._merge_buffers(out)
+        check(lib().gb_fleet_merge_begin(self.h, _ptr(self._pending[0], _f64p), _ptr(self._pending[1], _i32p)))
+
+    def merge_end(self):
+        n, t = C.c_int64(), C.c_int64()
+        check(lib().gb_fleet_merge_end(self.h, C.byref(n), C.byref(t)))
+        out, col = self._pending
+        self._pending = None
+        return out, col, n.value, t.value
+
+    def convergence(self, measure=HELLINGER, merged=None):
+        out = np.zeros(self.chains[0].base.n_vars)
+        mp = None
+        if merged is not None:
+            merged = _f64(merged)
+            mp = _ptr(merged, _f64p)
+        check(lib().gb_fleet_convergence(self.h, measure, mp, _ptr(out, _f64p)))
+        return out
+
+    def adapt(self, base_models, new_chain_count, chains_per_new_model, cw, first_chain_id, measure=HELLINGER, max_groups=128):
+        chosen = np.zeros(max(new_chain_count, 1), dtype=np.int32)
+        n = C.c_int32()
+        arr = (C.c_void_p * len(base_models))(*[m.h.value if isinstance(m.h, C.c_void_p) else m.h for m in base_models])
+        check(lib().gb_fleet_adapt(self.h, arr, new_chain_count, chains_per_new_model, measure, int(cw), max_groups,
+                                   C.c_uint64(first_chain_id), _ptr(chosen, _i32p), C.byref(n)))
+        return chosen[:n.value].tolist()
 
 
 def convergence_finalize(base_model, wb, cw, total_chains, collapsed):

@@ -8,9 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
+#include "comm.hpp"
 #include "host_model.hpp"
 #include "kernels.cuh"
 
@@ -54,12 +56,14 @@ T* dev_upload(const std::vector<T>& h) {
     return d;
 }
 
+constexpr int kMaxDevices = 64;  // per-device caches of launch configuration (indexed by device, checked in require_device)
+
 void require_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n < 1)
         throw gb::Err("grample_b200: no CUDA device available (there is no CPU fallback)");
-    if (device < 0 || device >= n) throw gb::Err("grample_b200: invalid device index " + std::to_string(device));
+    if (device < 0 || device >= n || device >= kMaxDevices) throw gb::Err("grample_b200: invalid device index " + std::to_string(device));
     CUDA_CHECK(cudaSetDevice(device));
 }
 
@@ -71,9 +75,14 @@ int grid_for(int64_t items, int threads) {
     return (int)blocks;
 }
 
-constexpr int kMaxDevices = 64;  // per-device caches of launch configuration
+std::mutex g_cfg_mu;             // guards those caches: handles on different threads may configure the same kernel
 
 }  // namespace
+
+// Thread safety ("every entry thread-safe per handle"): every entry point that takes a gb_chains* holds the
+// handle's mutex for its whole duration, so goroutines / pthreads may call into ONE handle concurrently and the calls
+// serialise in arrival order (stream order on the device follows).  A model's lazily built tables have their own lock.
+#define GB_LOCK(c) std::lock_guard<std::recursive_mutex> _gb_lock((c)->mu)
 
 struct gb_model {
     gb::HostModel h;
@@ -84,6 +93,7 @@ struct gb_model {
     int32_t* d_colour_off = nullptr;
     gb::DevTab tab{};
     bool tab_built = false;
+    std::recursive_mutex mu;  // lazily built threshold tables: a model is shared by the groups of several handles
 
     ~gb_model() {
         if (device >= 0) {
@@ -137,6 +147,7 @@ struct gb_model {
     // thresholds: evaluate every (tabulated variable, neighbour configuration) conditional once on the device
     bool thr_built = false;
     void ensure_thresholds() {
+        std::lock_guard<std::recursive_mutex> lk(mu);
         if (thr_built) return;
         if (device < 0) throw gb::Err("table / hybrid mode needs a device-resident model (there is no CPU fallback)");
         require_device(device);
@@ -158,6 +169,7 @@ struct gb_model {
     }
     // table mode proper: every sampled variable tabulated with <= 256 configurations, fixed-size records
     void ensure_tab() {
+        std::lock_guard<std::recursive_mutex> lk(mu);
         if (!h.tab_ok) throw gb::Err("table mode does not apply to this model: " + h.tab_why);
         if (tab_built) return;
         ensure_thresholds();
@@ -170,6 +182,7 @@ struct gb_model {
     // single-collapsed variants): the resident table kernel runs it, wide variables through their tprog entry
     bool hybrid_all_tables() const { return hybrid_tables() && h.tab_all; }
     void ensure_hybrid() {
+        std::lock_guard<std::recursive_mutex> lk(mu);
         if (!hybrid_tables()) return;
         ensure_thresholds();
         if (h.tab_all && !tab_built) {
@@ -189,6 +202,7 @@ struct Group {
     uint32_t sweep = 0;  // next Philox sweep index
     int64_t total_samples = 0;  // Chain.TotalSampleCount summed over the group's chains
     uint64_t scan_step = 0;     // next random-scan step index
+    bool window_filled = false; // the group has been through an AdvanceChain round (its half-window histograms are valid)
     uint8_t* d_state = nullptr;
     unsigned long long* d_counts = nullptr;
     uint16_t* d_hist = nullptr;
@@ -209,6 +223,7 @@ using gbh::Group;
 using gbh::ResidentPlan;
 
 struct gb_chains {
+    std::recursive_mutex mu;  // GB_LOCK: one call at a time per handle
     int device = 0;
     cudaStream_t stream = nullptr;
     uint64_t seed = 0;
@@ -231,6 +246,17 @@ struct gb_chains {
     std::vector<int32_t> col_any32;    // col_any widened for the ABI's int32 output
     double* h_merge = nullptr;         // pinned staging buffer for the device -> host copy
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // interval path (cmd/root.go:498-539) off the sweep stream: integer count sums -> NCCL all-reduce -> finalize -> D2H
+    // run on `merge_stream` behind a snapshot event, so the sweeps enqueued after gb_chains_merge_begin overlap with it
+    gb_comm* comm = nullptr;                 // borrowed; nullptr or world == 1: no collective
+    cudaStream_t merge_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_merge_done = nullptr;
+    unsigned long long* d_cnt = nullptr;     // [total_card + 2]: summed counts, chain count, TotalSampleCount
+    unsigned long long* h_tail = nullptr;    // pinned [2]: the (all-reduced) tail of d_cnt
+    bool merge_pending = false, merge_ever = false, merge_staged = false;
+    double* merge_out = nullptr;             // destination of the pending merge
+    int32_t* merge_col_out = nullptr;
+    int64_t global_chains = -1, global_samples = -1;  // tail of the last completed merge
     // groups are independent between monitor intervals (like the reference's goroutine per chain,
     // chain.go:197-215): their launches fan out over side streams and join back on `stream`
     std::vector<cudaStream_t> side;
@@ -252,6 +278,11 @@ struct gb_chains {
         cudaFree(d_wb);
         cudaFree(d_skip);
         cudaFree(d_merged_in);
+        cudaFree(d_cnt);
+        if (h_tail) cudaFreeHost(h_tail);
+        if (merge_stream) cudaStreamDestroy(merge_stream);
+        if (ev_snap) cudaEventDestroy(ev_snap);
+        if (ev_merge_done) cudaEventDestroy(ev_merge_done);
         if (h_merge) cudaFreeHost(h_merge);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -305,13 +336,20 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     g.n_pad = (n_chains + 7) / 8 * 8;
     g.first_chain = first_chain;
     const gb::HostModel& h = model->h;
-    CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
-    CUDA_CHECK(cudaMalloc(&g.d_counts, (size_t)h.total_card * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMemsetAsync(g.d_counts, 0, (size_t)h.total_card * sizeof(unsigned long long), c->stream));
-    if (c->flags & GB_CHAINS_HISTORY) {
-        size_t hb = (size_t)2 * h.total_card * g.n_pad * sizeof(uint16_t);
-        CUDA_CHECK(cudaMalloc(&g.d_hist, hb));
-        CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, hb, c->stream));
+    try {
+        CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
+        CUDA_CHECK(cudaMalloc(&g.d_counts, (size_t)h.total_card * sizeof(unsigned long long)));
+        CUDA_CHECK(cudaMemsetAsync(g.d_counts, 0, (size_t)h.total_card * sizeof(unsigned long long), c->stream));
+        if (c->flags & GB_CHAINS_HISTORY) {
+            size_t hb = (size_t)2 * h.total_card * g.n_pad * sizeof(uint16_t);
+            CUDA_CHECK(cudaMalloc(&g.d_hist, hb));
+            CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, hb, c->stream));
+        }
+    } catch (...) {  // a failed allocation must not leak the ones before it
+        cudaFree(g.d_state);
+        cudaFree(g.d_counts);
+        cudaFree(g.d_hist);
+        throw;
     }
     g.dev.state = g.d_state;
     g.dev.counts = g.d_counts;
@@ -350,7 +388,8 @@ void launch_colour(gb_chains* c, Group& g, const int32_t* d_vars, int32_t n, int
 template <int VB, int NN, bool HIST, int PF>
 void launch_tab_variant(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
     static int resident_dev[kMaxDevices] = {};  // per device: CTAs that fit at once (persistent tile loop)
-    int& resident = resident_dev[c->device % kMaxDevices];
+    std::lock_guard<std::mutex> cfg_lock(g_cfg_mu);
+    int& resident = resident_dev[c->device];
     constexpr size_t ring = (size_t)(PF > 0 ? (PF + 1) * NN * 256 * 8 : 0);  // cp.async prefetch ring
     if (!resident) {
         int per_sm = 0, sms = 0;
@@ -427,7 +466,8 @@ void launch_resident_rb(gb_chains* c, Group& g, int ch, size_t smem, int32_t his
     const int64_t passes = (items + 511) / 512;
     const int threads = CW == 0 ? (int)(((items + passes - 1) / passes + 31) / 32 * 32) : (int)std::min<int64_t>(256, (items + 31) / 32 * 32);
     static size_t configured_dev[kMaxDevices] = {};  // function attributes are per device
-    size_t& configured = configured_dev[c->device % kMaxDevices];
+    std::lock_guard<std::mutex> cfg_lock(g_cfg_mu);
+    size_t& configured = configured_dev[c->device];
     if (smem > configured) {
         CUDA_CHECK(cudaFuncSetAttribute(gb::k_sweep_resident<Real, MAXC, CW, TS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -473,9 +513,8 @@ bool tab_resident(const gb_chains* c, const Group& g) {
 
 #if GB_MAIN
 ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
-    static int disabled = -1, no_ts = -1;
-    if (disabled < 0) disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
-    if (no_ts < 0) no_ts = std::getenv("GB_NO_SMEM_TABLES") ? 1 : 0;  // A/B knob
+    static const int disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
+    static const int no_ts = std::getenv("GB_NO_SMEM_TABLES") ? 1 : 0;  // A/B knob (function-local statics initialise thread-safely)
     ResidentPlan p;
     if (disabled || (c->flags & GB_CHAINS_PER_COLOUR)) return p;
     const gb::HostModel& h = g.model->h;
@@ -621,7 +660,8 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
     static size_t configured_dev[2][kMaxDevices] = {};  // function attributes are per device
     const bool wide = h.tab_max_nbr > 8;
-    size_t& configured = configured_dev[wide][c->device % kMaxDevices];
+    std::lock_guard<std::mutex> cfg_lock(g_cfg_mu);
+    size_t& configured = configured_dev[wide][c->device];
     auto kernel = wide ? gb::k_sweep_tab_resident<true> : gb::k_sweep_tab_resident<false>;
     if (smem > configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -717,7 +757,10 @@ void sweeps(gb_chains* c, int64_t n, int record) {
     CUDA_CHECK(cudaGetLastError());
 }
 
-// (*Chain).AdvanceChain for one group: cw + 1 recorded sweeps, the last 2 * (cw / 2) into the window
+// (*Chain).AdvanceChain for one group: cw + 1 recorded sweeps.  buffer/circular.go: the window keeps the last
+// 2 * (cw / 2) values (NewCircularInt rounds the size down to even, circular.go:16-27) and FirstHalf / SecondHalf split
+// exactly those — for an odd cw the newest cw - 1 samples, i.e. the round's first 2 sweeps stay out of the histograms
+// (1 for an even cw).
 void advance_group(gb_chains* c, Group& g, int32_t cw) {
     const int32_t half = cw / 2;
     if (c->flags & GB_CHAINS_HISTORY) {
@@ -725,6 +768,7 @@ void advance_group(gb_chains* c, Group& g, int32_t cw) {
         CUDA_CHECK(cudaMemsetAsync(g.d_hist, 0, (size_t)2 * g.model->h.total_card * g.n_pad * sizeof(uint16_t), c->stream));
     }
     run_group(c, g, (int64_t)cw + 1, 1, cw + 1 - 2 * half, half);
+    g.window_filled = true;
 }
 
 // skip flags: bit0 = collapsed in any group, bit1 = fixed
@@ -745,8 +789,17 @@ void ensure_scratch(gb_chains* c) {
     const gb::HostModel& h = c->base();
     if (!c->d_merge) CUDA_CHECK(cudaMalloc(&c->d_merge, (size_t)h.total_card * sizeof(double)));
     if (!c->d_merged_in) CUDA_CHECK(cudaMalloc(&c->d_merged_in, (size_t)h.total_card * sizeof(double)));
-    if (!c->d_wb) CUDA_CHECK(cudaMalloc(&c->d_wb, (size_t)2 * h.n_vars * sizeof(double)));
+    if (!c->d_wb) CUDA_CHECK(cudaMalloc(&c->d_wb, ((size_t)2 * h.n_vars + 1) * sizeof(double)));  // + the chain count
     if (!c->d_skip) CUDA_CHECK(cudaMalloc(&c->d_skip, (size_t)h.n_vars));
+    if (!c->d_cnt) CUDA_CHECK(cudaMalloc(&c->d_cnt, ((size_t)h.total_card + 2) * sizeof(unsigned long long)));
+    if (!c->h_tail) CUDA_CHECK(cudaMallocHost(&c->h_tail, 2 * sizeof(unsigned long long)));
+    if (!c->merge_stream) {
+        int lo = 0, hi = 0;  // highest priority: its small kernels and the NCCL kernel take the first free SM slots
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&c->merge_stream, cudaStreamNonBlocking, hi));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_merge_done, cudaEventDisableTiming));
+    }
 }
 
 void refresh_collapsed_cache(gb_chains* c) {
@@ -766,12 +819,118 @@ void upload_skip(gb_chains* c) {
     const gb::HostModel& h = c->base();
     c->skip_bits.resize(h.n_vars);
     for (int v = 0; v < h.n_vars; v++) c->skip_bits[v] = (uint8_t)(c->col_any[v] | (h.fixed[v] >= 0 ? 2 : 0));
+    if (c->merge_ever) CUDA_CHECK(cudaStreamSynchronize(c->merge_stream));  // an earlier merge may still read the old flags
     CUDA_CHECK(cudaMemcpyAsync(c->d_skip, c->skip_bits.data(), c->skip_bits.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->col_any32.assign(c->col_any.begin(), c->col_any.end());
     c->skip_uploaded = true;
 }
 
+int64_t local_chains(const gb_chains* c) {
+    int64_t n = 0;
+    for (const auto& g : c->groups) n += g.n_chains;
+    return n;
+}
+bool has_peers(const gb_chains* c) { return c->comm && c->comm->world > 1; }
+
+// ---- MergeChains (chain.go:96-148) in three phases, so that a fleet of handles can put phase 2 of all its devices
+// ---- inside one NCCL group and so that phases 2-3 overlap with the sweeps enqueued after phase 1.
+// phase 1, sweep stream: snapshot = integer sums of the groups' counts (+ chain count, TotalSampleCount)
+void merge_snapshot(gb_chains* c) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    if (c->merge_pending) throw gb::Err("a merge is already pending on this handle: call gb_chains_merge_end first");
+    ensure_scratch(c);
+    const gb::HostModel& h = c->base();
+    upload_skip(c);
+    if (c->merge_ever) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_merge_done, 0));  // d_cnt of the previous interval has been consumed
+    CUDA_CHECK(cudaMemsetAsync(c->d_cnt, 0, ((size_t)h.total_card + 2) * sizeof(unsigned long long), c->stream));
+    bool first = true;
+    for (auto& g : c->groups) {
+        gb::k_merge_counts<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(
+            g.model->dev, g.d_counts, c->d_skip, c->d_cnt, first ? (unsigned long long)local_chains(c) : 0ull,
+            first ? (unsigned long long)c->total_samples : 0ull);
+        first = false;
+    }
+    c->launches += (int64_t)c->groups.size();
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(c->ev_snap, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->merge_stream, c->ev_snap, 0));
+}
+// phase 2, merge stream: sum over the ranks of the communicator (collective: every rank calls it; a fleet brackets
+// the calls of its devices with ncclGroupStart / ncclGroupEnd)
+void merge_reduce(gb_chains* c) {
+    if (!has_peers(c)) return;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    NCCL_CHECK(gbn::api().AllReduce(c->d_cnt, c->d_cnt, (size_t)c->base().total_card + 2, gbn::kNcclUint64, gbn::kNcclSum,
+                                    c->comm->nccl, c->merge_stream));
+}
+// phase 3, merge stream: counts -> marginals (every chain starts at uniform 1/card, model/variable.go:45) -> host.
+// A page-locked destination (cudaHostAlloc / cudaHostRegister / a pinned torch tensor) receives the DMA directly; a
+// pageable one goes through the handle's pinned staging buffer.  out == nullptr: keep the result on the device only.
+void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    const gb::HostModel& h = c->base();
+    const size_t bytes = (size_t)h.total_card * sizeof(double);
+    const double unit = (c->flags & GB_CHAINS_RAO_BLACKWELL) ? 1.0 / gb::kRbScale : 1.0;
+    gb::k_merge_finalize<<<(h.total_card + 255) / 256, 256, 0, c->merge_stream>>>(c->groups[0].model->dev, c->d_cnt, c->d_skip,
+                                                                                  c->d_merge, unit);
+    c->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    c->merge_staged = false;
+    if (out) {
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();  // (older drivers report an unregistered host pointer as an error)
+        if (pinned) {
+            CUDA_CHECK(cudaMemcpyAsync(out, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
+        } else {
+            if (!c->h_merge) CUDA_CHECK(cudaMallocHost(&c->h_merge, bytes));
+            CUDA_CHECK(cudaMemcpyAsync(c->h_merge, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
+            c->merge_staged = true;
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c->h_tail, c->d_cnt + h.total_card, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c->merge_stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_merge_done, c->merge_stream));
+    c->merge_out = out;
+    c->merge_col_out = collapsed_out;
+    c->merge_pending = true;
+    c->merge_ever = true;
+}
+// host side of the merge on an already-reduced vector: collapsed-in-any variables take the first such chain's local marginal
+void merge_overrides(gb_chains* c, double* out, int32_t* collapsed_out) {
+    const gb::HostModel& h = c->base();
+    refresh_collapsed_cache(c);
+    if (collapsed_out) {
+        upload_skip(c);
+        std::memcpy(collapsed_out, c->col_any32.data(), (size_t)h.n_vars * sizeof(int32_t));
+    }
+    if (!out) return;
+    for (int v : c->col_vars) {
+        const auto& m = c->groups[c->col_first_group[v]].model->h.coll_marg[v];  // chain.go:113-129: first chain found
+        for (int k = 0; k < h.card[v]; k++) out[h.card_off[v] + k] = m[k];
+    }
+}
+void merge_wait(gb_chains* c) {
+    if (!c->merge_pending) throw gb::Err("no merge is pending on this handle: call gb_chains_merge_begin first");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    CUDA_CHECK(cudaEventSynchronize(c->ev_merge_done));
+    c->merge_pending = false;
+    const gb::HostModel& h = c->base();
+    if (c->merge_staged) std::memcpy(c->merge_out, c->h_merge, (size_t)h.total_card * sizeof(double));
+    c->global_chains = (int64_t)c->h_tail[0];
+    c->global_samples = (int64_t)c->h_tail[1];
+    merge_overrides(c, c->merge_out, c->merge_col_out);
+}
+void merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out) {
+    merge_snapshot(c);
+    merge_reduce(c);
+    merge_collect(c, out, collapsed_out);
+    merge_wait(c);
+}
+
+// Legacy multi-device form (the caller all-reduces a float64 device buffer itself): this device's contribution
+// n_local / card + counts, collapsed variables zero
 void merge_partial(gb_chains* c) {
     CUDA_CHECK(cudaSetDevice(c->device));
     ensure_scratch(c);
@@ -790,11 +949,9 @@ void merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const gb::HostModel& h = c->base();
     const size_t bytes = (size_t)h.total_card * sizeof(double);
-    // a caller buffer that is page-locked (cudaHostAlloc / cudaHostRegister / a pinned torch tensor) receives the DMA
-    // directly; a pageable one goes through the handle's pinned staging buffer
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    if (!pinned) cudaGetLastError();  // (older drivers report an unregistered host pointer as an error)
+    if (!pinned) cudaGetLastError();
     if (pinned) {
         CUDA_CHECK(cudaMemcpyAsync(out, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -804,40 +961,74 @@ void merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         std::memcpy(out, c->h_merge, bytes);
     }
-    refresh_collapsed_cache(c);
-    if (collapsed_out) {
-        upload_skip(c);
-        std::memcpy(collapsed_out, c->col_any32.data(), (size_t)h.n_vars * sizeof(int32_t));
-    }
-    for (int v : c->col_vars) {
-        const auto& m = c->groups[c->col_first_group[v]].model->h.coll_marg[v];  // chain.go:113-129: first chain found
-        for (int k = 0; k < h.card[v]; k++) out[h.card_off[v] + k] = m[k];
-    }
+    merge_overrides(c, out, collapsed_out);
 }
 
-void convergence_partial(gb_chains* c, int measure, const double* merged) {
+// ---- ChainConvergence (chain.go:32-92) in phases, like the merge.
+// phase 1, sweep stream: per-variable sums of within / between distances over this device's chains, chain count in the tail
+void convergence_enqueue(gb_chains* c, int measure, const double* merged) {
     CUDA_CHECK(cudaSetDevice(c->device));
     if (!(c->flags & GB_CHAINS_HISTORY)) throw gb::Err("chains were created without GB_CHAINS_HISTORY");
     if (measure < 0 || measure > 3) throw gb::Err("unknown measure");
     ensure_scratch(c);
     const gb::HostModel& h = c->base();
-    std::vector<double> tmp;
-    if (!merged) {
-        merge_partial(c);
-        tmp.resize(h.total_card);
-        merge_finalize(c, tmp.data(), nullptr);
-        merged = tmp.data();
-    }
     upload_skip(c);
     CUDA_CHECK(cudaMemcpyAsync(c->d_merged_in, merged, (size_t)h.total_card * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemsetAsync(c->d_wb, 0, (size_t)2 * h.n_vars * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->d_wb, 0, ((size_t)2 * h.n_vars + 1) * sizeof(double), c->stream));
     for (auto& g : c->groups) {
         const int64_t items = (int64_t)h.n_vars * g.n_chains;
         gb::k_chain_dist<<<grid_for(items, 256), 256, 0, c->stream>>>(g.model->dev, g.dev, c->d_merged_in, c->d_skip,
-                                                                     measure, c->d_wb);
+                                                                     measure, c->d_wb, (double)g.n_chains);
         c->launches++;
     }
     CUDA_CHECK(cudaGetLastError());
+}
+// phase 2: sum over the ranks (collective)
+void convergence_reduce(gb_chains* c) {
+    if (!has_peers(c)) return;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    NCCL_CHECK(gbn::api().AllReduce(c->d_wb, c->d_wb, (size_t)2 * c->base().n_vars + 1, gbn::kNcclFloat64, gbn::kNcclSum,
+                                    c->comm->nccl, c->stream));
+}
+// phase 3: scores on the host (chain.go:46-59, 69-88) from the reduced sums and the global chain count
+void convergence_finalize(const gb::HostModel& h, const double* wb, int32_t cw, int64_t total_chains, const uint8_t* collapsed,
+                          double* out);
+void convergence_collect(gb_chains* c, double* out) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    const gb::HostModel& h = c->base();
+    std::vector<double> wb((size_t)2 * h.n_vars + 1);
+    CUDA_CHECK(cudaMemcpyAsync(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const int64_t total = (int64_t)(wb.back() + 0.5);
+    if (total < 2) throw gb::Err("Convergence requires at least 2 chains");
+    refresh_collapsed_cache(c);
+    convergence_finalize(h, wb.data(), c->last_cw, total, c->col_any.data(), out);
+}
+// the three phases on one handle; merged == nullptr: MergeChains first (collective when a communicator is attached)
+void convergence_scores(gb_chains* c, int measure, const double* merged, double* out) {
+    if (c->last_cw < 2) throw gb::Err("Total seen < Convergence Window: run gb_chains_advance first");
+    for (const auto& g : c->groups)
+        if (!g.window_filled) throw gb::Err("Total seen < Convergence Window: a chain group has not advanced since it was added");
+    std::vector<double> tmp;
+    if (!merged) {
+        tmp.resize(c->base().total_card);
+        merged_marginals(c, tmp.data(), nullptr);
+        merged = tmp.data();
+    }
+    convergence_enqueue(c, measure, merged);
+    convergence_reduce(c);
+    convergence_collect(c, out);
+}
+// legacy: this device's sums only, left in d_wb for the caller's own all-reduce
+void convergence_partial(gb_chains* c, int measure, const double* merged) {
+    std::vector<double> tmp;
+    if (!merged) {
+        tmp.resize(c->base().total_card);
+        merge_partial(c);
+        merge_finalize(c, tmp.data(), nullptr);
+        merged = tmp.data();
+    }
+    convergence_enqueue(c, measure, merged);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
@@ -900,7 +1091,7 @@ gb_model* collapse_model(const gb_model* src, int32_t var, uint64_t seed, int32_
         if (new_size > gb::kMaxTabSize)
             throw gb::Err("Function over " + std::to_string(blanket.size()) + " vars has size > " + std::to_string(gb::kMaxTabSize));
     }
-    if ((int)blanket.size() > gb::kNeighborVarMaxDev) throw gb::Err("blanket exceeds the device limit");
+    if ((int)blanket.size() > gb::kNeighborVarMaxDev) throw gb::Err("blanket exceeds the device limit");  // unreachable: 2^23 entries cap it at 23
 
     const auto& vf = h.var_funcs[var];
     gb::CollapsePlan pl{};
@@ -927,22 +1118,25 @@ gb_model* collapse_model(const gb_model* src, int32_t var, uint64_t seed, int32_
         }
         f_stride_v.push_back(sv);
     }
-    int32_t* d_off = dev_upload(f_tab_off);
-    int32_t* d_sv = dev_upload(f_stride_v);
-    int32_t* d_sb = dev_upload(f_stride_b);
-    pl.f_tab_off = d_off;
-    pl.f_stride_v = d_sv;
-    pl.f_stride_b = d_sb;
-    double *d_new = nullptr, *d_marg = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_new, (size_t)new_size * sizeof(double)));
+    struct DevBuf {  // scratch of this call, released on every exit path
+        void* p = nullptr;
+        ~DevBuf() { cudaFree(p); }
+    } b_off, b_sv, b_sb, b_new, b_marg;
+    b_off.p = dev_upload(f_tab_off);
+    b_sv.p = dev_upload(f_stride_v);
+    b_sb.p = dev_upload(f_stride_b);
+    pl.f_tab_off = static_cast<int32_t*>(b_off.p);
+    pl.f_stride_v = static_cast<int32_t*>(b_sv.p);
+    pl.f_stride_b = static_cast<int32_t*>(b_sb.p);
+    CUDA_CHECK(cudaMalloc(&b_new.p, (size_t)new_size * sizeof(double)));
     std::vector<double> marg(pl.card_v, 1e-12);  // line 138-140
-    d_marg = dev_upload(marg);
+    b_marg.p = dev_upload(marg);
+    double *d_new = static_cast<double*>(b_new.p), *d_marg = static_cast<double*>(b_marg.p);
     gb::k_collapse<<<(int)((new_size + 255) / 256), 256>>>(pl, src->dev.tab64, d_new, d_marg);
     CUDA_CHECK(cudaGetLastError());
     std::vector<double> new_tab((size_t)new_size);
     CUDA_CHECK(cudaMemcpy(new_tab.data(), d_new, (size_t)new_size * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(marg.data(), d_marg, marg.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_off); cudaFree(d_sv); cudaFree(d_sb); cudaFree(d_new); cudaFree(d_marg);
     gb::norm_marginal(marg);  // line 263
 
     // lines 275-290: append the new factor, drop the variable's old factors, keep order
@@ -1148,25 +1342,34 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
 }
 int gb_chains_add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_chain_id) {
     GB_TRY
+    GB_LOCK(c);
     CUDA_CHECK(cudaSetDevice(c->device));
     add_group(c, model, n_chains, first_chain_id, false);
     GB_END
 }
 void gb_chains_destroy(gb_chains* c) { delete c; }
-int gb_chains_n_groups(const gb_chains* c, int32_t* out) { *out = (int32_t)c->groups.size(); return 0; }
-int gb_chains_n_chains(const gb_chains* c, int64_t* out) {
-    int64_t n = 0;
-    for (auto& g : c->groups) n += g.n_chains;
-    *out = n;
+int gb_chains_n_groups(const gb_chains* cc, int32_t* out) {
+    gb_chains* c = const_cast<gb_chains*>(cc);
+    GB_LOCK(c);
+    *out = (int32_t)c->groups.size();
+    return 0;
+}
+int gb_chains_n_chains(const gb_chains* cc, int64_t* out) {
+    gb_chains* c = const_cast<gb_chains*>(cc);
+    GB_LOCK(c);
+    *out = local_chains(c);
     return 0;
 }
 
 int gb_chains_sweep(gb_chains* c, int64_t n_sweeps, int record) {
-    GB_TRY sweeps(c, n_sweeps, record);
+    GB_TRY
+    GB_LOCK(c);
+    sweeps(c, n_sweeps, record);
     GB_END
 }
 int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_out) {
     GB_TRY
+    GB_LOCK(c);
     CUDA_CHECK(cudaSetDevice(c->device));
     if (!c->ev0) {
         CUDA_CHECK(cudaEventCreate(&c->ev0));
@@ -1179,9 +1382,15 @@ int gb_chains_sweep_timed(gb_chains* c, int64_t n_sweeps, int record, float* ms_
     CUDA_CHECK(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
     GB_END
 }
-int gb_chains_launch_count(const gb_chains* c, int64_t* out) { *out = c->launches; return 0; }
+int gb_chains_launch_count(const gb_chains* cc, int64_t* out) {
+    gb_chains* c = const_cast<gb_chains*>(cc);
+    GB_LOCK(c);
+    *out = c->launches;
+    return 0;
+}
 int gb_chains_scan(gb_chains* c, int64_t n_steps, int record) {
     GB_TRY
+    GB_LOCK(c);
     if (n_steps < 0) throw gb::Err("Invalid step count");
     if (c->flags & GB_CHAINS_RAO_BLACKWELL) throw gb::Err("the random-scan parity mode records plain counts (no GB_CHAINS_RAO_BLACKWELL)");
     CUDA_CHECK(cudaSetDevice(c->device));
@@ -1205,11 +1414,14 @@ int gb_chains_scan(gb_chains* c, int64_t n_steps, int record) {
     GB_END
 }
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps) {
-    GB_TRY sweeps(c, n_sweeps, 0);
+    GB_TRY
+    GB_LOCK(c);
+    sweeps(c, n_sweeps, 0);
     GB_END
 }
 int gb_chains_advance(gb_chains* c, int32_t cw) {
     GB_TRY
+    GB_LOCK(c);
     if (cw < 0) throw gb::Err("Invalid convergence window");
     CUDA_CHECK(cudaSetDevice(c->device));
     c->last_cw = cw;
@@ -1217,7 +1429,12 @@ int gb_chains_advance(gb_chains* c, int32_t cw) {
     CUDA_CHECK(cudaGetLastError());
     GB_END
 }
-int gb_chains_total_samples(const gb_chains* c, int64_t* out) { *out = c->total_samples; return 0; }
+int gb_chains_total_samples(const gb_chains* cc, int64_t* out) {
+    gb_chains* c = const_cast<gb_chains*>(cc);
+    GB_LOCK(c);
+    *out = c->total_samples;
+    return 0;
+}
 
 // ---- per-group forms: one reference Chain maps to one group of replica chains
 static Group& group_at(gb_chains* c, int32_t group) {
@@ -1226,6 +1443,7 @@ static Group& group_at(gb_chains* c, int32_t group) {
 }
 int gb_chains_group_sweep(gb_chains* c, int32_t group, int64_t n_sweeps, int record) {
     GB_TRY
+    GB_LOCK(c);
     CUDA_CHECK(cudaSetDevice(c->device));
     run_group(c, group_at(c, group), n_sweeps, record, 0, -1);
     CUDA_CHECK(cudaGetLastError());
@@ -1233,6 +1451,7 @@ int gb_chains_group_sweep(gb_chains* c, int32_t group, int64_t n_sweeps, int rec
 }
 int gb_chains_group_advance(gb_chains* c, int32_t group, int32_t cw) {
     GB_TRY
+    GB_LOCK(c);
     if (cw < 0) throw gb::Err("Invalid convergence window");
     CUDA_CHECK(cudaSetDevice(c->device));
     c->last_cw = cw;
@@ -1243,27 +1462,55 @@ int gb_chains_group_advance(gb_chains* c, int32_t group, int32_t cw) {
 int gb_chains_group_info(gb_chains* c, int32_t group, int32_t* n_chains_out, int64_t* total_samples_out,
                          gb_model** model_out) {
     GB_TRY
+    GB_LOCK(c);
     Group& g = group_at(c, group);
     if (n_chains_out) *n_chains_out = g.n_chains;
     if (total_samples_out) *total_samples_out = g.total_samples;
     if (model_out) *model_out = g.model;
     GB_END
 }
+// The wait itself happens OUTSIDE the handle's lock: a goroutine parked in wg.Wait() must not keep the others from
+// enqueuing work (everything enqueued before this call is covered; what arrives later is not waited for).
 int gb_chains_synchronize(gb_chains* c) {
     GB_TRY
-    CUDA_CHECK(cudaSetDevice(c->device));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cudaEvent_t ev = nullptr;
+    {
+        GB_LOCK(c);
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(ev, c->stream));
+    }
+    const cudaError_t e = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    CUDA_CHECK(e);
     GB_END
 }
 
 int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out) {
     GB_TRY
-    merge_partial(c);
-    merge_finalize(c, out, collapsed_out);
+    GB_LOCK(c);
+    merged_marginals(c, out, collapsed_out);
+    GB_END
+}
+int gb_chains_merge_begin(gb_chains* c, double* out, int32_t* collapsed_out) {
+    GB_TRY
+    GB_LOCK(c);
+    merge_snapshot(c);
+    merge_reduce(c);
+    merge_collect(c, out, collapsed_out);
+    GB_END
+}
+int gb_chains_merge_end(gb_chains* c, int64_t* total_chains_out, int64_t* total_samples_out) {
+    GB_TRY
+    GB_LOCK(c);
+    merge_wait(c);
+    if (total_chains_out) *total_chains_out = c->global_chains;
+    if (total_samples_out) *total_samples_out = c->global_samples;
     GB_END
 }
 int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out) {
     GB_TRY
+    GB_LOCK(c);
     merge_partial(c);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the caller all-reduces the buffer on ITS stream
     *dev_ptr_out = c->d_merge;
@@ -1271,27 +1518,22 @@ int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_o
     GB_END
 }
 int gb_chains_merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out) {
-    GB_TRY merge_finalize(c, out, collapsed_out);
+    GB_TRY
+    GB_LOCK(c);
+    merge_finalize(c, out, collapsed_out);
     GB_END
 }
 
 int gb_chains_convergence(gb_chains* c, int measure, const double* merged, double* out) {
     GB_TRY
-    int64_t total = 0;
-    for (auto& g : c->groups) total += g.n_chains;
-    if (total < 2) throw gb::Err("Convergence requires at least 2 chains");
-    if (c->last_cw < 2) throw gb::Err("Total seen < Convergence Window: run gb_chains_advance first");
-    convergence_partial(c, measure, merged);
-    const gb::HostModel& h = c->base();
-    std::vector<double> wb((size_t)2 * h.n_vars);
-    CUDA_CHECK(cudaMemcpy(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    std::vector<uint8_t> col = collapsed_any(c);
-    convergence_finalize(h, wb.data(), c->last_cw, total, col.data(), out);
+    GB_LOCK(c);
+    convergence_scores(c, measure, merged, out);
     GB_END
 }
 int gb_chains_convergence_partial_dev(gb_chains* c, int measure, const double* merged, double** dev_ptr_out,
                                       int64_t* n_out) {
     GB_TRY
+    GB_LOCK(c);
     convergence_partial(c, measure, merged);
     *dev_ptr_out = c->d_wb;
     *n_out = (int64_t)2 * c->base().n_vars;
@@ -1307,56 +1549,50 @@ int gb_convergence_finalize(const gb_model* base, const double* wb, int32_t cw, 
     GB_END
 }
 
-// scores == nullptr: ChainConvergence over this handle's chains; otherwise the caller's per-variable
-// scores (multi-GPU: computed from the all-reduced within/between sums, identical on every rank, so
-// every rank chooses the same variables); total_chains_hint < 0: this handle's chain count
-static int adapt_impl(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
-                      int measure, int32_t cw, const double* scores, int64_t total_chains_hint, int32_t max_groups,
-                      uint64_t first_chain_id, uint64_t id_stride, int32_t* chosen_out, int32_t* n_chosen_out) {
-    if (n_chosen_out) *n_chosen_out = 0;
-    GB_TRY
-    CUDA_CHECK(cudaSetDevice(c->device));
-    int64_t total = 0;
-    for (auto& g : c->groups) total += g.n_chains;
-    if (total_chains_hint >= 0) total = total_chains_hint;
-    if (total < 2) throw gb::Err("At least 2 chains required for adaptation");
-    if ((int32_t)c->groups.size() >= max_groups) return 0;  // adaptive.go:62-64
+// ---- (*ConvergenceSampler).Adapt (adaptive.go:57-157) in steps, so that a fleet can run them in lockstep over its devices
+struct AdaptPlan {
+    bool noop = false;          // adaptive.go:62-64 (MaxChains reached) or no candidates (:88-91)
+    bool need_scores = false;   // more candidates than new chains: ChainConvergence decides (:100-119)
+    std::vector<int32_t> cand;  // adaptive.go:81-87: not fixed, not collapsed in any chain, 1 < blanket <= 12 on the ORIGINAL graph
+};
+static AdaptPlan adapt_plan(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t max_groups) {
+    AdaptPlan p;
+    if ((int32_t)c->groups.size() >= max_groups) {
+        p.noop = true;
+        return p;
+    }
     const gb::HostModel& b = base->h;
     std::vector<uint8_t> col = collapsed_any(c);
-    std::vector<int32_t> cand;  // adaptive.go:81-87: blanket sizes on the ORIGINAL graph
     for (int v = 0; v < b.n_vars; v++) {
         int sz = (int)b.nbrs[v].size();
-        if (b.fixed[v] < 0 && !col[v] && sz > 1 && sz <= gb::kNeighborVarMax) cand.push_back(v);
+        if (b.fixed[v] < 0 && !col[v] && sz > 1 && sz <= gb::kNeighborVarMax) p.cand.push_back(v);
     }
-    if (cand.empty()) return 0;
-    std::vector<int32_t> targets;
-    if ((int32_t)cand.size() <= new_chain_count) {
-        targets = cand;
-    } else {
-        std::vector<double> conv(b.n_vars);
-        if (scores) {
-            conv.assign(scores, scores + b.n_vars);
-        } else {
-            convergence_partial(c, measure, nullptr);
-            std::vector<double> wb((size_t)2 * b.n_vars);
-            CUDA_CHECK(cudaMemcpy(wb.data(), c->d_wb, wb.size() * sizeof(double), cudaMemcpyDeviceToHost));
-            convergence_finalize(b, wb.data(), cw, total, col.data(), conv.data());
-        }
-        // adaptive.go:111-119: sort descending, take from the END (= lowest scores); ties by id
-        std::stable_sort(cand.begin(), cand.end(), [&](int32_t x, int32_t y) { return conv[x] > conv[y]; });
-        for (int i = 0; i < new_chain_count; i++) targets.push_back(cand[cand.size() - 1 - i]);
-    }
+    if (p.cand.empty()) p.noop = true;
+    else p.need_scores = (int32_t)p.cand.size() > new_chain_count;
+    return p;
+}
+// adaptive.go:111-119: sort descending, take from the END (= lowest scores); ties by id
+static std::vector<int32_t> adapt_pick(const AdaptPlan& p, const double* conv, int32_t new_chain_count) {
+    if (!p.need_scores) return p.cand;
+    std::vector<int32_t> cand = p.cand, targets;
+    std::stable_sort(cand.begin(), cand.end(), [&](int32_t x, int32_t y) { return conv[x] > conv[y]; });
+    for (int i = 0; i < new_chain_count; i++) targets.push_back(cand[cand.size() - 1 - i]);
+    return targets;
+}
+// adaptive.go:130-154: one new group per chosen variable over a fresh clone of `base` with that variable collapsed
+static int adapt_apply(gb_chains* c, const gb_model* base, const std::vector<int32_t>& targets, int32_t chains_local,
+                       uint64_t first_chain_id, uint64_t id_stride, int32_t* chosen_out) {
     uint64_t first = first_chain_id;
     int n_done = 0;
     for (int32_t v : targets) {
         gb_model* nm = collapse_model(base, v, 0, nullptr, nullptr);
         try {
-            add_group(c, nm, chains_per_new_model, first, true);
+            add_group(c, nm, chains_local, first, true);
         } catch (...) {
             delete nm;
             throw;
         }
-        first += id_stride ? id_stride : (uint64_t)((chains_per_new_model + 7) / 8 * 8);
+        first += id_stride ? id_stride : (uint64_t)((chains_local + 7) / 8 * 8);
         // adaptive.go:145: NewChain(..., burnIn=2) — two single-variable steps; one un-recorded
         // sweep (>= 2 updates) is the sweep-granular equivalent
         run_group(c, c->groups.back(), 1, 0, 0, -1);
@@ -1364,6 +1600,53 @@ static int adapt_impl(gb_chains* c, const gb_model* base, int32_t new_chain_coun
         n_done++;
     }
     CUDA_CHECK(cudaGetLastError());
+    return n_done;
+}
+// this rank's share of `total` chains: contiguous, aligned to the blocks of 8 chains that share Philox calls
+static void shard_chains(int64_t total, int world, int rank, uint64_t* first_out, int32_t* n_out) {
+    const int64_t blocks = (total + 7) / 8, per = (blocks + world - 1) / world;
+    const int64_t first = std::min<int64_t>((int64_t)rank * per, blocks) * 8, last = std::min<int64_t>((int64_t)(rank + 1) * per, blocks) * 8;
+    *first_out = (uint64_t)first;
+    *n_out = (int32_t)std::max<int64_t>(0, std::min<int64_t>(last, total) - first);
+}
+
+// scores == nullptr: ChainConvergence over this handle's chains — over the chains of every rank when a communicator
+// is attached (collective; chains_per_new_model then counts a new variant's chains over ALL ranks and this rank takes
+// its shard); otherwise the caller's per-variable scores with an explicit local share
+static int adapt_impl(gb_chains* c, const gb_model* base, int32_t new_chain_count, int32_t chains_per_new_model,
+                      int measure, int32_t cw, const double* scores, int64_t total_chains_hint, int32_t max_groups,
+                      uint64_t first_chain_id, uint64_t id_stride, int32_t* chosen_out, int32_t* n_chosen_out) {
+    if (n_chosen_out) *n_chosen_out = 0;
+    GB_TRY
+    GB_LOCK(c);
+    CUDA_CHECK(cudaSetDevice(c->device));
+    const bool collective = !scores && has_peers(c);
+    if (!collective) {
+        const int64_t total = total_chains_hint >= 0 ? total_chains_hint : local_chains(c);
+        if (total < 2) throw gb::Err("At least 2 chains required for adaptation");
+    }
+    const AdaptPlan plan = adapt_plan(c, base, new_chain_count, max_groups);  // identical on every rank: same group list
+    if (plan.noop) return 0;
+    std::vector<double> conv;
+    if (plan.need_scores) {
+        if (scores) conv.assign(scores, scores + base->h.n_vars);
+        else {
+            conv.resize(base->h.n_vars);
+            if (cw >= 2) c->last_cw = cw;
+            convergence_scores(c, measure, nullptr, conv.data());
+        }
+    }
+    const std::vector<int32_t> targets = adapt_pick(plan, conv.data(), new_chain_count);
+    int32_t local = chains_per_new_model;
+    uint64_t first = first_chain_id, stride = id_stride;
+    if (collective) {
+        uint64_t off = 0;
+        shard_chains(chains_per_new_model, c->comm->world, c->comm->rank, &off, &local);
+        if (local < 1) throw gb::Err("fewer than 8 chains per rank in a new variant: rank " + std::to_string(c->comm->rank) + " would hold none");
+        first += off;
+        stride = (uint64_t)((chains_per_new_model + 7) / 8 * 8);
+    }
+    const int n_done = adapt_apply(c, base, targets, local, first, stride, chosen_out);
     if (n_chosen_out) *n_chosen_out = n_done;
     GB_END
 }
@@ -1388,6 +1671,7 @@ int gb_chains_adapt_scores(gb_chains* c, const gb_model* base, int32_t new_chain
 
 int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out) {
     GB_TRY
+    GB_LOCK(c);
     if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
     CUDA_CHECK(cudaSetDevice(c->device));
     Group& g = c->groups[group];
@@ -1401,6 +1685,7 @@ int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out) {
 }
 int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in) {
     GB_TRY
+    GB_LOCK(c);
     if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
     CUDA_CHECK(cudaSetDevice(c->device));
     Group& g = c->groups[group];
@@ -1421,6 +1706,7 @@ int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in) {
 }
 int gb_chains_group_counts(gb_chains* c, int32_t group, uint64_t* out) {
     GB_TRY
+    GB_LOCK(c);
     if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
     CUDA_CHECK(cudaSetDevice(c->device));
     Group& g = c->groups[group];
@@ -1430,6 +1716,7 @@ int gb_chains_group_counts(gb_chains* c, int32_t group, uint64_t* out) {
 }
 int gb_chains_group_history(gb_chains* c, int32_t group, uint16_t* out) {
     GB_TRY
+    GB_LOCK(c);
     if (group < 0 || group >= (int32_t)c->groups.size()) throw gb::Err("group index out of range");
     if (!(c->flags & GB_CHAINS_HISTORY)) throw gb::Err("chains were created without GB_CHAINS_HISTORY");
     CUDA_CHECK(cudaSetDevice(c->device));
@@ -1440,6 +1727,252 @@ int gb_chains_group_history(gb_chains* c, int32_t group, uint16_t* out) {
     CUDA_CHECK(cudaMemcpy(hh.data(), g.d_hist, hh.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     for (size_t r = 0; r < (size_t)2 * tc; r++)
         for (int ch = 0; ch < g.n_chains; ch++) out[r * g.n_chains + ch] = hh[r * g.n_pad + ch];
+    GB_END
+}
+
+// ------------------------------------------------------------------ communicators and fleets
+int gb_comm_unique_id(uint8_t* id_out) {
+    GB_TRY
+    gbn::UniqueId id;
+    NCCL_CHECK(gbn::api().GetUniqueId(&id));
+    std::memcpy(id_out, id.internal, gbn::kUniqueIdBytes);
+    GB_END
+}
+int gb_comm_init_rank(const uint8_t* id, int32_t world, int32_t rank, int device, gb_comm** out) {
+    GB_TRY
+    if (world < 1 || rank < 0 || rank >= world) throw gb::Err("invalid communicator rank / size");
+    require_device(device);
+    auto cm = std::make_unique<gb_comm>();
+    cm->world = world;
+    cm->rank = rank;
+    cm->device = device;
+    if (world > 1) {
+        if (!id) throw gb::Err("a communicator of more than one rank needs the unique id of gb_comm_unique_id");
+        gbn::UniqueId uid;
+        std::memcpy(uid.internal, id, gbn::kUniqueIdBytes);
+        NCCL_CHECK(gbn::api().CommInitRank(&cm->nccl, world, uid, rank));
+    }
+    *out = cm.release();
+    GB_END
+}
+int gb_comm_info(const gb_comm* cm, int32_t* world_out, int32_t* rank_out, int* device_out) {
+    if (world_out) *world_out = cm->world;
+    if (rank_out) *rank_out = cm->rank;
+    if (device_out) *device_out = cm->device;
+    return 0;
+}
+void gb_comm_destroy(gb_comm* cm) {
+    if (!cm) return;
+    if (cm->nccl) {
+        cudaSetDevice(cm->device);
+        try {
+            gbn::api().CommDestroy(cm->nccl);
+        } catch (...) {
+        }
+    }
+    delete cm;
+}
+int gb_chains_attach_comm(gb_chains* c, gb_comm* cm) {
+    GB_TRY
+    GB_LOCK(c);
+    if (cm && cm->device != c->device) throw gb::Err("communicator rank is bound to a different device than the chains");
+    if (c->merge_pending) throw gb::Err("a merge is pending on this handle");
+    c->comm = cm;
+    GB_END
+}
+int gb_chains_global_totals(const gb_chains* cc, int64_t* total_chains_out, int64_t* total_samples_out) {
+    gb_chains* c = const_cast<gb_chains*>(cc);
+    GB_TRY
+    GB_LOCK(c);
+    if (c->global_chains < 0) throw gb::Err("no merge has completed on this handle yet");
+    if (total_chains_out) *total_chains_out = c->global_chains;
+    if (total_samples_out) *total_samples_out = c->global_samples;
+    GB_END
+}
+
+}  // extern "C"
+
+// A fleet = the chain handles of ONE process's devices joined by a single-process communicator (ncclCommInitAll).
+// Its collectives run each phase on every device before the next, with the NCCL calls of a phase inside one group, which
+// is how a single thread drives several ranks.  Every device ends up with the same merged marginals / scores.
+struct gb_fleet {
+    std::mutex mu;
+    std::vector<gb_comm*> comms;
+    std::vector<gb_chains*> chains;  // borrowed, one per device (nullptr until attached)
+    ~gb_fleet() {
+        for (auto* cm : comms) gb_comm_destroy(cm);
+    }
+};
+namespace {
+struct FleetLock {  // the fleet's own lock, then every handle's, in device order
+    std::lock_guard<std::mutex> f;
+    std::vector<std::unique_lock<std::recursive_mutex>> h;
+    explicit FleetLock(gb_fleet* fl) : f(fl->mu) {
+        for (auto* c : fl->chains) {
+            if (!c) throw gb::Err("fleet: a device has no chains attached");
+            h.emplace_back(c->mu);
+        }
+    }
+};
+struct NcclGroup {
+    bool on;
+    explicit NcclGroup(bool enable) : on(enable) {
+        if (on) NCCL_CHECK(gbn::api().GroupStart());
+    }
+    void end() {
+        if (on) {
+            on = false;
+            NCCL_CHECK(gbn::api().GroupEnd());
+        }
+    }
+    ~NcclGroup() {
+        if (on) gbn::api().GroupEnd();
+    }
+};
+void fleet_merge_begin(gb_fleet* f, double* out, int32_t* collapsed_out) {
+    for (auto* c : f->chains) merge_snapshot(c);
+    NcclGroup grp(f->chains.size() > 1);
+    for (auto* c : f->chains) merge_reduce(c);
+    grp.end();
+    for (size_t i = 0; i < f->chains.size(); i++) merge_collect(f->chains[i], i == 0 ? out : nullptr, i == 0 ? collapsed_out : nullptr);
+}
+void fleet_merge_end(gb_fleet* f) {
+    for (auto* c : f->chains) merge_wait(c);
+}
+void fleet_convergence(gb_fleet* f, int measure, const double* merged, double* out) {
+    std::vector<double> tmp;
+    if (!merged) {
+        tmp.resize(f->chains[0]->base().total_card);
+        fleet_merge_begin(f, tmp.data(), nullptr);
+        fleet_merge_end(f);
+        merged = tmp.data();
+    }
+    for (auto* c : f->chains) {
+        if (c->last_cw < 2) throw gb::Err("Total seen < Convergence Window: run gb_fleet_advance first");
+        for (const auto& g : c->groups)
+            if (!g.window_filled) throw gb::Err("Total seen < Convergence Window: a chain group has not advanced since it was added");
+        convergence_enqueue(c, measure, merged);
+    }
+    NcclGroup grp(f->chains.size() > 1);
+    for (auto* c : f->chains) convergence_reduce(c);
+    grp.end();
+    std::vector<double> other(f->chains[0]->base().n_vars);
+    for (size_t i = 0; i < f->chains.size(); i++) convergence_collect(f->chains[i], i == 0 ? out : other.data());
+}
+}  // namespace
+
+extern "C" {
+
+int gb_fleet_create(int32_t n_dev, const int* devices, gb_fleet** out) {
+    GB_TRY
+    if (n_dev < 1) throw gb::Err("a fleet needs at least one device");
+    for (int i = 0; i < n_dev; i++) require_device(devices[i]);
+    auto f = std::make_unique<gb_fleet>();
+    std::vector<gbn::Comm> raw(n_dev, nullptr);
+    if (n_dev > 1) NCCL_CHECK(gbn::api().CommInitAll(raw.data(), n_dev, devices));
+    for (int i = 0; i < n_dev; i++) {
+        auto* cm = new gb_comm();
+        cm->nccl = raw[i];
+        cm->world = n_dev;
+        cm->rank = i;
+        cm->device = devices[i];
+        cm->in_fleet = true;
+        f->comms.push_back(cm);
+    }
+    f->chains.assign(n_dev, nullptr);
+    *out = f.release();
+    GB_END
+}
+void gb_fleet_destroy(gb_fleet* f) { delete f; }
+int gb_fleet_size(const gb_fleet* f, int32_t* n_out) {
+    *n_out = (int32_t)f->comms.size();
+    return 0;
+}
+int gb_fleet_attach(gb_fleet* f, int32_t i, gb_chains* c) {
+    GB_TRY
+    std::lock_guard<std::mutex> lk(f->mu);
+    if (i < 0 || i >= (int32_t)f->comms.size()) throw gb::Err("fleet: device slot out of range");
+    if (!c) throw gb::Err("fleet: no chains supplied");
+    if (gb_chains_attach_comm(c, f->comms[i]) != 0) throw gb::Err(g_err);
+    f->chains[i] = c;
+    GB_END
+}
+// the per-device calls only enqueue work, so one thread keeps every device busy
+int gb_fleet_sweep(gb_fleet* f, int64_t n_sweeps, int record) {
+    GB_TRY
+    FleetLock lk(f);
+    for (auto* c : f->chains) sweeps(c, n_sweeps, record);
+    GB_END
+}
+int gb_fleet_advance(gb_fleet* f, int32_t cw) {
+    GB_TRY
+    FleetLock lk(f);
+    for (auto* c : f->chains)
+        if (gb_chains_advance(c, cw) != 0) throw gb::Err(g_err);
+    GB_END
+}
+int gb_fleet_synchronize(gb_fleet* f) {
+    GB_TRY
+    FleetLock lk(f);
+    for (auto* c : f->chains) {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    GB_END
+}
+int gb_fleet_merge_begin(gb_fleet* f, double* out, int32_t* collapsed_out) {
+    GB_TRY
+    FleetLock lk(f);
+    fleet_merge_begin(f, out, collapsed_out);
+    GB_END
+}
+int gb_fleet_merge_end(gb_fleet* f, int64_t* total_chains_out, int64_t* total_samples_out) {
+    GB_TRY
+    FleetLock lk(f);
+    fleet_merge_end(f);
+    if (total_chains_out) *total_chains_out = f->chains[0]->global_chains;
+    if (total_samples_out) *total_samples_out = f->chains[0]->global_samples;
+    GB_END
+}
+int gb_fleet_merged_marginals(gb_fleet* f, double* out, int32_t* collapsed_out) {
+    GB_TRY
+    FleetLock lk(f);
+    fleet_merge_begin(f, out, collapsed_out);
+    fleet_merge_end(f);
+    GB_END
+}
+int gb_fleet_convergence(gb_fleet* f, int measure, const double* merged, double* out) {
+    GB_TRY
+    FleetLock lk(f);
+    fleet_convergence(f, measure, merged, out);
+    GB_END
+}
+int gb_fleet_adapt(gb_fleet* f, gb_model* const* bases, int32_t new_chain_count, int32_t chains_per_new_model, int measure,
+                   int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out, int32_t* n_chosen_out) {
+    if (n_chosen_out) *n_chosen_out = 0;
+    GB_TRY
+    FleetLock lk(f);
+    const int world = (int)f->chains.size();
+    const AdaptPlan plan = adapt_plan(f->chains[0], bases[0], new_chain_count, max_groups);
+    if (plan.noop) return 0;
+    std::vector<double> conv(bases[0]->h.n_vars, 0.0);
+    if (plan.need_scores) {
+        if (cw >= 2)
+            for (auto* c : f->chains) c->last_cw = cw;
+        fleet_convergence(f, measure, nullptr, conv.data());
+    }
+    const std::vector<int32_t> targets = adapt_pick(plan, conv.data(), new_chain_count);
+    const uint64_t stride = (uint64_t)((chains_per_new_model + 7) / 8 * 8);
+    int n_done = 0;
+    for (int i = 0; i < world; i++) {
+        uint64_t off = 0;
+        int32_t local = 0;
+        shard_chains(chains_per_new_model, world, i, &off, &local);
+        if (local < 1) throw gb::Err("fewer than 8 chains per device in a new variant: device slot " + std::to_string(i) + " would hold none");
+        CUDA_CHECK(cudaSetDevice(f->chains[i]->device));
+        n_done = adapt_apply(f->chains[i], bases[i], targets, local, first_chain_id + off, stride, i == 0 ? chosen_out : nullptr);
+    }
+    if (n_chosen_out) *n_chosen_out = n_done;
     GB_END
 }
 

@@ -77,6 +77,11 @@ struct HostModel {
         for (int64_t i = (int64_t)scope.size() - 1; i >= 0; i--) {
             int32_t v = scope[i];
             if (v < 0 || v >= n_vars) throw Err("Invalid var idx " + std::to_string(v) + " in function scope");
+            // The reference accepts a scope that names a variable twice and then reads BOTH slots from the state
+            // (function.go:180-202), i.e. only the table's diagonal in that pair is reachable.  None of the UAI
+            // fixtures does this and the fast paths here assume distinct scope variables, so it is rejected up front.
+            for (int64_t j = i + 1; j < (int64_t)scope.size(); j++)
+                if (scope[j] == v) throw Err("Variable " + std::to_string(v) + " appears twice in a function scope (not supported)");
             f.strides[i] = sz;
             sz *= card[v];
             if (sz > kMaxTabSize) throw Err("Function over " + std::to_string(scope.size()) + " vars has size > " + std::to_string(kMaxTabSize));

@@ -23,7 +23,7 @@
 
 namespace gb {
 
-constexpr int kNeighborVarMaxDev = 12;  // sampler.NeighborVarMax
+constexpr int kNeighborVarMaxDev = 23;  // blanket variables K3 can enumerate: model.maxTabSize = 2^23 bounds an explicit Collapse(var) to 23 binary neighbours (sampler.NeighborVarMax = 12 only limits the random pick and Adapt)
 constexpr int kMaxCardDev = 64;         // GB_MAX_CARD
 
 struct DevModel {
@@ -1369,7 +1369,7 @@ k_conditional(const DevModel m, const int32_t n_states, const int32_t* __restric
 
 // ------------------------------------------------------------------ K3
 struct CollapsePlan {
-    int32_t n_b;            // blanket size without the collapsed variable (<= 11)
+    int32_t n_b;            // blanket size without the collapsed variable (<= kNeighborVarMaxDev)
     int32_t n_f;            // factors touching the collapsed variable
     int32_t card_v;
     int64_t new_size;       // entries of the new table
@@ -1458,7 +1458,8 @@ __device__ __forceinline__ double measure_dev(int which, int card, FA A, FB B) {
 // histogram bin seeded with 1e-8 (chain.go:264-287); sums over chains into wb[v], wb[n_vars+v].
 static __global__ void __launch_bounds__(256)
 k_chain_dist(const DevModel m, const DevGroup g, const double* __restrict__ merged,
-             const uint8_t* __restrict__ skip, const int which, double* __restrict__ wb) {
+             const uint8_t* __restrict__ skip, const int which, double* __restrict__ wb, const double tail_chains) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wb + 2 * m.n_vars, tail_chains);  // chains behind these sums (summed over ranks with them)
     const int64_t total = (int64_t)m.n_vars * g.n_chains;
     for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
          item += (int64_t)gridDim.x * blockDim.x) {
@@ -1490,6 +1491,32 @@ k_merge_partial(const DevModel m, const unsigned long long* __restrict__ counts,
     const int v = m.entry_var[i];
     if (skip[v] & 1) return;
     out[i] += n_chains * (1.0 / (double)m.card[v]) + (double)counts[i] * count_unit;  // 1, or 2^-24 for the Rao-Blackwell bins
+}
+
+// MergeChains, integer form (multi-GPU and asynchronous path): the sample counts of this device's groups are summed as
+// 64-bit integers (collapsed-in-any variables stay 0); the tail carries this device's chain count and TotalSampleCount.
+// After the (optional) NCCL sum over ranks, k_merge_finalize adds the chains' uniform start mass (model/variable.go:45)
+// in one rounding per entry, so the merged marginals are bit-identical however the chains are sharded over devices.
+static __global__ void __launch_bounds__(256)
+k_merge_counts(const DevModel m, const unsigned long long* __restrict__ counts, const uint8_t* __restrict__ skip,
+               unsigned long long* __restrict__ sum, const unsigned long long tail_chains, const unsigned long long tail_samples) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        sum[m.total_card] += tail_chains;
+        sum[m.total_card + 1] += tail_samples;
+    }
+    if (i >= m.total_card) return;
+    if (skip[m.entry_var[i]] & 1) return;
+    sum[i] += counts[i];
+}
+static __global__ void __launch_bounds__(256)
+k_merge_finalize(const DevModel m, const unsigned long long* __restrict__ sum, const uint8_t* __restrict__ skip,
+                 double* __restrict__ out, const double count_unit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.total_card) return;
+    const int v = m.entry_var[i];
+    const double n_chains = (double)sum[m.total_card];
+    out[i] = (skip[v] & 1) ? 0.0 : n_chains * (1.0 / (double)m.card[v]) + (double)sum[i] * count_unit;
 }
 
 }  // namespace gb

@@ -11,7 +11,11 @@
  *     gb_last_error() (thread-local), mirroring Go's `(value, error)` returns;
  *   - caller-allocated output buffers; host pointers unless a name says `_dev`;
  *   - every entry point selects its handle's CUDA device itself (goroutines migrate threads);
- *   - there is NO CPU fallback: without a CUDA device every compute call fails loudly.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails loudly;
+ *   - thread safety: every entry point that takes a gb_chains* (or gb_fleet*) holds that handle's lock for the call,
+ *     so goroutines / threads may call into one handle concurrently; the calls serialise in arrival order and the
+ *     device work follows in stream order.  gb_chains_synchronize waits outside the lock.  A gb_model may be shared
+ *     by handles driven from different threads (its lazily built tables are guarded).
  *
  * Layouts
  *   - a model is given as CSR arrays: card[n_vars], fixed[n_vars] (-1 = free), factor scopes
@@ -32,6 +36,8 @@ extern "C" {
 
 typedef struct gb_model gb_model;   /* factor graph + sampler bookkeeping, host + device copies */
 typedef struct gb_chains gb_chains; /* a population of chains (grouped by model) on ONE device   */
+typedef struct gb_comm gb_comm;     /* one rank of an NCCL communicator, bound to one device      */
+typedef struct gb_fleet gb_fleet;   /* the chain handles of one process's devices + their communicator */
 
 /* sampler.NeighborVarMax (sampler/gibbs-collapsed.go:93) and model.maxTabSize (model/function.go:59) */
 #define GB_NEIGHBOR_VAR_MAX 12
@@ -161,7 +167,9 @@ int gb_chains_scan(gb_chains* c, int64_t n_steps, int record);
 int gb_chains_burnin(gb_chains* c, int64_t n_sweeps);
 /* One reference "round" for all chains — (*Chain).AdvanceChain (chain.go:180-218) + the
  * WaitGroup barrier (cmd/root.go:475-479): cw+1 recorded sweeps, the last 2*(cw/2) of which
- * fill the first/second half-window histograms (buffer/circular.go semantics). */
+ * fill the first/second half-window histograms (buffer/circular.go: the ring holds 2*(cw/2) values and Add
+ * overwrites the oldest, so FirstHalf/SecondHalf split the NEWEST 2*(cw/2) samples — for an odd cw the round's
+ * first two samples of a variable stay outside the window, for an even cw the first one). */
 int gb_chains_advance(gb_chains* c, int32_t cw);
 /* sum of Chain.TotalSampleCount over this device's chains (cmd/root.go:488-491) */
 int gb_chains_total_samples(const gb_chains* c, int64_t* out);
@@ -184,7 +192,19 @@ int gb_chains_synchronize(gb_chains* c);
  * `out` is host memory; when it is page-locked (cudaHostAlloc / cudaHostRegister) the device-to-host copy lands in it
  * directly, otherwise it is staged through a pinned buffer of the handle. */
 int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out);
-/* Multi-device form: this device's un-merged contribution is written to a DEVICE buffer of
+/* The same, split so that the interval path overlaps with the next round's sweeps (the reference's monitor only
+ * READS the merged marginals, cmd/root.go:498-539): _begin snapshots the counts in stream order and runs the reduction
+ * (integer sums over this device's groups, NCCL sum over the communicator's ranks when one is attached, conversion to
+ * marginals, copy to `out`) on a side stream; sweeps enqueued afterwards run concurrently with it.  _end blocks until
+ * `out` / `collapsed_out` of the matching _begin are complete and returns the chain count and TotalSampleCount summed
+ * over all ranks (either may be NULL).  One merge may be pending per handle; `out` must stay valid until _end.
+ * The counts travel as 64-bit integers and the chains' uniform start mass is added once, after the reduction, so the
+ * result is bit-identical however the chains are sharded over devices. */
+int gb_chains_merge_begin(gb_chains* c, double* out, int32_t* collapsed_out);
+int gb_chains_merge_end(gb_chains* c, int64_t* total_chains_out, int64_t* total_samples_out);
+/* chain count / TotalSampleCount over all ranks as of the last completed merge (cmd/root.go:488-491) */
+int gb_chains_global_totals(const gb_chains* c, int64_t* total_chains_out, int64_t* total_samples_out);
+/* Legacy multi-device form (the CALLER all-reduces; do not mix with an attached communicator): this device's un-merged contribution is written to a DEVICE buffer of
  * sum(card) doubles (collapsed variables zero) so the host plumbing can all-reduce it in
  * place (NCCL); finalize overwrites collapsed variables and copies to the host. */
 int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out);
@@ -193,7 +213,7 @@ int gb_chains_merge_finalize(gb_chains* c, double* out, int32_t* collapsed_out);
 /* sampler.ChainConvergence + (*Chain).ChainDist (chain.go:32-92, 253-290) with `measure`
  * (K4 on the device).  merged == NULL: merge this device's chains first.  out[n_vars]. */
 int gb_chains_convergence(gb_chains* c, int measure, const double* merged, double* out);
-/* Multi-device form: per-variable sums of within/between distances over this device's chains
+/* Legacy multi-device form (the CALLER all-reduces): per-variable sums of within/between distances over this device's chains
  * into a DEVICE buffer [2*n_vars] (W then B) to be all-reduced, then finalised with the global
  * chain count. */
 int gb_chains_convergence_partial_dev(gb_chains* c, int measure, const double* merged, double** dev_ptr_out,
@@ -210,7 +230,12 @@ int gb_chains_adapt(gb_chains* c, const gb_model* base, int32_t new_chain_count,
                     int measure, int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out,
                     int32_t* n_chosen_out);
 
-/* Multi-GPU form of Adapt: `scores` [n_vars] are the ChainConvergence scores finalised from the
+/* With a communicator attached gb_chains_adapt is collective: the scores come from ChainConvergence over the chains of
+ * every rank (identical on every rank, so all ranks collapse the same variables), chains_per_new_model counts a new
+ * variant's chains over ALL ranks (this rank creates its block-aligned shard) and first_chain_id is the global id of the
+ * first new variant's first chain; consecutive variants are ceil8(chains_per_new_model) ids apart.
+ *
+ * Explicit form of the same (caller-computed scores): `scores` [n_vars] are the ChainConvergence scores finalised from the
  * all-reduced within/between sums (gb_chains_convergence_partial_dev -> all-reduce ->
  * gb_convergence_finalize), identical on every rank, so every rank picks the same variables;
  * total_chains = chains over all ranks; chains_per_new_model = THIS rank's share of each new
@@ -228,6 +253,45 @@ int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in);
 int gb_chains_group_counts(gb_chains* c, int32_t group, uint64_t* out);
 /* per-chain half-window histograms of one group: uint16 [2][sum(card)][n_chains] */
 int gb_chains_group_history(gb_chains* c, int32_t group, uint16_t* out);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * The reference's only synchronisation is the round barrier (cmd/root.go:475-479) followed by MergeChains /
+ * ChainConvergence on the host (:498-539, 640-668).  Here chains shard over devices by global chain id and those two
+ * reductions run inside the library over NCCL (NVLink / NVSwitch): 64-bit integer counts (sum(card) + 2 words) and the
+ * within / between sums (2 * n_vars + 1 doubles).  libnccl.so.2 is bound at run time (dlopen); single-device use
+ * never touches it.
+ *
+ * One process per GPU: rank 0 calls gb_comm_unique_id and hands the 128 bytes to the other ranks by any means (the
+ * launcher's store, a file, MPI); every rank calls gb_comm_init_rank with its device and attaches the communicator to
+ * its chain handle.  From then on gb_chains_merged_marginals / gb_chains_merge_begin / gb_chains_convergence /
+ * gb_chains_adapt are COLLECTIVE: every rank calls them in the same order. */
+#define GB_COMM_ID_BYTES 128
+int gb_comm_unique_id(uint8_t* id_out /*[GB_COMM_ID_BYTES]*/);
+int gb_comm_init_rank(const uint8_t* id /*[GB_COMM_ID_BYTES], may be NULL when world == 1*/, int32_t world, int32_t rank,
+                      int device, gb_comm** out);
+int gb_comm_info(const gb_comm* comm, int32_t* world_out, int32_t* rank_out, int* device_out);
+void gb_comm_destroy(gb_comm* comm);
+/* comm may be NULL (detach).  The handle borrows the communicator: destroy the chains first. */
+int gb_chains_attach_comm(gb_chains* c, gb_comm* comm);
+/* One process, several GPUs (a Go or C++ host like cmd/root.go): a fleet owns a single-process communicator over
+ * devices[] (ncclCommInitAll); the caller creates one model copy and one gb_chains per device (first_chain_id = the
+ * shard's first global chain id) and attaches them.  The gb_fleet_* calls are the gb_chains_* calls of the same name
+ * applied to every device — phase by phase, the NCCL calls of a phase inside one group, so ONE thread drives all
+ * devices; results are written once (they are identical on every device).  gb_fleet_adapt takes one base model per
+ * device slot (bases[i] lives on devices[i]). */
+int gb_fleet_create(int32_t n_dev, const int* devices, gb_fleet** out);
+void gb_fleet_destroy(gb_fleet* f);
+int gb_fleet_size(const gb_fleet* f, int32_t* n_out);
+int gb_fleet_attach(gb_fleet* f, int32_t slot, gb_chains* c);
+int gb_fleet_sweep(gb_fleet* f, int64_t n_sweeps, int record);
+int gb_fleet_advance(gb_fleet* f, int32_t cw);
+int gb_fleet_synchronize(gb_fleet* f);
+int gb_fleet_merged_marginals(gb_fleet* f, double* out, int32_t* collapsed_out);
+int gb_fleet_merge_begin(gb_fleet* f, double* out, int32_t* collapsed_out);
+int gb_fleet_merge_end(gb_fleet* f, int64_t* total_chains_out, int64_t* total_samples_out);
+int gb_fleet_convergence(gb_fleet* f, int measure, const double* merged, double* out);
+int gb_fleet_adapt(gb_fleet* f, gb_model* const* bases, int32_t new_chain_count, int32_t chains_per_new_model, int measure,
+                   int32_t cw, int32_t max_groups, uint64_t first_chain_id, int32_t* chosen_out, int32_t* n_chosen_out);
 
 /* ------------------------------------------------------------------ scoring (host)
  * model.NewErrorSuite (model/error.go:28-78).  fixed arrays may be NULL (= all free).

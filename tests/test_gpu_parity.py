@@ -227,6 +227,55 @@ def test_table_thresholds_match_oracle_conditionals(res, name, evid):
     assert total == n_thr
 
 
+def ising_models(rows, cols, wmax=4.9):
+    arrays = gb.ising_torus(rows, cols, wmax=wmax)
+    return gb.Model.from_arrays(*arrays, device=0), oracle.Model.create(*arrays)
+
+
+@pytest.mark.parametrize("which", ["Grids_11", "ising_6x8"])
+def test_table_threshold_quantisation_bound(res, which):
+    """Precision of table mode, stated: value 0 is drawn iff a uniform 32-bit draw u <= T, i.e. with
+    probability (T + 1) / 2^32.  For EVERY (variable, neighbour configuration) that probability is within 2^-32 ABSOLUTE
+    of the oracle's float64 conditional e0 / (e0 + e1) (gibbs-simple.go:186-258 after the 1e-6 floor), and the
+    threshold is exactly the reference's own predicate r = U * tot, r <= e0 (sampler.go:115-123) evaluated on the
+    32-bit grid.  Consequence, also asserted: the RELATIVE error of the sampled law is at most 2^-32 / p, i.e.
+    2.33e-4 at the 1e-6 probability floor and <= 1e-6 for every conditional above 2.33e-4 — a 32-bit draw cannot
+    resolve a floor-level probability to north_star's 1e-6 relative; the float64 path (53-bit draws) can."""
+    if which == "Grids_11":
+        dm, om = load_pair(res, "Grids_11.uai", False)
+    else:
+        dm, om = ising_models(6, 8)
+    samp = oracle.Sampler(oracle.Generator(3), om, collapsed=True)
+    cards = dm.cards
+    worst_abs, worst_rel, n_cfg, at_floor = 0.0, 0.0, 0, 0
+    for v in range(dm.n_vars):
+        thr = dm.thresholds(v)
+        nb = [u for u in samp.neighbors(v) if u != v and dm.fixed[u] < 0]
+        for cfg in range(len(thr)):
+            st = np.zeros(dm.n_vars, dtype=np.int32)
+            rem = cfg
+            for u in nb:
+                st[u] = rem % cards[u]
+                rem //= cards[u]
+            e = samp.conditional(v, st)
+            p0 = e[0] / (e[0] + e[1])
+            q0 = (int(thr[cfg]) + 1) / 4294967296.0
+            assert int(thr[cfg]) == expected_threshold(e), (v, cfg)   # the reference's predicate, exactly
+            assert abs(q0 - p0) <= 2.0 ** -32, (v, cfg, q0, p0)
+            worst_abs = max(worst_abs, abs(q0 - p0))
+            for p, q in ((p0, q0), (1.0 - p0, 1.0 - q0)):
+                worst_rel = max(worst_rel, abs(q - p) / p)
+                at_floor += p < 2e-6
+                assert abs(q - p) / p <= 2.0 ** -32 / p * (1 + 1e-9)
+                if p > 2.33e-4:
+                    assert abs(q - p) / p <= 1e-6
+            n_cfg += 1
+    assert n_cfg == dm.table_mode()[1]
+    assert worst_rel <= 2.0 ** -32 / 0.99e-6  # the floor keeps every probability >= ~1e-6
+    print(f"{which}: {n_cfg} configurations, worst |q - p| = {worst_abs:.3e} (2^-32 = {2.0 ** -32:.3e}), worst relative "
+          f"{worst_rel:.3e}, {at_floor} probabilities at the 1e-6 floor")
+
+
 @pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
 @pytest.mark.parametrize("n_chains,first", [(13, 16), (64, 0), (2100, 8)])
 def test_table_sweep_bitexact_grids(res, n_chains, first, per_colour):
@@ -769,6 +818,83 @@ def test_chain_convergence_parity(res, name, evid):
     assert n == 2 * dm.n_vars and p
 
 
+@pytest.mark.parametrize("cw", [5, 8, 21])
+def test_convergence_window_placement(res, cw):
+    """Which samples form the two half windows (buffer/circular.go): the ring holds 2 * (cw / 2) values and Add overwrites
+    the oldest, so after AdvanceChain's cw + 1 samples the halves are the NEWEST 2 * (cw / 2) — odd windows included.
+    The device histograms are checked against the actual trajectory pushed sample by sample through the oracle's ring."""
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    n_chains = 8
+    a = gb.Chains(dm, n_chains, seed=9, history=True, device=0)
+    b = gb.Chains(dm, n_chains, seed=9, history=False, device=0)
+    a.burnin(3)
+    b.burnin(3)
+    a.advance(cw)
+    traj = []
+    for _ in range(cw + 1):
+        b.sweep(1)
+        traj.append(b.get_state(0, n_chains))
+    traj = np.stack(traj)  # [cw + 1][chain][var]
+    assert np.array_equal(traj[-1], a.get_state(0, n_chains))
+    hist = a.group_history(0, n_chains)
+    half = cw // 2
+    for c in range(n_chains):
+        for v in range(0, dm.n_vars, 7):
+            ring = oracle.CircularInt(cw)
+            for s in range(cw + 1):
+                ring.add(int(traj[s, c, v]))
+            for h, vals in ((0, ring.first_half()), (1, ring.second_half())):
+                assert len(vals) == half
+                assert [int(hist[h, 2 * v + k, c]) for k in range(2)] == [list(vals).count(k) for k in range(2)], (c, v, h)
+    # and the scores equal the oracle's ChainConvergence over chains fed the full trajectories
+    merged, _ = a.merged_marginals()
+    cards = dm.cards
+    offs = np.concatenate([[0], np.cumsum(cards)])
+    ochains = []
+    for c in range(n_chains):
+        marg = [merged[offs[v]:offs[v + 1]] if c == 0 else np.zeros(cards[v]) for v in range(dm.n_vars)]
+        oc = oracle.Chain.from_marginals(cards, marg, cw=cw)
+        for v in range(dm.n_vars):
+            oc.set_history(v, [int(x) for x in traj[:, c, v]])
+        ochains.append(oc)
+    assert np.allclose(a.convergence(gb.HELLINGER), oracle.chain_convergence(ochains, oracle.HELLINGER, dm.n_vars), rtol=1e-9)
+
+
+def test_async_merge_and_single_rank_communicator(res):
+    """gb_chains_merge_begin / _end: the snapshot is taken in stream order, later sweeps do not leak into it, and the
+    result equals the blocking call; a communicator of one rank (no NCCL) changes nothing."""
+    dm, _ = load_pair(res, "Pedigree_11.uai", True)
+    nm, _, _ = dm.collapse(50)
+    ch = gb.Chains([dm, nm], [24, 8], seed=5, device=0)
+    ch.sweep(30)
+    ref, col = ch.merged_marginals()
+    ref, col = ref.copy(), col.copy()
+    ch.merge_begin()
+    ch.sweep(200)  # enqueued behind the snapshot: must not show up in it
+    out, col2, n_all, samples = ch.merge_end()
+    assert np.array_equal(out, ref) and np.array_equal(col, col2)
+    assert n_all == 32 and samples == 30 * (len(dm.schedule()[0]) * 24 + len(nm.schedule()[0]) * 8)
+    with pytest.raises(gb.GrampleError, match="no merge is pending"):
+        ch.merge_end()
+    ch.merge_begin()
+    with pytest.raises(gb.GrampleError, match="already pending"):
+        ch.merge_begin()
+    ch.merge_end()
+    later, _ = ch.merged_marginals()
+    assert later.sum() > ref.sum()
+    comm = gb.Comm.init_rank(None, 1, 0, 0)
+    assert comm.info == (1, 0, 0)
+    ch.attach_comm(comm)
+    again, _ = ch.merged_marginals()
+    assert np.array_equal(again, later)
+    assert ch.global_totals()[0] == 32
+    ch.attach_comm(None)
+    # multi-group sums are exact integers plus ONE rounding of the start mass: the legacy float64 partial agrees to rounding
+    ch.merge_partial_dev()
+    legacy, _ = ch.merge_finalize()
+    assert np.allclose(legacy, later, rtol=1e-15)
+
+
 def test_convergence_requires_history_and_chains(res):
     dm, _ = load_pair(res, "sample.uai", False)
     ch = gb.Chains(dm, 4, seed=1, history=False, device=0)
@@ -782,6 +908,15 @@ def test_convergence_requires_history_and_chains(res):
     ch2 = gb.Chains(dm, 4, seed=1, history=True, device=0)
     with pytest.raises(gb.GrampleError):  # chain.go:255-257
         ch2.convergence()
+    # a group added after the last round has empty windows: the reference errors with "Total seen < Convergence Window"
+    ch3 = gb.Chains(dm, 4, seed=1, history=True, device=0)
+    ch3.advance(10)
+    ch3.convergence()
+    ch3.add_group(dm, 4, 8)
+    with pytest.raises(gb.GrampleError, match="has not advanced"):
+        ch3.convergence()
+    ch3.advance(10)
+    ch3.convergence()
 
 
 # ------------------------------------------------------------------ adaptive (a12)
