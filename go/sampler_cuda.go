@@ -5,16 +5,24 @@
 // Drop this file into the reference's `sampler/` directory and build with `-tags cuda`
 // (see INTEGRATION.md).  It keeps the exported API that cmd/root.go and cmd/collapse.go drive:
 //
-//	NewGibbsSimple, NewGibbsCollapsed, (*GibbsCollapsed).Collapse/BlanketSize/FunctionCount,
-//	NeighborVarMax, NewChain, (*Chain).AdvanceChain, Chain.TotalSampleCount/LastSample,
+//	NewGibbsSimple, (*GibbsSimple).Sample/SampleVar/FunctionsChanged, NewGibbsCollapsed,
+//	(*GibbsCollapsed).Collapse/BlanketSize/FunctionCount/Sample/FunctionsChanged, NeighborVarMax,
+//	Measure, NewChain, (*Chain).AdvanceChain/ChainDist, Chain.TotalSampleCount/LastSample/ChainHistory,
 //	MergeChains, ChainConvergence, NewConvergenceSampler, NewIdentitySampler, Adapt.
 //
 // The pure-Go files it replaces (gibbs-simple.go, gibbs-collapsed.go, chain.go, adaptive.go) get
-// the build constraint `//go:build !cuda`; sampler.go (interfaces, UniformSampler) stays.
+// the build constraint `//go:build !cuda`; sampler.go (interfaces, UniformSampler) stays.  With
+// chain.go excluded this file also defines what lived there and is not sampling: type Measure
+// (chain.go:24), MergeChains (chain.go:96-148) and (*Chain).ChainDist (chain.go:253-290).
+//
+// Concurrency: every C-ABI entry that takes the gb_chains handle holds the handle's own lock
+// (include/grample_b200.h, "thread safety"), so the goroutines AdvanceChain spawns may call in
+// concurrently; thePool.mu only guards the creation of the handle and the chain-id counter.
 //
 // NOTE: this image has no Go toolchain, so this file has been written against
 // include/grample_b200.h but never compiled; the C++ mirror of the same layer
-// (grample_b200/host/grample.hpp) is what the tests exercise.
+// (grample_b200/host/grample.hpp) is what the tests exercise, and tests/threads_test.cpp makes
+// this file's concurrent call pattern (16 threads on one handle) through the C ABI.
 package sampler
 
 /*
@@ -26,10 +34,13 @@ package sampler
 import "C"
 
 import (
+	"math"
 	"reflect"
 	"runtime"
 	"sync"
+	"sync/atomic"
 
+	"github.com/CraigKelly/grample/buffer"
 	"github.com/CraigKelly/grample/model"
 	"github.com/CraigKelly/grample/rand"
 	"github.com/pkg/errors"
@@ -39,8 +50,12 @@ import (
 var (
 	// Replicas is the number of device chains behind ONE *Chain (the reference runs one).
 	Replicas = 1024
-	// Precision selects the sweep arithmetic (C.GB_F64 follows the reference literally).
-	Precision = C.GB_F32
+	// Precision selects the sweep arithmetic.  GB_HYBRID is the one default of every host of the
+	// boundary (this shim, the C++ mirror, the CLI's `auto`): the reference's float64 arithmetic
+	// throughout, sampled from float64-derived threshold tables where a variable's conditional can
+	// be tabulated and by the float64 log-sum-exp kernels elsewhere.  C.GB_F64 forces the
+	// per-update log-sum-exp everywhere; C.GB_F32 is the float32 opt-in.
+	Precision = C.GB_HYBRID
 	// Device is the CUDA device the process drives (one process per GPU).
 	Device = 0
 	// RaoBlackwell makes recorded updates add the sampled conditional to every bin of the variable instead of
@@ -54,6 +69,15 @@ func chainFlags() C.uint32_t {
 		f |= C.GB_CHAINS_RAO_BLACKWELL
 	}
 	return f
+}
+
+// chainPrecision: the Rao-Blackwell estimator accumulates log-sum-exp conditionals, so it runs GB_F64
+// unless the caller chose GB_F32.
+func chainPrecision() C.int {
+	if RaoBlackwell && Precision != C.GB_F32 {
+		return C.GB_F64
+	}
+	return C.int(Precision)
 }
 
 func lastErr(what string) error { return errors.Errorf("%s: %s", what, C.GoString(C.gb_last_error())) }
@@ -116,11 +140,14 @@ type pool struct {
 
 var thePool = &pool{}
 
-// GibbsSimple keeps the reference's name; the sampling itself happens in the sweep kernels.
+// GibbsSimple keeps the reference's name; chains advance in the sweep kernels, single steps
+// (Sample / SampleVar) go through gb_model_sample.
 type GibbsSimple struct {
-	gen *rand.Generator
-	pgm *model.Model
-	dev *devModel
+	gen  *rand.Generator
+	pgm  *model.Model
+	dev  *devModel
+	seed uint64 // Philox key of the single-step path
+	step uint64 // its counter (one per Sample / SampleVar call)
 }
 
 // NewGibbsSimple creates a new sampler (sampler/gibbs-simple.go:25-115).
@@ -135,13 +162,59 @@ func NewGibbsSimple(gen *rand.Generator, m *model.Model) (*GibbsSimple, error) {
 	for _, v := range m.Vars {
 		v.State["Selections"] = 0.0
 	}
-	return &GibbsSimple{gen: gen, pgm: m, dev: dev}, nil
+	return &GibbsSimple{gen: gen, pgm: m, dev: dev, seed: uint64(gen.Int63())}, nil
 }
 
-// Sample is kept for interface compatibility (FullSampler); single steps are not exposed by the
-// device path — chains advance in whole sweeps through AdvanceChain.
-func (g *GibbsSimple) Sample(s []int) (int, error) {
-	return -1, errors.New("single-step Sample is not available on the CUDA path; use Chain.AdvanceChain")
+// FunctionsChanged must be called after the model's Funcs changed (gibbs-simple.go:119-145): the
+// device copy is rebuilt from the Go model.  (Collapse does not need it: the library returns the
+// collapsed model itself.)  The reference also re-draws its private state here; on this path a
+// chain's state lives in its device group, which restarts when NewChain is called on the sampler.
+func (g *GibbsSimple) FunctionsChanged() error {
+	dev, err := flatten(g.pgm)
+	if err != nil {
+		return err
+	}
+	g.dev = dev
+	return nil
+}
+
+func (g *GibbsSimple) sampleOne(varIdx int, excludeCollapsed bool, s []int) (int, error) {
+	if len(s) != len(g.pgm.Vars) {
+		return -1, errors.Errorf("Sample size %d != Var size %d in model %s", len(s), len(g.pgm.Vars), g.pgm.Name)
+	}
+	st := make([]C.int32_t, len(s))
+	for i, x := range s {
+		st[i] = C.int32_t(x)
+	}
+	excl := C.int(0)
+	if excludeCollapsed {
+		excl = 1
+	}
+	prec := C.int(C.GB_F64)
+	if Precision == C.GB_F32 {
+		prec = C.GB_F32
+	}
+	var v C.int32_t
+	step := atomic.AddUint64(&g.step, 1)
+	if C.gb_model_sample(g.dev.h, prec, C.int32_t(varIdx), excl, C.uint64_t(g.seed), C.uint64_t(step), &st[0], &v) != 0 {
+		return -1, lastErr("Could not sample from var in model")
+	}
+	g.pgm.Vars[int(v)].State["Selections"] += 1.0 // gibbs-simple.go:165
+	s[int(v)] = int(st[int(v)])
+	return int(v), nil
+}
+
+// Sample returns a single sample — uniformly selects a variable to sample from
+// (gibbs-simple.go:148-160; FullSampler).  One small kernel launch per call: the throughput path is
+// Chain.AdvanceChain.
+func (g *GibbsSimple) Sample(s []int) (int, error) { return g.sampleOne(-1, false, s) }
+
+// SampleVar samples the given variable conditioned on the rest of `s` (gibbs-simple.go:163-271).
+func (g *GibbsSimple) SampleVar(varIdx int, s []int) (int, error) {
+	if varIdx < 0 || varIdx >= len(g.pgm.Vars) {
+		return -1, errors.Errorf("Invalid variable index %d", varIdx)
+	}
+	return g.sampleOne(varIdx, false, s)
 }
 
 // GibbsCollapsed supports collapsing specified variables (sampler/gibbs-collapsed.go:17-20).
@@ -198,8 +271,12 @@ func (g *GibbsCollapsed) Collapse(varIdx int) (*model.Variable, error) {
 	return dest, nil
 }
 
-// Sample — see GibbsSimple.Sample.
-func (g *GibbsCollapsed) Sample(s []int) (int, error) { return g.baseSampler.Sample(s) }
+// Sample is GibbsSimple.Sample over the un-collapsed variables (gibbs-collapsed.go:317-334).
+func (g *GibbsCollapsed) Sample(s []int) (int, error) { return g.baseSampler.sampleOne(-1, true, s) }
+
+// FunctionsChanged — see GibbsSimple.FunctionsChanged (gibbs-collapsed.go:44-78: the neighbour sets
+// are rebuilt by gb_model_create).
+func (g *GibbsCollapsed) FunctionsChanged() error { return g.baseSampler.FunctionsChanged() }
 
 func devOf(s FullSampler) (*GibbsSimple, error) {
 	switch t := s.(type) {
@@ -211,17 +288,24 @@ func devOf(s FullSampler) (*GibbsSimple, error) {
 	return nil, errors.New("the CUDA path needs a GibbsSimple or GibbsCollapsed sampler")
 }
 
-// Chain provides functionality around a Gibbs sampler (sampler/chain.go:13-20).  ChainHistory is
-// kept on the device as per-chain half-window histograms.
+// Measure is an error metric used by ChainConvergence, e.g. model.HellingerDiff (sampler/chain.go:24).
+type Measure func(v1 *model.Variable, v2 *model.Variable) float64
+
+// Chain provides functionality around a Gibbs sampler (sampler/chain.go:13-20).  The sliding windows
+// live on the device as per-replica half-window histograms; ChainHistory is filled after every round
+// with replica 0's window (values in ascending order inside each half — every consumer in the
+// reference only counts them) so that code reading it keeps working.
 type Chain struct {
 	Target            *model.Model
 	Sampler           FullSampler
 	ConvergenceWindow int
+	ChainHistory      []*buffer.CircularInt
 	TotalSampleCount  int64
 	LastSample        []int
 
 	group    C.int32_t
 	replicas int
+	hist     []C.uint16_t // [2][sum(card)][replicas] half-window histograms of the last round
 }
 
 var nextChainID uint64
@@ -251,7 +335,10 @@ func NewChain(mod *model.Model, samp FullSampler, cw int, burnIn int64) (*Chain,
 	C.gb_chains_n_groups(thePool.h, &ng)
 	C.gb_model_schedule(base.dev.h, &nOrder, nil, nil, nil)
 	ch := &Chain{Target: mod, Sampler: samp, ConvergenceWindow: cw, LastSample: make([]int, len(mod.Vars)),
-		group: ng - 1, replicas: Replicas}
+		ChainHistory: make([]*buffer.CircularInt, len(mod.Vars)), group: ng - 1, replicas: Replicas}
+	for i := range ch.ChainHistory {
+		ch.ChainHistory[i] = buffer.NewCircularInt(cw)
+	}
 	sweeps := (burnIn + int64(nOrder) - 1) / int64(nOrder) // burnIn counts single-variable steps
 	if C.gb_chains_group_sweep(thePool.h, ch.group, C.int64_t(sweeps), 0) != 0 {
 		return nil, errors.Wrap(lastErr("sweep"), "Failure during chain burn in")
@@ -266,12 +353,12 @@ func (c *Chain) AdvanceChain(wg *sync.WaitGroup) error {
 	wg.Add(1)
 	go func() {
 		defer wg.Done()
-		runtime.LockOSThread()
+		runtime.LockOSThread() // gb_last_error is thread-local
 		defer runtime.UnlockOSThread()
-		thePool.mu.Lock()
-		rc := C.gb_chains_group_advance(thePool.h, c.group, C.int32_t(c.ConvergenceWindow))
-		thePool.mu.Unlock()
-		if rc != 0 || C.gb_chains_synchronize(thePool.h) != 0 {
+		// no shim-level lock: the handle serialises concurrent callers itself, and
+		// gb_chains_synchronize waits outside the handle's lock
+		if C.gb_chains_group_advance(thePool.h, c.group, C.int32_t(c.ConvergenceWindow)) != 0 ||
+			C.gb_chains_synchronize(thePool.h) != 0 {
 			panic("Async sample generation failed - cannot continue")
 		}
 		c.refresh()
@@ -286,19 +373,34 @@ func (c *Chain) refresh() {
 	base, _ := devOf(c.Sampler)
 	C.gb_model_total_card(base.dev.h, &tc)
 	counts := make([]C.uint64_t, int(tc))
-	thePool.mu.Lock()
 	C.gb_chains_group_counts(thePool.h, c.group, &counts[0])
 	var total C.int64_t
 	C.gb_chains_group_info(thePool.h, c.group, nil, &total, nil)
 	state := make([]C.int32_t, c.replicas*len(c.Target.Vars))
 	C.gb_chains_get_state(thePool.h, c.group, &state[0])
-	thePool.mu.Unlock()
+	c.hist = make([]C.uint16_t, 2*int(tc)*c.replicas)
+	C.gb_chains_group_history(thePool.h, c.group, &c.hist[0])
 	c.TotalSampleCount = int64(total)
+	unit := 1.0
+	if RaoBlackwell {
+		unit = 1.0 / 16777216.0 // bins are fixed point in units of 2^-24
+	}
 	o := 0
 	for i, v := range c.Target.Vars {
 		if !v.Collapsed {
 			for k := range v.Marginal {
-				v.Marginal[k] = float64(c.replicas)/float64(v.Card) + float64(counts[o+k])
+				v.Marginal[k] = float64(c.replicas)/float64(v.Card) + float64(counts[o+k])*unit
+			}
+		}
+		// replica 0's window, oldest half first (buffer/circular.go: Add keeps the newest BufSize values)
+		if v.FixedVal < 0 && !v.Collapsed {
+			for half := 0; half < 2; half++ {
+				for k := 0; k < v.Card; k++ {
+					n := int(c.hist[(half*int(tc)+o+k)*c.replicas])
+					for j := 0; j < n; j++ {
+						c.ChainHistory[i].Add(k)
+					}
+				}
 			}
 		}
 		o += v.Card
@@ -306,8 +408,81 @@ func (c *Chain) refresh() {
 	}
 }
 
-// MergeChains is unchanged from the reference (sampler/chain.go:96-148): it only reads
-// Target.Vars, which refresh() keeps current.  (Body omitted here: keep the reference's.)
+// MergeChains returns a single variable array from multiple chains (sampler/chain.go:96-148): a
+// variable collapsed in ANY chain is reported by a clone of the first such chain's variable and takes
+// no part in the summation; every other variable is the sum of the chains' Marginal vectors.  It
+// only reads Target.Vars, which refresh() keeps current after every round.
+func MergeChains(chains []*Chain) ([]*model.Variable, error) {
+	if len(chains) < 1 {
+		return nil, errors.Errorf("Can not merge 0 chains")
+	}
+	if len(chains) == 1 {
+		return chains[0].Target.Vars, nil
+	}
+	n := len(chains[0].Target.Vars)
+	merged := make([]*model.Variable, n)
+	frozen := make([]bool, n)
+	for i := 0; i < n; i++ {
+		src := chains[0].Target.Vars[i]
+		for _, ch := range chains {
+			if i < len(ch.Target.Vars) && ch.Target.Vars[i].Collapsed {
+				src, frozen[i] = ch.Target.Vars[i], true
+				break
+			}
+		}
+		merged[i] = src.Clone()
+	}
+	for _, ch := range chains[1:] {
+		if len(ch.Target.Vars) != n {
+			return nil, errors.Errorf("Cannot merge chain with %d vars into %d vars", len(ch.Target.Vars), n)
+		}
+		for i, v := range ch.Target.Vars {
+			if frozen[i] {
+				continue
+			}
+			for k, p := range v.Marginal {
+				merged[i].Marginal[k] += p
+			}
+		}
+	}
+	return merged, nil
+}
+
+// ChainDist returns the (within-chain, between-chain) distance of one variable under distFunc
+// (sampler/chain.go:253-290), averaged over this chain's replicas: each replica's half-window
+// histograms (every bin seeded with 1e-8) give within = d(first half, second half) and
+// between = d(merged, both halves).  ChainConvergence itself runs on the device; this host form
+// exists for callers that hold a custom Measure.
+func (c *Chain) ChainDist(distFunc Measure, varIdx int, mergedVar *model.Variable) (float64, float64, error) {
+	if c.hist == nil {
+		return math.NaN(), math.NaN(), errors.Errorf("Total seen %d < Convergence Window %d", 0, c.ConvergenceWindow)
+	}
+	vsrc := c.Target.Vars[varIdx]
+	if vsrc.Card != mergedVar.Card {
+		return math.NaN(), math.NaN(), errors.Errorf("Variable mismatch")
+	}
+	o, tc := 0, 0
+	for i, v := range c.Target.Vars {
+		if i < varIdx {
+			o += v.Card
+		}
+		tc += v.Card
+	}
+	within, between := 0.0, 0.0
+	for r := 0; r < c.replicas; r++ {
+		v1, v2 := vsrc.Clone(), vsrc.Clone()
+		for k := range vsrc.Marginal {
+			v1.Marginal[k] = 1e-8 + float64(c.hist[(o+k)*c.replicas+r])
+			v2.Marginal[k] = 1e-8 + float64(c.hist[(tc+o+k)*c.replicas+r])
+		}
+		within += distFunc(v1, v2)
+		for k, p := range v2.Marginal {
+			v1.Marginal[k] += p
+		}
+		between += distFunc(mergedVar, v1)
+	}
+	return within / float64(c.replicas), between / float64(c.replicas), nil
+}
 
 // measureID maps the reference's Measure functions (model/error.go) to the ids of the device
 // convergence kernel; Go funcs are only comparable through their code pointers.
@@ -343,9 +518,9 @@ func ChainConvergence(chains []*Chain, distFunc Measure, mergedVars []*model.Var
 		}
 	}
 	out := make([]C.double, len(mergedVars))
-	thePool.mu.Lock()
+	runtime.LockOSThread() // keep gb_last_error on this thread
+	defer runtime.UnlockOSThread()
 	rc := C.gb_chains_convergence(thePool.h, measureID(distFunc), &merged[0], &out[0])
-	thePool.mu.Unlock()
 	if rc != 0 {
 		return nil, lastErr("ChainConvergence")
 	}
@@ -421,9 +596,7 @@ func (c *ConvergenceSampler) Adapt(chains []*Chain, newChainCount int) ([]*Chain
 	var tc C.int32_t
 	C.gb_model_total_card(c.base.h, &tc)
 	merged := make([]C.double, int(tc))
-	thePool.mu.Lock()
 	rc = C.gb_chains_merged_marginals(thePool.h, &merged[0], nil)
-	thePool.mu.Unlock()
 	if rc != 0 {
 		return nil, lastErr("MergeChains")
 	}

@@ -57,6 +57,7 @@ _SIGS = {
     "gb_model_thresholds": (C.c_int, [_vp, C.c_int32, _i32p, C.POINTER(C.c_uint32)]),
     "gb_model_collapse": (C.c_int, [_vp, C.c_int32, C.c_uint64, _i32p, _f64p, C.POINTER(_vp)]),
     "gb_conditional": (C.c_int, [_vp, C.c_int, C.c_int32, _i32p, _i32p, _f64p]),
+    "gb_model_sample": (C.c_int, [_vp, C.c_int, C.c_int32, C.c_int, C.c_uint64, C.c_uint64, _i32p, _i32p]),
     "gb_chains_create": (C.c_int, [C.c_int32, C.POINTER(_vp), _i32p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.POINTER(_vp)]),
     "gb_chains_add_group": (C.c_int, [_vp, _vp, C.c_int32, C.c_uint64]),
     "gb_chains_destroy": (None, [_vp]),

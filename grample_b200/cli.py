@@ -242,11 +242,11 @@ def _sample(args, out, mon, start, dist=None, rank=0, world=1):
     out.write("Reading model from %s\n" % args.model)
     mod = core.Model.from_uai(args.model, use_evidence=args.evidence, device=args.device)
     if args.precision == "auto":
-        # all-table models (binary variables, <= 65536 neighbour configurations) and their single-collapsed variants run
-        # on the resident table kernel under hybrid mode; anything else takes the float32 log-sum-exp kernels
-        order, _ = mod.schedule()
-        all_tables = len(order) > 0 and bool(mod.hybrid_mask()[order].all())
-        args.precision = "hybrid" if all_tables and not args.rao_blackwell else "f32"
+        # ONE default for every host of the boundary (this CLI, the C++ mirror grample.hpp, the Go shim): GB_HYBRID =
+        # the reference's float64 arithmetic throughout — variables whose conditional can be tabulated are sampled from
+        # float64-derived thresholds, the rest by the float64 log-sum-exp kernels.  float32 is an explicit opt-in
+        # (--precision f32).  The Rao-Blackwell estimator accumulates log-sum-exp conditionals, hence GB_F64 with it.
+        args.precision = "f64" if args.rao_blackwell else "hybrid"
         out.write("Precision: %s\n" % args.precision)
     prec = {"f64": F64, "f32": F32, "table": TABLE, "hybrid": HYBRID}[args.precision]
     n, cards, fixed = mod.n_vars, mod.cards, mod.fixed

@@ -163,6 +163,19 @@ class Model:
         return [out[i, :cards[variables[i]]].copy() for i in range(n)]
 
 
+def _model_sample(self, state, step, var=-1, seed=1, precision=F64, exclude_collapsed=False):
+    """(*GibbsSimple).Sample / SampleVar on one caller-held state: updates `state` (int32 [n_vars]) in place and returns
+    the sampled variable's index."""
+    assert state.dtype == np.int32 and state.flags["C_CONTIGUOUS"]
+    v = C.c_int32()
+    check(lib().gb_model_sample(self.h, precision, int(var), int(exclude_collapsed), C.c_uint64(seed), C.c_uint64(step),
+                                _ptr(state, _i32p), C.byref(v)))
+    return v.value
+
+
+Model.sample = _model_sample
+
+
 class Chains:
     """All chains of one device, grouped by model (one group per collapsed variant)."""
 
@@ -261,8 +274,9 @@ class Chains:
     def merge_begin(self, out=None):
         """MergeChains off the sweep stream: snapshot now, reduce (NCCL when a communicator is attached) and copy to the
         host on a side stream while later sweeps run.  `out` must stay alive until merge_end()."""
-        self._pending = self._merge_buffers(out)
-        check(lib().gb_chains_merge_begin(self.h, _ptr(self._pending[0], _f64p), _ptr(self._pending[1], _i32p)))
+        bufs = self._merge_buffers(out)
+        check(lib().gb_chains_merge_begin(self.h, _ptr(bufs[0], _f64p), _ptr(bufs[1], _i32p)))
+        self._pending = bufs  # (only now: a refused call must not drop the buffers a pending merge still writes to)
 
     def merge_end(self):
         """-> (merged, collapsed flags, chains over all ranks, TotalSampleCount over all ranks)"""
@@ -420,8 +434,9 @@ class Fleet:
         return out, col
 
     def merge_begin(self, out=None):
-        self._pending = self.chains[0]._merge_buffers(out)
-        check(lib().gb_fleet_merge_begin(self.h, _ptr(self._pending[0], _f64p), _ptr(self._pending[1], _i32p)))
+        bufs = self.chains[0]._merge_buffers(out)
+        check(lib().gb_fleet_merge_begin(self.h, _ptr(bufs[0], _f64p), _ptr(bufs[1], _i32p)))
+        self._pending = bufs
 
     def merge_end(self):
         n, t = C.c_int64(), C.c_int64()

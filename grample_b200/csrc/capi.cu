@@ -1282,9 +1282,9 @@ int gb_model_collapse(const gb_model* src, int32_t var, uint64_t seed, int32_t* 
     GB_END
 }
 
-int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int32_t* states,
-                   const int32_t* vars, double* out) {
-    GB_TRY
+// K5 on validated inputs: floored un-normalised weights e[k] (gibbs-simple.go:171-258) of (state, variable) pairs
+static void conditional_impl(const gb_model* m, int precision, int32_t n_states, const int32_t* states, const int32_t* vars,
+                             double* out) {
     if (m->device < 0) throw gb::Err("gb_conditional needs a device-resident model (there is no CPU fallback)");
     require_device(m->device);
     const gb::HostModel& h = m->h;
@@ -1298,12 +1298,16 @@ int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int
             if (x < 0 || x >= h.card[u]) throw gb::Err("Value " + std::to_string(x) + " invalid for cardinality " + std::to_string(h.card[u]));
         }
     }
-    int32_t *d_states = nullptr, *d_vars = nullptr;
-    double* d_out = nullptr;
+    struct DevBuf {
+        void* p = nullptr;
+        ~DevBuf() { cudaFree(p); }
+    } b_states, b_vars, b_out;
     const size_t ns = (size_t)n_states;
-    CUDA_CHECK(cudaMalloc(&d_states, ns * h.n_vars * sizeof(int32_t)));
-    CUDA_CHECK(cudaMalloc(&d_vars, ns * sizeof(int32_t)));
-    CUDA_CHECK(cudaMalloc(&d_out, ns * gb::kProbeStride * sizeof(double)));
+    CUDA_CHECK(cudaMalloc(&b_states.p, ns * h.n_vars * sizeof(int32_t)));
+    CUDA_CHECK(cudaMalloc(&b_vars.p, ns * sizeof(int32_t)));
+    CUDA_CHECK(cudaMalloc(&b_out.p, ns * gb::kProbeStride * sizeof(double)));
+    int32_t *d_states = static_cast<int32_t*>(b_states.p), *d_vars = static_cast<int32_t*>(b_vars.p);
+    double* d_out = static_cast<double*>(b_out.p);
     CUDA_CHECK(cudaMemcpy(d_states, states, ns * h.n_vars * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d_vars, vars, ns * sizeof(int32_t), cudaMemcpyHostToDevice));
     const int blocks = (n_states + 127) / 128;
@@ -1311,7 +1315,48 @@ int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int
     else gb::k_conditional<double><<<blocks, 128>>>(m->dev, n_states, d_states, d_vars, d_out);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpy(out, d_out, ns * gb::kProbeStride * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_states); cudaFree(d_vars); cudaFree(d_out);
+}
+
+int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int32_t* states,
+                   const int32_t* vars, double* out) {
+    GB_TRY
+    conditional_impl(m, precision, n_states, states, vars, out);
+    GB_END
+}
+
+// (*GibbsSimple).Sample / SampleVar, (*GibbsCollapsed).Sample for ONE caller-held state (gibbs-simple.go:148-271,
+// gibbs-collapsed.go:317-334): variable choice on the host, conditional on the device (K5), inverse-CDF draw on the host
+int gb_model_sample(const gb_model* m, int precision, int32_t var, int exclude_collapsed, uint64_t seed, uint64_t step,
+                    int32_t* state_inout, int32_t* var_out) {
+    if (var_out) *var_out = -1;  // the reference returns index -1 on failure
+    GB_TRY
+    const gb::HostModel& h = m->h;
+    const gb::Philox4 r = gb::philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, gb::kTagScan, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if (var < 0) {  // UniformSampler.VarSample (sampler.go:135-174): uniform over FixedVal < 0 (and not Collapsed)
+        std::vector<int32_t> elig;
+        for (int v = 0; v < h.n_vars; v++)
+            if (h.fixed[v] < 0 && !(exclude_collapsed && h.collapsed[v])) elig.push_back(v);
+        if (elig.empty()) throw gb::Err("No Variables to select");
+        var = elig[(size_t)(((uint64_t)r.x * elig.size()) >> 32)];
+    }
+    if (var >= h.n_vars) throw gb::Err("Invalid variable index");
+    double e[gb::kProbeStride];
+    conditional_impl(m, precision, 1, state_inout, &var, e);
+    // UniformSampler.WeightedSample (sampler.go:107-123): re-sum, r = U * tot, first k with r <= w[k]
+    const int card = h.card[var];
+    double tot = 0.0;
+    for (int k = 0; k < card; k++) tot += e[k];
+    double u = gb::u53(r.z, r.w) * tot;
+    int sel = card - 1;
+    for (int k = 0; k < card; k++) {
+        if (u <= e[k]) {
+            sel = k;
+            break;
+        }
+        u -= e[k];
+    }
+    state_inout[var] = sel;
+    if (var_out) *var_out = var;
     GB_END
 }
 

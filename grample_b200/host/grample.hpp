@@ -47,7 +47,7 @@ inline void check(int rc, const char* what) {
 struct Options {
     int device = 0;
     int replicas = 1;              // device chains per reference Chain
-    int precision = GB_F64;        // GB_F64 follows the reference literally
+    int precision = GB_HYBRID;     // the one default of every host (CLI `auto`, Go shim): float64 reference arithmetic, tabulated where possible; GB_F64 = per-update log-sum-exp everywhere
     bool history = true;           // per-chain half-window histograms (needed by ChainConvergence)
 };
 inline Options& options() {

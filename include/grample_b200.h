@@ -130,6 +130,18 @@ int gb_model_collapse(const gb_model* src, int32_t var, uint64_t seed, int32_t* 
 int gb_conditional(const gb_model* m, int precision, int32_t n_states, const int32_t* states,
                    const int32_t* vars, double* out);
 
+/* (*GibbsSimple).Sample / SampleVar and (*GibbsCollapsed).Sample for ONE caller-held state — the single-step form of
+ * the FullSampler interface (sampler/sampler.go:16-22, gibbs-simple.go:148-271, gibbs-collapsed.go:317-334) that the
+ * reference's benchmarks drive (gibbs-simple_test.go:68-86).  var < 0: a variable drawn uniformly among those with
+ * FixedVal < 0 (and, with exclude_collapsed, not Collapsed; UniformSampler.VarSample, sampler.go:135-174), else that
+ * variable (SampleVar).  The conditional is evaluated on the device (K5, `precision` GB_F64 or GB_F32), the
+ * inverse-CDF draw (sampler.go:107-123) uses the Philox stream keyed by (seed, step): the caller passes a step
+ * counter it increments.  state_inout[n_vars] is updated in place like the reference's `s []int`; *var_out = the
+ * variable sampled (-1 on failure, as the reference returns).  One kernel launch and two small copies per step: an
+ * API-compatibility path, not a throughput path — chains advance through gb_chains_*. */
+int gb_model_sample(const gb_model* m, int precision, int32_t var, int exclude_collapsed, uint64_t seed, uint64_t step,
+                    int32_t* state_inout, int32_t* var_out);
+
 /* ------------------------------------------------------------------ chains
  * gb_chains_create replaces the chain-construction loop cmd/root.go:381-430 +
  * sampler.NewChain (sampler/chain.go:151-175) for ALL chains of one device at once:

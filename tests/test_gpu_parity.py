@@ -895,6 +895,42 @@ def test_async_merge_and_single_rank_communicator(res):
     assert np.allclose(legacy, later, rtol=1e-15)
 
 
+def test_single_step_sample(res):
+    """gb_model_sample = (*GibbsSimple).Sample / SampleVar on a caller-held state (gibbs-simple.go:148-271): the value is
+    the inverse-CDF draw (sampler.go:107-123) of the oracle's conditional with the documented Philox fields, the variable
+    choice is uniform over the eligible ones, errors follow the reference."""
+    dm, om = load_pair(res, "Pedigree_11.uai", True)
+    samp = oracle.Sampler(oracle.Generator(1), om, collapsed=True)
+    rng = np.random.default_rng(4)
+    st = random_states(rng, dm.cards, dm.fixed, 1)[0].copy()
+    free = [v for v in range(dm.n_vars) if dm.fixed[v] < 0]
+    seed, picks = 99, np.zeros(dm.n_vars, dtype=np.int64)
+    for step in range(300):
+        before = st.copy()
+        v = dm.sample(st, step, seed=seed)
+        words = oracle.philox([step, 0, 0, 4], [seed, 0])  # tag kTagScan = 4
+        assert v == free[(int(words[0]) * len(free)) >> 32]
+        picks[v] += 1
+        e = samp.conditional(v, before)
+        r = ((int(words[2]) << 32 | int(words[3])) >> 11) * 2.0 ** -53 * e.sum()
+        k = 0
+        while k < len(e) - 1 and not r <= e[k]:
+            r -= e[k]
+            k += 1
+        assert st[v] == k and np.array_equal(np.delete(st, v), np.delete(before, v))
+    assert (picks[dm.fixed >= 0] == 0).all()
+    v = dm.sample(st, 1000, var=free[3], seed=seed)  # SampleVar
+    assert v == free[3]
+    fixed_var = int(np.nonzero(dm.fixed >= 0)[0][0])
+    with pytest.raises(gb.GrampleError, match="FixedVal"):
+        dm.sample(st, 0, var=fixed_var)
+    # statistics on one.uai (gibbs-simple_test.go:13-38: both values appear; here also the 0.25 / 0.75 law)
+    one, _ = load_pair(res, "one.uai", False)
+    s1 = np.zeros(1, dtype=np.int32)
+    ones = sum(one.sample(s1, i, seed=5) == 0 and int(s1[0]) for i in range(1024))
+    assert 0.70 < ones / 1024 < 0.80
+
+
 def test_convergence_requires_history_and_chains(res):
     dm, _ = load_pair(res, "sample.uai", False)
     ch = gb.Chains(dm, 4, seed=1, history=False, device=0)
@@ -1095,13 +1131,13 @@ def test_cli_sample_adaptive(res, tmp_path):
 
 
 def test_cli_precision_auto(res):
-    """--precision auto: hybrid (exact float64 conditionals from threshold tables) when every sampled variable gets a
-    table, float32 log-sum-exp otherwise and with the Rao-Blackwell estimator"""
+    """--precision auto = the one default of every host of the boundary: hybrid (float64 reference arithmetic, threshold
+    tables where a variable qualifies, float64 log-sum-exp elsewhere); float64 with the Rao-Blackwell estimator"""
     import io
 
     from grample_b200 import cli
-    for argv, want in ((["-m", res("Grids_11.uai")], "hybrid"), (["-m", res("ObjectDetection_11.uai")], "f32"),
-                       (["-m", res("Grids_11.uai"), "--rao-blackwell"], "f32")):
+    for argv, want in ((["-m", res("Grids_11.uai")], "hybrid"), (["-m", res("ObjectDetection_11.uai")], "hybrid"),
+                       (["-m", res("Grids_11.uai"), "--rao-blackwell"], "f64")):
         args = cli.build_parser().parse_args(["sample"] + argv + ["-o", "-b", "200", "-w", "10", "-i", "20000", "--replicas", "8"])
         out = io.StringIO()
         final, _ = cli.sample(args, out)
