@@ -30,6 +30,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / warnings must not share stdout with the JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -52,7 +54,7 @@ def parse_args():
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
     ap.add_argument("--side", type=int, default=1024, help="torus side (variables = side^2)")
     ap.add_argument("--wmax", type=float, default=4.9)
-    ap.add_argument("--precision", default="table", choices=["table", "f32", "f64"],
+    ap.add_argument("--precision", default="table", choices=["bits", "table", "f32", "f64"],
                     help="table: float64 conditionals tabulated per neighbour configuration, integer sweep")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,15 +241,19 @@ def measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, 
         chains.merge_end()
     barrier()
     e0 = time.time()
+    marks = []
     chains.sweep(1, record=True)
     chains.merge_begin(bufs[0])
     for i in range(1, args.steps):
         chains.sweep(1, record=True)             # interval i is enqueued ...
         merged, _, n_all, samples_all = chains.merge_end()   # ... while interval i - 1's merged marginals arrive
+        marks.append(time.time())
         chains.merge_begin(bufs[i % 2])
     merged, _, n_all, samples_all = chains.merge_end()
+    marks.append(time.time())
     barrier()
     e_ms = (time.time() - e0) * 1e3
+    measure.interval_ms = [round((b - a) * 1e3, 3) for a, b in zip([e0] + marks[:-1], marks)]  # arrival times of the merged marginals
     if dist is not None:
         t = torch.tensor([e_ms], device=f"cuda:{dev}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,9 +296,10 @@ def run_native(args):
     dev = local_rank
     torch.cuda.set_device(dev)
 
-    prec = {"table": gb.TABLE, "f32": gb.F32, "f64": gb.F64}[args.precision]
-    kernel = {"table": "k_sweep_tab<64,4,false,3>", "f32": "k_sweep_colour<float,2,4>", "f64": "k_sweep_colour<double,2,4>"}[args.precision]
-    dtype = {"table": "u32", "f32": "f32", "f64": "f64"}[args.precision]
+    prec = {"bits": gb.TABLE_BITS, "table": gb.TABLE, "f32": gb.F32, "f64": gb.F64}[args.precision]
+    kernel = {"bits": "k_sweep_bits<2>", "table": "k_sweep_tab<64,4,false,3>", "f32": "k_sweep_colour<float,2,4>",
+              "f64": "k_sweep_colour<double,2,4>"}[args.precision]
+    dtype = {"bits": "u32", "table": "u32", "f32": "f32", "f64": "f64"}[args.precision]
     t_setup = time.time()
     arrays = gb.ising_torus(args.side, args.side, wmax=args.wmax)
     model = gb.Model.from_arrays(*arrays, device=dev)
@@ -310,6 +317,7 @@ def run_native(args):
     ms, launches, clocks, e_ms, merged = measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, dev)
     value = world * updates_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * updates_per_step * args.steps / (e_ms * 1e-3)
+    weak_intervals = measure.interval_ms
     score = gb.error_suite(model.cards, np.full(total_card, 0.5), merged)  # host scoring of the read-back (untimed sanity use)
 
     # ---------------- strong scaling (the SAME 65536 chains split over the N GPUs), N > 1 only
@@ -324,7 +332,7 @@ def run_native(args):
         s_updates = world * n_vars * per * args.steps
         strong = {"chains_total": per * world, "chains_per_gpu": per, "value": s_updates / (s_ms * 1e-3), "unit": UNIT,
                   "ms_per_step": s_ms / args.steps, "e2e": {"value": s_updates / (s_e_ms * 1e-3), "unit": UNIT, "ms_per_step": s_e_ms / args.steps,
-                                                             "d2h_bytes_per_step": int(total_card * 8 + 16)},
+                                                             "d2h_bytes_per_step": int(total_card * 8 + 16), "interval_ms": measure.interval_ms},
                   "gpu_launches": int(s_launches), "clocks": s_clocks,
                   "note": "efficiency = strong.value (or strong.e2e.value) / the N = 1 run's value (e2e.value): same total work"}
         chains = sch
@@ -391,7 +399,7 @@ def run_native(args):
                        "setup_seconds": round(setup_s, 2)},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": int(total_card * 8 + 16), "ms_per_step": e_ms / args.steps,
+                    "d2h_bytes_per_step": int(total_card * 8 + 16), "ms_per_step": e_ms / args.steps, "interval_ms": weak_intervals,
                     "path": "per step: gb_chains_sweep, gb_chains_merge_end (the previous step's merged marginals, pinned host "
                             "buffer), gb_chains_merge_begin; in-library NCCL sum of the uint64 counts when N > 1",
                     "note": "the interval loop of cmd/root.go has no per-interval host input: chain state is device-resident "

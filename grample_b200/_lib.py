@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgrample_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "grample_b200.h")
 
-F64, F32, TABLE, HYBRID = 0, 1, 2, 3
+F64, F32, TABLE, HYBRID, TABLE_BITS = 0, 1, 2, 3, 4
 MAX_ABS, MEAN_ABS, HELLINGER, JS = 0, 1, 2, 3
 CHAINS_HISTORY = 1
 CHAINS_PER_COLOUR = 2
@@ -54,6 +54,7 @@ _SIGS = {
     "gb_model_function_count": (C.c_int, [_vp, C.c_int32, _i32p]),
     "gb_model_schedule": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p]),
     "gb_model_table_mode": (C.c_int, [_vp, _i32p, _i64p]),
+    "gb_model_bits_mode": (C.c_int, [_vp, _i32p]),
     "gb_model_thresholds": (C.c_int, [_vp, C.c_int32, _i32p, C.POINTER(C.c_uint32)]),
     "gb_model_collapse": (C.c_int, [_vp, C.c_int32, C.c_uint64, _i32p, _f64p, C.POINTER(_vp)]),
     "gb_conditional": (C.c_int, [_vp, C.c_int, C.c_int32, _i32p, _i32p, _f64p]),

@@ -130,6 +130,12 @@ class Model:
         check(lib().gb_model_table_mode(self.h, C.byref(ok), C.byref(n)))
         return bool(ok.value), n.value
 
+    def bits_mode(self):
+        """whether precision=TABLE_BITS (bit-packed state, bit-sliced sweep) applies"""
+        ok = C.c_int32()
+        check(lib().gb_model_bits_mode(self.h, C.byref(ok)))
+        return bool(ok.value)
+
     def hybrid_mask(self):
         """int32 [n_vars]: 1 where precision=HYBRID samples the variable from a threshold table"""
         out = np.zeros(self.n_vars, dtype=np.int32)

@@ -15,6 +15,9 @@
 #include "comm.hpp"
 #include "host_model.hpp"
 #include "kernels.cuh"
+#if !defined(GB_PART) || GB_PART == 0 || GB_PART == 1
+#include "bits.cuh"
+#endif
 
 // Build partition (see __graft_entry__.build): the log-sum-exp sweep kernels are ~70 heavy template instantiations, so the
 // library is compiled as three translation units in parallel from this one source — GB_PART 1 = everything but the LSE
@@ -168,6 +171,10 @@ struct gb_model {
         thr_built = true;
     }
     // table mode proper: every sampled variable tabulated with <= 256 configurations, fixed-size records
+    void ensure_bits() {
+        if (!h.bits_ok) throw gb::Err("bit-sliced table mode does not apply to this model: " + h.bits_why);
+        ensure_tab();
+    }
     void ensure_tab() {
         std::lock_guard<std::recursive_mutex> lk(mu);
         if (!h.tab_ok) throw gb::Err("table mode does not apply to this model: " + h.tab_why);
@@ -204,6 +211,8 @@ struct Group {
     uint64_t scan_step = 0;     // next random-scan step index
     bool window_filled = false; // the group has been through an AdvanceChain round (its half-window histograms are valid)
     uint8_t* d_state = nullptr;
+    uint32_t* d_bits = nullptr;  // GB_TABLE_BITS: [n_vars][n_words] one bit per chain (d_state stays null)
+    int32_t n_words = 0;
     unsigned long long* d_counts = nullptr;
     uint16_t* d_hist = nullptr;
     gb::DevGroup dev{};
@@ -257,6 +266,9 @@ struct gb_chains {
     double* merge_out = nullptr;             // destination of the pending merge
     int32_t* merge_col_out = nullptr;
     int64_t global_chains = -1, global_samples = -1;  // tail of the last completed merge
+    // GB_TABLE_BITS: tile counters of the dynamically scheduled sweep launches (a ring, re-zeroed when it wraps)
+    unsigned int* d_tile_ring = nullptr;
+    uint32_t tile_slot = 0;
     // groups are independent between monitor intervals (like the reference's goroutine per chain,
     // chain.go:197-215): their launches fan out over side streams and join back on `stream`
     std::vector<cudaStream_t> side;
@@ -270,10 +282,12 @@ struct gb_chains {
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& g : groups) {
             cudaFree(g.d_state);
+            cudaFree(g.d_bits);
             cudaFree(g.d_counts);
             cudaFree(g.d_hist);
             if (g.owns_model) delete g.model;
         }
+        cudaFree(d_tile_ring);
         cudaFree(d_merge);
         cudaFree(d_wb);
         cudaFree(d_skip);
@@ -324,7 +338,11 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     if (model->device != c->device) throw gb::Err("model lives on a different device than the chains");
     if (n_chains < 1) throw gb::Err("a chain group needs at least 1 chain");
     if (first_chain % 8) throw gb::Err("first_chain_id must be a multiple of 8 (chains share Philox calls in blocks of 8)");
+    const bool bits = c->precision == GB_TABLE_BITS;
+    if (bits && first_chain % 32) throw gb::Err("first_chain_id must be a multiple of 32 under GB_TABLE_BITS (one state word holds 32 chains)");
+    if (bits && (c->flags & GB_CHAINS_HISTORY)) throw gb::Err("GB_TABLE_BITS keeps no per-chain histories (no GB_CHAINS_HISTORY): use GB_TABLE");
     if (c->precision == GB_TABLE) model->ensure_tab();
+    if (bits) model->ensure_bits();
     if (c->precision == GB_HYBRID) model->ensure_hybrid();
     if (!c->groups.empty() && (model->h.n_vars != c->base().n_vars || model->h.card != c->base().card))
         throw gb::Err("Cannot merge chain with different variables");
@@ -336,8 +354,10 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     g.n_pad = (n_chains + 7) / 8 * 8;
     g.first_chain = first_chain;
     const gb::HostModel& h = model->h;
+    g.n_words = (g.n_chains + 31) / 32;
     try {
-        CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
+        if (bits) CUDA_CHECK(cudaMalloc(&g.d_bits, (size_t)h.n_vars * g.n_words * sizeof(uint32_t)));
+        else CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
         CUDA_CHECK(cudaMalloc(&g.d_counts, (size_t)h.total_card * sizeof(unsigned long long)));
         CUDA_CHECK(cudaMemsetAsync(g.d_counts, 0, (size_t)h.total_card * sizeof(unsigned long long), c->stream));
         if (c->flags & GB_CHAINS_HISTORY) {
@@ -347,6 +367,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
         }
     } catch (...) {  // a failed allocation must not leak the ones before it
         cudaFree(g.d_state);
+        cudaFree(g.d_bits);
         cudaFree(g.d_counts);
         cudaFree(g.d_hist);
         throw;
@@ -360,8 +381,12 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     g.dev.seed_lo = (uint32_t)c->seed;
     g.dev.seed_hi = (uint32_t)(c->seed >> 32);
     g.dev.rb = (c->flags & GB_CHAINS_RAO_BLACKWELL) ? 1 : 0;
-    const int64_t items = (int64_t)h.n_vars * (g.n_pad / 4);
-    gb::k_init_state<<<grid_for(items, 256), 256, 0, c->stream>>>(model->dev, g.dev);
+    if (bits) {
+        gb::k_init_bits<<<grid_for((int64_t)h.n_vars * g.n_words, 256), 256, 0, c->stream>>>(model->dev, g.dev, g.d_bits, g.n_words);
+    } else {
+        const int64_t items = (int64_t)h.n_vars * (g.n_pad / 4);
+        gb::k_init_state<<<grid_for(items, 256), 256, 0, c->stream>>>(model->dev, g.dev);
+    }
     c->launches++;
     CUDA_CHECK(cudaGetLastError());
     c->groups.push_back(g);
@@ -424,6 +449,42 @@ void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist
     }
 }
 
+// GB_TABLE_BITS: one colour of one group on bit-packed state; W = state words per thread
+template <int W>
+void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
+    static int resident_dev[kMaxDevices] = {};  // per device: CTAs that fit at once (persistent CTAs, tiles handed out by an atomic counter)
+    int resident;
+    {
+        std::lock_guard<std::mutex> cfg_lock(g_cfg_mu);
+        int& r = resident_dev[c->device];
+        if (!r) {
+            int per_sm = 0, sms = 0;
+            CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_bits<W>, 256, 0));
+            r = std::max(1, per_sm * sms);
+        }
+        resident = r;
+    }
+    constexpr uint32_t kRing = 1024;
+    if (!c->d_tile_ring) CUDA_CHECK(cudaMalloc(&c->d_tile_ring, kRing * sizeof(unsigned int)));
+    const uint32_t slot = c->tile_slot++ % kRing;
+    if (slot == 0) CUDA_CHECK(cudaMemsetAsync(c->d_tile_ring, 0, kRing * sizeof(unsigned int), c->stream));  // earlier launches of this stream are done with it
+    const gb::HostModel& h = g.model->h;
+    const int64_t tiles = (int64_t)((g.n_words + 256 * W - 1) / (256 * W)) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
+    gb::k_sweep_bits<W><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
+                                                     record, c->d_tile_ring + slot);
+    c->launches++;
+}
+void launch_bits(gb_chains* c, Group& g, int col, int32_t n, int record) {
+    const char* env_w = std::getenv("GB_BITS_W");  // A/B and test knob
+    const int force_w = env_w ? std::atoi(env_w) : 0;
+    // two words per thread amortise the warp-uniform coefficient reads; one word keeps small populations spread over the SMs
+    const bool two = force_w ? force_w == 2 : g.n_words >= 2048;
+    if (two) launch_bits_w<2>(c, g, col, n, record);
+    else launch_bits_w<1>(c, g, col, n, record);
+}
+
 // one sweep of one group: one launch per colour
 void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
     const gb::HostModel& h = g.model->h;
@@ -434,6 +495,8 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         if (n == 0) continue;
         if (c->precision == GB_TABLE) {
             launch_tab(c, g, col, n, record, hist_half);
+        } else if (c->precision == GB_TABLE_BITS) {
+            launch_bits(c, g, col, n, record);
         } else if (c->precision == GB_F32) {
             gbh::lse_colour_f32(c, g, dv, n, record, hist_half);
         } else {
@@ -516,7 +579,7 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     static const int disabled = std::getenv("GB_NO_RESIDENT") ? 1 : 0;
     static const int no_ts = std::getenv("GB_NO_SMEM_TABLES") ? 1 : 0;  // A/B knob (function-local statics initialise thread-safely)
     ResidentPlan p;
-    if (disabled || (c->flags & GB_CHAINS_PER_COLOUR)) return p;
+    if (disabled || (c->flags & GB_CHAINS_PER_COLOUR) || c->precision == GB_TABLE_BITS) return p;
     const gb::HostModel& h = g.model->h;
     if (h.n_vars > 4096) return p;
     auto base = [&](int ch) { return (((size_t)h.n_vars * ch + 15) & ~(size_t)15) + (size_t)h.total_card * 4; };
@@ -1257,6 +1320,10 @@ int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out)
     if (n_thresholds_out) *n_thresholds_out = m->h.n_thresholds;
     GB_END
 }
+int gb_model_bits_mode(const gb_model* m, int32_t* ok_out) {
+    *ok_out = m->h.bits_ok ? 1 : 0;
+    return 0;
+}
 int gb_model_hybrid_mask(const gb_model* m, int32_t* mask_out) {
     GB_TRY
     const bool on = m->hybrid_tables();
@@ -1366,7 +1433,8 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
                      gb_chains** out) {
     GB_TRY
     if (n_groups < 1) throw gb::Err("at least one chain group is required");
-    if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE && precision != GB_HYBRID) throw gb::Err("unknown precision");
+    if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE && precision != GB_HYBRID && precision != GB_TABLE_BITS)
+        throw gb::Err("unknown precision");
     if ((flags & GB_CHAINS_RAO_BLACKWELL) && precision != GB_F64 && precision != GB_F32)
         throw gb::Err("GB_CHAINS_RAO_BLACKWELL needs precision GB_F64 or GB_F32 (the estimator accumulates the log-sum-exp conditionals)");
     require_device(device);
@@ -1438,6 +1506,7 @@ int gb_chains_scan(gb_chains* c, int64_t n_steps, int record) {
     GB_LOCK(c);
     if (n_steps < 0) throw gb::Err("Invalid step count");
     if (c->flags & GB_CHAINS_RAO_BLACKWELL) throw gb::Err("the random-scan parity mode records plain counts (no GB_CHAINS_RAO_BLACKWELL)");
+    if (c->precision == GB_TABLE_BITS) throw gb::Err("the random-scan parity mode needs byte state: not available under GB_TABLE_BITS");
     CUDA_CHECK(cudaSetDevice(c->device));
     for (auto& g : c->groups) {
         const gb::HostModel& h = g.model->h;
@@ -1721,6 +1790,14 @@ int gb_chains_get_state(gb_chains* c, int32_t group, int32_t* out) {
     CUDA_CHECK(cudaSetDevice(c->device));
     Group& g = c->groups[group];
     const int nv = g.model->h.n_vars;
+    if (g.d_bits) {
+        std::vector<uint32_t> wb((size_t)nv * g.n_words);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaMemcpy(wb.data(), g.d_bits, wb.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int ch = 0; ch < g.n_chains; ch++)
+            for (int v = 0; v < nv; v++) out[(size_t)ch * nv + v] = (int32_t)((wb[(size_t)v * g.n_words + (ch >> 5)] >> (ch & 31)) & 1u);
+        return 0;
+    }
     std::vector<uint8_t> st((size_t)nv * g.n_pad);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     CUDA_CHECK(cudaMemcpy(st.data(), g.d_state, st.size(), cudaMemcpyDeviceToHost));
@@ -1735,6 +1812,21 @@ int gb_chains_set_state(gb_chains* c, int32_t group, const int32_t* in) {
     CUDA_CHECK(cudaSetDevice(c->device));
     Group& g = c->groups[group];
     const gb::HostModel& h = g.model->h;
+    if (g.d_bits) {
+        std::vector<uint32_t> wb((size_t)h.n_vars * g.n_words, 0u);
+        for (int ch = 0; ch < g.n_chains; ch++)
+            for (int v = 0; v < h.n_vars; v++) {
+                const int x = in[(size_t)ch * h.n_vars + v];
+                if (x < 0 || x >= h.card[v]) throw gb::Err("Value " + std::to_string(x) + " invalid for cardinality " + std::to_string(h.card[v]));
+                if (h.fixed[v] >= 0 && x != h.fixed[v]) throw gb::Err("state contradicts FixedVal of variable " + std::to_string(v));
+                wb[(size_t)v * g.n_words + (ch >> 5)] |= (uint32_t)x << (ch & 31);
+            }
+        for (int v = 0; v < h.n_vars; v++)  // padding chains of the last word carry a fixed variable's value too
+            if (h.fixed[v] > 0 && (g.n_chains & 31)) wb[(size_t)v * g.n_words + g.n_words - 1] |= ~0u << (g.n_chains & 31);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaMemcpy(g.d_bits, wb.data(), wb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        return 0;
+    }
     std::vector<uint8_t> st((size_t)h.n_vars * g.n_pad, 0);
     for (int ch = 0; ch < g.n_chains; ch++)
         for (int v = 0; v < h.n_vars; v++) {

@@ -60,6 +60,8 @@ struct HostModel {
     // ---- tabulated-conditional fast path (binary sampled variables, <= 256 neighbour configurations)
     bool tab_ok = false, tab_all = false;
     std::string tab_why;                           // why the fast path does not apply
+    bool bits_ok = false;                          // GB_TABLE_BITS applies: tab_ok and every sampled variable has <= 4 free neighbours, all binary
+    std::string bits_why;
     std::vector<int32_t> tp_off, tprog;            // per var: [n_nbr, thr_off, (nbr_var, stride) * n_nbr]
     std::vector<int32_t> trec;                     // per sweep position: kTabRec words (see kernels.cuh)
     int64_t n_thresholds = 0;
@@ -197,6 +199,21 @@ struct HostModel {
                 r[4 + i] = i < tp[0] ? tp[2 + 2 * i] : v;
                 r[12 + i] = i < tp[0] ? tp[3 + 2 * i] : 0;
             }
+        }
+        // bit-sliced variant: the configuration index must be the neighbours' bits themselves (strides 1, 2, 4, 8)
+        bits_ok = tab_ok;
+        bits_why = tab_why;
+        for (size_t j = 0; j < order.size() && bits_ok; j++) {
+            const int32_t* r = trec.data() + j * 20;
+            if (r[2] > 4) {
+                bits_ok = false;
+                bits_why = "variable " + std::to_string(r[0]) + " has more than 4 free neighbours";
+            }
+            for (int i = 0; i < r[2] && bits_ok; i++)
+                if (card[r[4 + i]] != 2 || r[12 + i] != (1 << i)) {
+                    bits_ok = false;
+                    bits_why = "variable " + std::to_string(r[0]) + " has a non-binary neighbour";
+                }
         }
     }
 

@@ -10,6 +10,11 @@
 //                   (word[i >> 1] >> 16*(i & 1)) & 0xffff of each call; the 32-bit draw is
 //                   word32 = (hi16 << 16) | lo16, U = word32 * 2^-32.  The table-mode sweep only
 //                   evaluates the Lo call when hi16 alone does not decide the comparison.
+//   tags kTagPlaneA / kTagPlaneB / kTagTie24 (bit-sliced table sweep, bits.cuh): chain_block = chain >> 5 (one 32-chain
+//                   state word), p = chain & 31.  The 32-bit draw of chain p is u = hi8 << 24 | lo24 with
+//                   bit 7..4 of hi8 = bit p of words x, y, z, w of the PlaneA call, bit 3..0 = bit p of the PlaneB
+//                   call's words, lo24 = word (p & 3) of the call with tag kTagTie24 | (p >> 2) << 8, shifted right by 8
+//                   (only evaluated when hi8 equals the threshold's top byte).
 //   tag kTagDraw53: chain_block = chain >> 1, words (0,1) -> chain 2b, (2,3) -> chain 2b+1,
 //                   x = ((w_a << 32) | w_b) >> 11, U = x * 2^-53   (same range as Go's Float64)
 //   tag kTagInit  : chain_block = chain >> 2, value = (word * card) >> 32
@@ -19,7 +24,8 @@
 
 namespace gb {
 
-enum : uint32_t { kTagDraw24 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagCollapse = 5, kTagDraw16Hi = 6, kTagDraw16Lo = 7 };
+enum : uint32_t { kTagDraw24 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagCollapse = 5, kTagDraw16Hi = 6, kTagDraw16Lo = 7,
+                  kTagPlaneA = 8, kTagPlaneB = 9, kTagTie24 = 10 };
 
 struct Philox4 {
     uint32_t x, y, z, w;

@@ -58,7 +58,13 @@ enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 }
  *            configuration, 32-bit draws), every other variable by the GB_F64 path (53-bit draws) —
  *            reference float64 arithmetic throughout, for models GB_TABLE rejects (collapsed variants
  *            with wide blankets, mixed cardinalities).  Models with a cardinality above 4 run as GB_F64. */
-enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2, GB_HYBRID = 3 };
+/*   GB_TABLE_BITS the arithmetic and the law of GB_TABLE (float64 conditional per configuration, 32-bit thresholds,
+ *            32-bit draws) on chain state packed one bit per chain, updated 32 chains at a time with bit-sliced
+ *            logic (csrc/bits.cuh).  Applies when every sampled variable is binary with at most 4 free neighbours,
+ *            all binary (gb_model_bits_mode) — the Ising / Grids problems; no per-chain histories (no
+ *            GB_CHAINS_HISTORY), chain shards start on multiples of 32.  Its Philox stream is organised in bit planes,
+ *            so trajectories differ from GB_TABLE's for the same seed; both are bit-checked against the oracle. */
+enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2, GB_HYBRID = 3, GB_TABLE_BITS = 4 };
 /* gb_chains_create flags */
 #define GB_CHAINS_HISTORY 1u /* keep per-chain half-window histograms (needed by gb_chains_convergence*) */
 #define GB_CHAINS_PER_COLOUR 2u /* always launch one kernel per colour (disables the shared-memory-resident multi-sweep kernels small models use; same results) */
@@ -109,6 +115,8 @@ int gb_model_schedule(const gb_model* m, int32_t* n_order, int32_t* n_colours, i
 /* hybrid mode: mask_out[n_vars] = 1 where the variable is sampled from a threshold table under GB_HYBRID */
 int gb_model_hybrid_mask(const gb_model* m, int32_t* mask_out);
 int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out);
+/* whether GB_TABLE_BITS applies to this model */
+int gb_model_bits_mode(const gb_model* m, int32_t* ok_out);
 /* the tabulated thresholds of one sampled variable (builds the tables on first use): value 0 is
  * drawn iff the 32-bit draw <= threshold[configuration]; configuration = sum(state[nbr_i] * stride_i)
  * over the variable's free neighbours in ascending id order.  Pass out = NULL to query n. */

@@ -20,7 +20,9 @@
 namespace oracle {
 
 // Stream tags — MUST match grample_b200/csrc/philox.cuh
-enum : uint32_t { kTagDraw24 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagDraw16Hi = 6, kTagDraw16Lo = 7 };
+enum : uint32_t { kTagDraw24 = 1, kTagDraw53 = 2, kTagInit = 3, kTagScan = 4, kTagDraw16Hi = 6, kTagDraw16Lo = 7,
+                  kTagPlaneA = 8, kTagPlaneB = 9, kTagTie24 = 10 };
+constexpr int kBitsPlanes = 33;  // `bits` value selecting the 32-bit draw of the bit-sliced table sweep (GB_TABLE_BITS)
 
 inline double philox_uniform(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t var, int bits) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -31,6 +33,23 @@ inline double philox_uniform(uint64_t seed, uint32_t chain, uint32_t sweep, uint
         int a = 2 * (int)(chain & 1);
         uint64_t x = (((uint64_t)out[a] << 32) | out[a + 1]) >> 11;
         return (double)x * (1.0 / 9007199254740992.0);
+    }
+    if (bits == kBitsPlanes) {
+        // GB_TABLE_BITS: the draws of the 32 chains of one state word are bit-sliced over Philox output words
+        // (philox.cuh): bit b of the top byte = bit p of plane word b; the low 24 bits come from a call of their own
+        const uint32_t w = chain >> 5, p = chain & 31;
+        uint32_t a[4], b[4], t[4];
+        uint32_t ca[4] = {var, sweep, w, kTagPlaneA}, cb[4] = {var, sweep, w, kTagPlaneB}, ct[4] = {var, sweep, w, kTagTie24 | ((p >> 2) << 8)};
+        Philox4x32::gen(ca, key, a);
+        Philox4x32::gen(cb, key, b);
+        Philox4x32::gen(ct, key, t);
+        uint32_t hi8 = 0;
+        for (int i = 0; i < 4; i++) {
+            hi8 |= ((a[i] >> p) & 1u) << (7 - i);
+            hi8 |= ((b[i] >> p) & 1u) << (3 - i);
+        }
+        const uint32_t word = (hi8 << 24) | (t[p & 3] >> 8);
+        return (double)word * (1.0 / 4294967296.0);
     }
     // 32-bit draw of the table-mode sweep: hi and lo halves come from two calls shared by 8 chains
     uint32_t hi[4], lo[4];

@@ -336,6 +336,95 @@ def test_table_sweep_bitexact_wide_blankets(res, name, evid, per_colour):
     assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
 
 
+# ------------------------------------------------------------------ bit-sliced table mode (GB_TABLE_BITS, csrc/bits.cuh)
+def bits_case(which, res):
+    if which == "Grids_11":
+        return load_pair(res, "Grids_11.uai", False)
+    if which == "ising_evidence":  # evidence folds into the tables and leaves variables with 1..3 free neighbours
+        arrays = list(gb.ising_torus(6, 8, wmax=4.9, seed=5))
+        arrays[1] = arrays[1].copy()
+        arrays[1][[3, 17, 40, 41]] = [1, 0, 1, 1]
+        return gb.Model.from_arrays(*arrays, device=0), oracle.Model.create(*arrays)
+    arrays = gb.ising_torus(32, 48, wmax=0.5, seed=11)  # several tiles per colour, weak couplings (both values common)
+    return gb.Model.from_arrays(*arrays, device=0), oracle.Model.create(*arrays)
+
+
+@pytest.mark.parametrize("words", ["1", "2"], ids=["W1", "W2"])
+@pytest.mark.parametrize("which,n_chains,first,n_sweeps", [
+    ("Grids_11", 13, 32, 6), ("Grids_11", 96, 0, 5), ("Grids_11", 2100, 64, 3), ("ising_evidence", 75, 0, 7),
+    ("ising_32x48", 40, 0, 2)])
+def test_bits_sweep_bitexact(res, monkeypatch, which, n_chains, first, n_sweeps, words):
+    """GB_TABLE_BITS against the oracle replaying its bit-plane Philox stream (oracle/sweep.hpp, bits = 33) with the
+    reference's float64 arithmetic: identical states and counts, ragged chain counts, both words-per-thread variants.
+    The initial state equals GB_TABLE's (same init stream)."""
+    monkeypatch.setenv("GB_BITS_W", words)
+    dm, om = bits_case(which, res)
+    assert dm.bits_mode()
+    order, _ = dm.schedule()
+    seed = 4242
+    ch = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.TABLE_BITS, device=0)
+    st0 = ch.get_state(0, n_chains)
+    ref = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.TABLE, device=0)
+    assert np.array_equal(st0, ref.get_state(0, n_chains))
+    ch.burnin(1)
+    ch.sweep(n_sweeps)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, _ = samp.sweep_run(order, seed, first, st0, 0, 1, bits=33, record=False)
+    ost, ocounts = samp.sweep_run(order, seed, first, ost, 1, n_sweeps, bits=33, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+    assert ch.total_samples == n_sweeps * len(order) * n_chains
+    merged, _ = ch.merged_marginals()
+    prior = np.concatenate([np.full(c, n_chains / c) for c in dm.cards])
+    assert np.array_equal(merged, ocounts + prior)
+
+
+def test_bits_tie_path_and_set_state(res):
+    """ties of the 8-bit first stage (probability 2^-8 per update) are resolved with the 24 remaining bits: over 4096
+    chains x 100 variables x 6 sweeps ~ 9600 of them occur, and the trajectory still equals the oracle's full 32-bit
+    comparison; set_state round-trips through the bit-packed layout."""
+    dm, om = load_pair(res, "Grids_11.uai", False)
+    order, _ = dm.schedule()
+    n_chains, seed = 4096, 7
+    ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.TABLE_BITS, device=0)
+    rng = np.random.default_rng(1)
+    st0 = rng.integers(0, 2, size=(n_chains, dm.n_vars)).astype(np.int32)
+    ch.set_state(0, st0)
+    assert np.array_equal(ch.get_state(0, n_chains), st0)
+    ch.sweep(6)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    ost, ocounts = samp.sweep_run(order, seed, 0, st0, 0, 6, bits=33, record=True)
+    assert np.array_equal(ost, ch.get_state(0, n_chains))
+    assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
+
+
+def test_bits_mode_rejections_and_statistics(res):
+    dm, _ = load_pair(res, "Promedus_11.uai", True)
+    assert not dm.bits_mode()
+    with pytest.raises(gb.GrampleError, match="bit-sliced table mode does not apply"):
+        gb.Chains(dm, 32, precision=gb.TABLE_BITS, device=0)
+    g, _ = load_pair(res, "Grids_11.uai", False)
+    with pytest.raises(gb.GrampleError, match="multiple of 32"):
+        gb.Chains(g, 32, first_chain_id=8, precision=gb.TABLE_BITS, device=0)
+    with pytest.raises(gb.GrampleError, match="no per-chain histories"):
+        gb.Chains(g, 32, precision=gb.TABLE_BITS, history=True, device=0)
+    ch = gb.Chains(g, 64, precision=gb.TABLE_BITS, device=0)
+    with pytest.raises(gb.GrampleError, match="random-scan"):
+        ch.scan(10)
+    # same law as GB_TABLE and GB_F64: marginals of a weakly coupled torus agree statistically
+    arrays = gb.ising_torus(8, 8, wmax=0.3, seed=3)
+    m = gb.Model.from_arrays(*arrays, device=0)
+    est = {}
+    for prec in (gb.TABLE_BITS, gb.TABLE, gb.F64):
+        c = gb.Chains(m, 2048, seed=12, precision=prec, device=0)
+        c.burnin(50)
+        c.sweep(100)
+        mg, _ = c.merged_marginals()
+        est[prec] = (mg.reshape(-1, 2) / mg.reshape(-1, 2).sum(1, keepdims=True))[:, 0]
+    assert np.abs(est[gb.TABLE_BITS] - est[gb.TABLE]).max() < 0.01
+    assert np.abs(est[gb.TABLE_BITS] - est[gb.F64]).max() < 0.01
+
+
 def test_resident_launch_chunking_keeps_the_window_schedule(res, monkeypatch):
     """a round split over several resident launches (32-bit shared counters bound the sweeps per launch)
     gives the same states, counts and half-window histograms as one launch"""
