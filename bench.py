@@ -4,10 +4,13 @@
 Workload (config.workload): BASELINE.json configs[4] — synthetic 1024x1024 binary Ising torus
 (1 M variables, 3 M factors), 2-colour sweep, 65536 chains per GPU (64 GiB of uint8 state per
 GPU, so inputs are far larger than the 126 MB L2 and no flush is needed between timed steps).
-Default arithmetic (`--precision table`, dtype "u32"): the reference's float64 conditional is
+Default arithmetic (`--precision bits`, dtype "u32"): the reference's float64 conditional is
 evaluated once per (variable, neighbour configuration) and stored as a 32-bit inverse-CDF
-threshold; the sweep itself is integer work with 32-bit Philox draws.  `--precision f32|f64`
-run the per-update log-sum-exp kernels instead (also reported under `secondary.lse` at N = 1).
+threshold; the sweep itself is integer work with 32-bit Philox draws on chain state packed one
+bit per chain (8 GiB per GPU), 32 chains per machine word, bit-sliced (csrc/bits.cuh).
+`--precision table` is the same arithmetic on uint8 state (64 GiB per GPU; round 1's kernel,
+reported under `secondary.table_u8` at N = 1); `--precision f32|f64` run the per-update
+log-sum-exp kernels (reported under `secondary.lse` at N = 1).
 One "step" = one systematic sweep of every chain (n_vars x chains recorded single-variable
 updates).  Chains shard across GPUs with no data-path collective.  `value` is the weak-scaling
 figure (fixed 65536 chains per GPU); at N > 1 the `strong` block adds SURVEY 8d's split of the
@@ -42,6 +45,7 @@ METRIC = "variable_updates_per_sec"
 UNIT = "updates/s"
 GATHER_BYTES_PER_UPDATE = 5.0  # 4 distinct neighbours read + 1 state byte written (uint8 state)
 COMPULSORY_BYTES_PER_UPDATE = 2.0  # each state byte read once and written once per sweep (perfect neighbour reuse)
+STATE_BYTES = {"bits": 0.125, "table": 1.0, "f32": 1.0, "f64": 1.0}  # bytes of chain state per (variable, chain)
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -54,7 +58,7 @@ def parse_args():
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
     ap.add_argument("--side", type=int, default=1024, help="torus side (variables = side^2)")
     ap.add_argument("--wmax", type=float, default=4.9)
-    ap.add_argument("--precision", default="table", choices=["bits", "table", "f32", "f64"],
+    ap.add_argument("--precision", default="bits", choices=["bits", "table", "f32", "f64"],
                     help="table: float64 conditionals tabulated per neighbour configuration, integer sweep")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -262,6 +266,20 @@ def measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, 
     return ms, launches, clocks, e_ms, merged
 
 
+def other_rate(gb, model, args, dev, n_vars, peak, prec, kernel, steps):
+    """another kernel on the same workload (uint8 state, SURVEY 8d's 5 B per update yardstick)"""
+    try:
+        ch = gb.Chains(model, args.chains, seed=20260101, precision=prec, device=dev)
+        ch.sweep(1, record=True)
+        ms = ch.sweep_timed(steps, record=True)
+        v = n_vars * args.chains * steps / (ms * 1e-3)
+        del ch
+        return {"kernel": kernel, "value": v, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+                "roofline_frac_at_5B": GATHER_BYTES_PER_UPDATE * v / 1e9 / peak}
+    except Exception as e:  # never lose the headline line over a secondary number
+        return {"error": str(e)[:200]}
+
+
 def lse_rates(gb, model, args, dev, n_vars, peak):
     """The general per-update log-sum-exp path (`k_sweep_colour<Real,2,4>`) on the SAME workload: everything table
     mode rejects lands on these kernels, so the bench line carries them next to the headline (N = 1 only)."""
@@ -341,28 +359,33 @@ def run_native(args):
     peak, peak_src = hbm_peak()
     launch_ms = ms / (args.steps * n_colours)
     updates_per_launch = updates_per_step / n_colours
-    achieved = GATHER_BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "issue",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    sb = STATE_BYTES[args.precision]
+    gather, compulsory = GATHER_BYTES_PER_UPDATE * sb, COMPULSORY_BYTES_PER_UPDATE * sb
+    rate = updates_per_launch / (launch_ms * 1e-3)  # updates per second of one launch on one GPU
+    achieved = gather * rate / 1e9
+    roofline = {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": kernel,
-                "algorithmic_bytes_per_update": GATHER_BYTES_PER_UPDATE, "updates_per_launch": updates_per_launch,
-                "launch_ms": launch_ms,
-                "frac_of_compulsory_ceiling": COMPULSORY_BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9 / peak,
-                "compulsory_bytes_per_update": COMPULSORY_BYTES_PER_UPDATE,
-                "bound_note": "achieved / peak / frac are SURVEY 8d's gather-byte yardstick (5 B per update) over the measured HBM copy "
-                              "bandwidth; frac_of_compulsory_ceiling is the same rate against the 2 B per update a perfect-reuse "
-                              "uint8 sweep must move.  ncu (profiles/) shows the kernel bound by instruction issue on the ALU / FMA "
-                              "pipes, not by DRAM: see `issue`"}
-    # DRAM traffic and issue figures of the dominant kernel from the committed ncu --set full capture
+                "algorithmic_bytes_per_update": gather, "updates_per_launch": updates_per_launch, "launch_ms": launch_ms,
+                "compulsory_bytes_per_update": compulsory, "frac_of_compulsory_ceiling": compulsory * rate / 1e9 / peak,
+                "frac_at_uint8_5B_yardstick": GATHER_BYTES_PER_UPDATE * rate / 1e9 / peak,
+                "bound_note": "achieved / peak / frac: SURVEY 8d's gather bytes (4 neighbour reads + 1 write of %g B of state each) over the measured "
+                              "HBM copy bandwidth; frac_at_uint8_5B_yardstick is the same rate on round 1's uint8 yardstick (5 B per update).  "
+                              "ncu (profiles/) shows the kernel bound by instruction issue, not DRAM: `issue` holds the fraction of the "
+                              "issue-slot ceiling (1 warp instruction per cycle per SM sub-partition)" % sb}
+    # DRAM traffic and instruction counts of the dominant kernel from the committed ncu --set full capture
     # (profiles/traffic.json: per update at the capture's chain count, scaled to this launch's update count)
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr) and args.precision == "table":
+    if os.path.exists(tr):
         try:
-            t = json.load(open(tr))
-            roofline["traffic"] = t["dram_bytes_per_update"] * updates_per_launch
-            roofline["traffic_source"] = t["source"]
-            if "issue" in t:
-                roofline["issue"] = t["issue"]
+            t = json.load(open(tr)).get(args.precision)
+            if t:
+                roofline["traffic"] = t["dram_bytes_per_update"] * updates_per_launch
+                roofline["traffic_source"] = t["source"]
+                sm_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
+                issue_peak = 148 * 4 * sm_hz  # warp instructions per second: 148 SMs x 4 sub-partitions x 1 per cycle
+                issued = t["lane_instructions_per_update"] / 32.0 * rate
+                roofline["issue"] = {"achieved": issued / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s", "frac": issued / issue_peak,
+                                     "lane_instructions_per_update": t["lane_instructions_per_update"], "ncu": t.get("ncu")}
         except Exception:
             pass
 
@@ -377,7 +400,10 @@ def run_native(args):
     secondary = None
     if world == 1 and not args.no_secondary:
         del chains
-        secondary = {"lse": lse_rates(gb, model, args, dev, n_vars, peak)} if args.precision == "table" else {}
+        secondary = {}
+        if args.precision == "bits":
+            secondary["table_u8"] = other_rate(gb, model, args, dev, n_vars, peak, gb.TABLE, "k_sweep_tab<64,4,false,3>", 3)
+            secondary["lse"] = lse_rates(gb, model, args, dev, n_vars, peak)
         secondary.update(small_model_rates(gb, dev))
         secondary["samples_to_mean_hellinger_below_0.01"] = samples_to_hellinger(gb, dev)
 
@@ -393,8 +419,9 @@ def run_native(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic",
             "config": {"mode": args.precision, "workload": f"ising_torus_{args.side}x{args.side}", "variables": n_vars, "factors": 3 * n_vars,
-                       "chains_per_gpu": args.chains, "colours": n_colours, "wmax": args.wmax, "state": "uint8 [var][chain]",
-                       "l2_policy": "inputs (state %.1f GiB per GPU) larger than L2, no flush" % (n_vars * args.chains / 2**30),
+                       "chains_per_gpu": args.chains, "colours": n_colours, "wmax": args.wmax,
+                       "state": "1 bit per chain, uint32 [var][chain / 32]" if args.precision == "bits" else "uint8 [var][chain]",
+                       "l2_policy": "inputs (state %.1f GiB per GPU) larger than L2, no flush" % (n_vars * args.chains * STATE_BYTES[args.precision] / 2**30),
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
                        "setup_seconds": round(setup_s, 2)},
             "clocks": clocks, "gpu_launches": int(launches),

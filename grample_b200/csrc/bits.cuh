@@ -33,7 +33,7 @@
 namespace gb {
 
 constexpr int kBitsVB = 32;     // sweep positions per tile (half of a locality-ordered 64-position patch)
-constexpr int kBitsQueue = 2048;  // deferred ties per tile (expected ~ W * 256 * kBitsVB / 8.5; overflow resolves inline)
+constexpr int kBitsQueue = 3072;  // deferred ties per tile (expected W * 256 * kBitsVB * 0.118 = 1930 for W = 2, sd 41; overflow resolves inline)
 constexpr int kBitsRec = 8;     // {v, card_off, thr_off, cfg mask, nbr[4]}
 
 // initial state, identical to k_init_state's values (Philox kTagInit: chain >> 2 per call, umulhi(word, 2))
@@ -91,6 +91,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
     constexpr int VB = kBitsVB;
     __shared__ __align__(16) int2 s_coef[VB * 8 * 8];   // [position][plane 7..0][pair k]: {a_k, b_k}
     __shared__ __align__(16) int32_t s_rec[VB * kBitsRec];
+    __shared__ __align__(16) const uint32_t* s_row[VB * 4];         // state rows of the 4 neighbours of every position
     __shared__ uint8_t s_t8[VB * 16];                    // top byte of the 16 thresholds of every position
     __shared__ unsigned int s_cnt[VB];                   // ones per position over the tile's chains
     __shared__ uint2 s_q[kBitsQueue];                    // deferred ties: {position << 16 | word slot, eq}
@@ -126,6 +127,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         if (tid < VB) s_cnt[tid] = 0;
         if (tid == 0) s_qn = 0;
         __syncthreads();
+        if (tid < nv * 4) s_row[tid] = bits + (size_t)s_rec[(tid >> 2) * kBitsRec + 4 + (tid & 3)] * n_words;
         for (int i = tid; i < nv * 16; i += 256) {
             const int j = i >> 4, c = i & 15;
             s_t8[i] = (uint8_t)(__ldg(t.thr + s_rec[j * kBitsRec + 2] + (c & s_rec[j * kBitsRec + 3])) >> 24);
@@ -151,6 +153,24 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         }
         const bool any_word = chunk * chunk_words + (tid & ~31) < n_words;  // the warp owns at least one real word
         if (any_word) {
+            // neighbour words of the NEXT position are in flight while this one computes (rows of the other colour:
+            // read-only for the whole launch)
+            uint32_t nx[W][4];
+            auto load_nbrs = [&](const int j) {
+                const uint4 lo = *reinterpret_cast<const uint4*>(&s_row[j * 4]), hi = *reinterpret_cast<const uint4*>(&s_row[j * 4 + 2]);
+                const uint32_t* r0 = reinterpret_cast<const uint32_t*>((uint64_t)lo.x | (uint64_t)lo.y << 32);
+                const uint32_t* r1 = reinterpret_cast<const uint32_t*>((uint64_t)lo.z | (uint64_t)lo.w << 32);
+                const uint32_t* r2 = reinterpret_cast<const uint32_t*>((uint64_t)hi.x | (uint64_t)hi.y << 32);
+                const uint32_t* r3 = reinterpret_cast<const uint32_t*>((uint64_t)hi.z | (uint64_t)hi.w << 32);
+#pragma unroll
+                for (int u = 0; u < W; u++) {
+                    nx[u][0] = __ldg(r0 + wi[u]);
+                    nx[u][1] = __ldg(r1 + wi[u]);
+                    nx[u][2] = __ldg(r2 + wi[u]);
+                    nx[u][3] = __ldg(r3 + wi[u]);
+                }
+            };
+            load_nbrs(0);
             for (int jg = 0; jg < nv; jg += 2) {
                 uint32_t acc = 0;  // ones of positions jg (low half) and jg + 1 (high half) over this thread's chains
 #pragma unroll
@@ -158,17 +178,16 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                     const int j = jg + h;
                     if (j < nv) {
                         const int4 ra = *reinterpret_cast<const int4*>(&s_rec[j * kBitsRec]);      // v, card_off, thr_off, cfg mask
-                        const int4 rn = *reinterpret_cast<const int4*>(&s_rec[j * kBitsRec + 4]);  // neighbours
                         uint32_t n[W][4], gt[W], eq[W];
 #pragma unroll
                         for (int u = 0; u < W; u++) {
-                            n[u][0] = __ldg(bits + (size_t)rn.x * n_words + wi[u]);
-                            n[u][1] = __ldg(bits + (size_t)rn.y * n_words + wi[u]);
-                            n[u][2] = __ldg(bits + (size_t)rn.z * n_words + wi[u]);
-                            n[u][3] = __ldg(bits + (size_t)rn.w * n_words + wi[u]);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) n[u][i] = nx[u][i];
                             gt[u] = 0u;
                             eq[u] = 0xffffffffu;
                         }
+                        load_nbrs(min(j + 1, nv - 1));
+                        uint32_t* const own = bits + (size_t)ra.x * n_words;
 #pragma unroll
                         for (int half = 0; half < 2; half++) {
                             uint32_t d[W][4];
@@ -199,7 +218,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                         }
 #pragma unroll
                         for (int u = 0; u < W; u++) {
-                            if (valid[u]) bits[(size_t)ra.x * n_words + wi[u]] = gt[u];
+                            if (valid[u]) own[wi[u]] = gt[u];
                             acc += (uint32_t)__popc(gt[u] & valid[u]) << (16 * h);
                             if (eq[u] & valid[u]) {  // undecided after 8 planes (2^-8 per chain): resolve after the tile
                                 const unsigned slot = atomicAdd(&s_qn, 1u);
@@ -209,7 +228,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                                     const uint32_t add = bits_resolve(t, &s_rec[j * kBitsRec], bits, n_words, wi[u], gw0 + (uint32_t)wi[u], sweep,
                                                                       seed_lo, seed_hi, eq[u] & valid[u]);
                                     if (add) {
-                                        bits[(size_t)ra.x * n_words + wi[u]] = gt[u] | add;
+                                        own[wi[u]] = gt[u] | add;
                                         acc += (uint32_t)__popc(add) << (16 * h);
                                     }
                                 }
