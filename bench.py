@@ -33,7 +33,17 @@ import sys
 import threading
 import time
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / warnings must not share stdout with the JSON line
+# stdout carries exactly ONE line, the JSON result.  Native libraries write there too (NCCL prints its version banner on
+# the first communicator of a process), so file descriptor 1 points at stderr for the whole run and the JSON line goes
+# to a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -201,7 +211,7 @@ def run_reference(args):
             "config": {"workload": f"ising_torus_{args.side}x{args.side}", "chains": threads, "schedule": "random scan"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, dev):
@@ -245,16 +255,19 @@ def measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, 
         chains.merge_end()
     barrier()
     e0 = time.time()
-    marks = []
+    marks, stages = [], []
     chains.sweep(1, record=True)
     chains.merge_begin(bufs[0])
     for i in range(1, args.steps):
         chains.sweep(1, record=True)             # interval i is enqueued ...
         merged, _, n_all, samples_all = chains.merge_end()   # ... while interval i - 1's merged marginals arrive
         marks.append(time.time())
+        stages.append(chains.merge_timing())
         chains.merge_begin(bufs[i % 2])
     merged, _, n_all, samples_all = chains.merge_end()
     marks.append(time.time())
+    stages.append(chains.merge_timing())
+    measure.merge_stage_ms = stages  # per interval: [count sums, NCCL sum incl. waiting for the slowest rank, conversion, D2H]
     barrier()
     e_ms = (time.time() - e0) * 1e3
     measure.interval_ms = [round((b - a) * 1e3, 3) for a, b in zip([e0] + marks[:-1], marks)]  # arrival times of the merged marginals
@@ -335,7 +348,7 @@ def run_native(args):
     ms, launches, clocks, e_ms, merged = measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, dev)
     value = world * updates_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * updates_per_step * args.steps / (e_ms * 1e-3)
-    weak_intervals = measure.interval_ms
+    weak_intervals, weak_stages = measure.interval_ms, measure.merge_stage_ms
     score = gb.error_suite(model.cards, np.full(total_card, 0.5), merged)  # host scoring of the read-back (untimed sanity use)
 
     # ---------------- strong scaling (the SAME 65536 chains split over the N GPUs), N > 1 only
@@ -350,7 +363,7 @@ def run_native(args):
         s_updates = world * n_vars * per * args.steps
         strong = {"chains_total": per * world, "chains_per_gpu": per, "value": s_updates / (s_ms * 1e-3), "unit": UNIT,
                   "ms_per_step": s_ms / args.steps, "e2e": {"value": s_updates / (s_e_ms * 1e-3), "unit": UNIT, "ms_per_step": s_e_ms / args.steps,
-                                                             "d2h_bytes_per_step": int(total_card * 8 + 16), "interval_ms": measure.interval_ms},
+                                                             "d2h_bytes_per_step": int(total_card * 8 + 16), "interval_ms": measure.interval_ms, "merge_stage_ms": measure.merge_stage_ms},
                   "gpu_launches": int(s_launches), "clocks": s_clocks,
                   "note": "efficiency = strong.value (or strong.e2e.value) / the N = 1 run's value (e2e.value): same total work"}
         chains = sch
@@ -426,7 +439,7 @@ def run_native(args):
                        "setup_seconds": round(setup_s, 2)},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": int(total_card * 8 + 16), "ms_per_step": e_ms / args.steps, "interval_ms": weak_intervals,
+                    "d2h_bytes_per_step": int(total_card * 8 + 16), "ms_per_step": e_ms / args.steps, "interval_ms": weak_intervals, "merge_stage_ms": weak_stages,
                     "path": "per step: gb_chains_sweep, gb_chains_merge_end (the previous step's merged marginals, pinned host "
                             "buffer), gb_chains_merge_begin; in-library NCCL sum of the uint64 counts when N > 1",
                     "note": "the interval loop of cmd/root.go has no per-interval host input: chain state is device-resident "
@@ -440,7 +453,7 @@ def run_native(args):
         line["cpu_baseline"] = cpu
     if secondary is not None:
         line["secondary"] = secondary
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         del chains  # (and with it the library's communicator) before torch tears its own down
         dist.destroy_process_group()

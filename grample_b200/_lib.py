@@ -78,6 +78,7 @@ _SIGS = {
     "gb_chains_merged_marginals": (C.c_int, [_vp, _f64p, _i32p]),
     "gb_chains_merge_begin": (C.c_int, [_vp, _f64p, _i32p]),
     "gb_chains_merge_end": (C.c_int, [_vp, _i64p, _i64p]),
+    "gb_chains_merge_timing": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "gb_chains_global_totals": (C.c_int, [_vp, _i64p, _i64p]),
     "gb_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "gb_comm_init_rank": (C.c_int, [C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int, C.POINTER(_vp)]),

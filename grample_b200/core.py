@@ -292,6 +292,12 @@ class Chains:
         self._pending = None
         return out, col, n.value, t.value
 
+    def merge_timing(self):
+        """device milliseconds of the last merge: [count sums, NCCL sum, conversion to marginals, copy to the host]"""
+        ms = (C.c_float * 4)()
+        check(lib().gb_chains_merge_timing(self.h, ms))
+        return [round(float(x), 4) for x in ms]
+
     def global_totals(self):
         n, t = C.c_int64(), C.c_int64()
         check(lib().gb_chains_global_totals(self.h, C.byref(n), C.byref(t)))

@@ -33,7 +33,7 @@
 namespace gb {
 
 constexpr int kBitsVB = 32;     // sweep positions per tile (half of a locality-ordered 64-position patch)
-constexpr int kBitsQueue = 3072;  // deferred ties per tile (expected W * 256 * kBitsVB * 0.118 = 1930 for W = 2, sd 41; overflow resolves inline)
+// deferred ties per tile: 6 per thread-word (expected kBitsVB * (1 - (255 / 256)^32) = 3.77, sd 0.08 over a tile; overflow resolves inline)
 constexpr int kBitsRec = 8;     // {v, card_off, thr_off, cfg mask, nbr[4]}
 
 // initial state, identical to k_init_state's values (Philox kTagInit: chain >> 2 per call, umulhi(word, 2))
@@ -83,8 +83,8 @@ __device__ __forceinline__ uint32_t bits_resolve(const DevTab& t, const int32_t*
 // CTA tile = (chunk of 256 * W consecutive state words = 8192 * W chains) x (kBitsVB consecutive sweep positions of the
 // colour); tiles are handed out by an atomic counter (`tile_counter`, zeroed before the launch), so a CTA that starts
 // late — e.g. behind the NCCL kernel of an overlapped merge — simply takes fewer tiles.
-template <int W>
-__global__ void __launch_bounds__(256)
+template <int W, int NT>  // W state words per thread, NT threads per CTA: a chunk is NT * W words = 32 * NT * W chains
+__global__ void __launch_bounds__(NT, NT == 128 ? (W == 2 ? 6 : 8) : 0)  // 256 threads: the compiler's own choice (80 / 48 registers); 128: the same warps per SM
 k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __restrict__ bits, const int32_t n_words,
              const int32_t j_begin, const int32_t n_vars_c, const uint32_t sweep, const int record,
              unsigned int* __restrict__ tile_counter) {
@@ -94,10 +94,11 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
     __shared__ __align__(16) const uint32_t* s_row[VB * 4];         // state rows of the 4 neighbours of every position
     __shared__ uint8_t s_t8[VB * 16];                    // top byte of the 16 thresholds of every position
     __shared__ unsigned int s_cnt[VB];                   // ones per position over the tile's chains
+    constexpr int kBitsQueue = 6 * NT * W;
     __shared__ uint2 s_q[kBitsQueue];                    // deferred ties: {position << 16 | word slot, eq}
     __shared__ unsigned int s_qn;
     __shared__ int s_tile;
-    const int chunk_words = 256 * W;
+    const int chunk_words = NT * W;
     const int chunks = (n_words + chunk_words - 1) / chunk_words;
     const int n_vb = (n_vars_c + VB - 1) / VB;
     const int64_t n_tiles = (int64_t)chunks * n_vb;
@@ -113,7 +114,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         const int nv = min(VB, n_vars_c - vb * VB);
         const int j0 = j_begin + vb * VB;
         // ---- stage the tile: records, threshold top bytes, multiplexer coefficients
-        for (int i = tid; i < nv * kBitsRec; i += 256) {
+        for (int i = tid; i < nv * kBitsRec; i += NT) {
             const int j = i >> 3, f = i & 7;
             const int32_t* r = t.trec + (size_t)(j0 + j) * kTabRec;  // {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
             int32_t val;
@@ -128,12 +129,12 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         if (tid == 0) s_qn = 0;
         __syncthreads();
         if (tid < nv * 4) s_row[tid] = bits + (size_t)s_rec[(tid >> 2) * kBitsRec + 4 + (tid & 3)] * n_words;
-        for (int i = tid; i < nv * 16; i += 256) {
+        for (int i = tid; i < nv * 16; i += NT) {
             const int j = i >> 4, c = i & 15;
             s_t8[i] = (uint8_t)(__ldg(t.thr + s_rec[j * kBitsRec + 2] + (c & s_rec[j * kBitsRec + 3])) >> 24);
         }
         __syncthreads();
-        for (int q = tid; q < nv * 64; q += 256) {  // pair q = (position, plane slot, k): plane slot 0 = bit 7
+        for (int q = tid; q < nv * 64; q += NT) {  // pair q = (position, plane slot, k): plane slot 0 = bit 7
             const int j = q >> 6, b = 7 - ((q >> 3) & 7), k = q & 7;
             const int t0 = (s_t8[j * 16 + 2 * k] >> b) & 1, t1 = (s_t8[j * 16 + 2 * k + 1] >> b) & 1;
             s_coef[q] = make_int2(t1 - t0, -t0);  // n0 * a + b = {0, ~0, n0, ~n0} for (t0, t1) = {00, 11, 01, 10}
@@ -145,7 +146,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         uint32_t valid[W];
 #pragma unroll
         for (int u = 0; u < W; u++) {
-            wi[u] = chunk * chunk_words + u * 256 + tid;
+            wi[u] = chunk * chunk_words + u * NT + tid;
             const int64_t first = 32ll * wi[u];
             const int64_t left = (int64_t)g.n_chains - first;
             valid[u] = wi[u] >= n_words || left <= 0 ? 0u : (left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u));
@@ -223,7 +224,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                             if (eq[u] & valid[u]) {  // undecided after 8 planes (2^-8 per chain): resolve after the tile
                                 const unsigned slot = atomicAdd(&s_qn, 1u);
                                 if (slot < (unsigned)kBitsQueue) {
-                                    s_q[slot] = make_uint2((uint32_t)j << 16 | (uint32_t)(u * 256 + tid), eq[u] & valid[u]);
+                                    s_q[slot] = make_uint2((uint32_t)j << 16 | (uint32_t)(u * NT + tid), eq[u] & valid[u]);
                                 } else {
                                     const uint32_t add = bits_resolve(t, &s_rec[j * kBitsRec], bits, n_words, wi[u], gw0 + (uint32_t)wi[u], sweep,
                                                                       seed_lo, seed_hi, eq[u] & valid[u]);
@@ -248,7 +249,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         __syncthreads();
         // ---- deferred ties: one queued word per thread
         const int nq = (int)min(s_qn, (unsigned)kBitsQueue);
-        for (int i = tid; i < nq; i += 256) {
+        for (int i = tid; i < nq; i += NT) {
             const uint2 it = s_q[i];
             const int j = (int)(it.x >> 16), slot = (int)(it.x & 0xffffu);
             const int32_t w = chunk * chunk_words + slot;

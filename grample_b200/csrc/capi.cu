@@ -260,6 +260,7 @@ struct gb_chains {
     gb_comm* comm = nullptr;                 // borrowed; nullptr or world == 1: no collective
     cudaStream_t merge_stream = nullptr;
     cudaEvent_t ev_snap = nullptr, ev_merge_done = nullptr;
+    cudaEvent_t ev_t[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing marks of the interval path (gb_chains_merge_timing)
     unsigned long long* d_cnt = nullptr;     // [total_card + 2]: summed counts, chain count, TotalSampleCount
     unsigned long long* h_tail = nullptr;    // pinned [2]: the (all-reduced) tail of d_cnt
     bool merge_pending = false, merge_ever = false, merge_staged = false;
@@ -297,6 +298,8 @@ struct gb_chains {
         if (merge_stream) cudaStreamDestroy(merge_stream);
         if (ev_snap) cudaEventDestroy(ev_snap);
         if (ev_merge_done) cudaEventDestroy(ev_merge_done);
+        for (auto e : ev_t)
+            if (e) cudaEventDestroy(e);
         if (h_merge) cudaFreeHost(h_merge);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -449,8 +452,8 @@ void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist
     }
 }
 
-// GB_TABLE_BITS: one colour of one group on bit-packed state; W = state words per thread
-template <int W>
+// GB_TABLE_BITS: one colour of one group on bit-packed state; W = state words per thread, NT = threads per CTA
+template <int W, int NT>
 void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
     static int resident_dev[kMaxDevices] = {};  // per device: CTAs that fit at once (persistent CTAs, tiles handed out by an atomic counter)
     int resident;
@@ -460,7 +463,7 @@ void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
         if (!r) {
             int per_sm = 0, sms = 0;
             CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_bits<W>, 256, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_bits<W, NT>, NT, 0));
             r = std::max(1, per_sm * sms);
         }
         resident = r;
@@ -470,19 +473,25 @@ void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
     const uint32_t slot = c->tile_slot++ % kRing;
     if (slot == 0) CUDA_CHECK(cudaMemsetAsync(c->d_tile_ring, 0, kRing * sizeof(unsigned int), c->stream));  // earlier launches of this stream are done with it
     const gb::HostModel& h = g.model->h;
-    const int64_t tiles = (int64_t)((g.n_words + 256 * W - 1) / (256 * W)) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
+    const int64_t tiles = (int64_t)((g.n_words + NT * W - 1) / (NT * W)) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
-    gb::k_sweep_bits<W><<<grid, 256, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
-                                                     record, c->d_tile_ring + slot);
+    gb::k_sweep_bits<W, NT><<<grid, NT, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
+                                                         record, c->d_tile_ring + slot);
     c->launches++;
 }
+// CTA shape by population: two words per thread amortise the warp-uniform coefficient reads; a chunk (NT * W words) must
+// not exceed the row, or threads idle — 8192 chains per GPU (the 8-GPU split of 65536) are 256 words = one chunk of 128 x 2
 void launch_bits(gb_chains* c, Group& g, int col, int32_t n, int record) {
-    const char* env_w = std::getenv("GB_BITS_W");  // A/B and test knob
-    const int force_w = env_w ? std::atoi(env_w) : 0;
-    // two words per thread amortise the warp-uniform coefficient reads; one word keeps small populations spread over the SMs
-    const bool two = force_w ? force_w == 2 : g.n_words >= 2048;
-    if (two) launch_bits_w<2>(c, g, col, n, record);
-    else launch_bits_w<1>(c, g, col, n, record);
+    const char* env = std::getenv("GB_BITS_SHAPE");  // A/B and test knob: "W,NT"
+    int w = g.n_words >= 256 ? 2 : 1, nt = g.n_words >= 512 ? 256 : 128;
+    if (env && std::strlen(env) >= 3) {
+        w = env[0] - '0';
+        nt = std::atoi(env + 2);
+    }
+    if (w == 2 && nt == 256) launch_bits_w<2, 256>(c, g, col, n, record);
+    else if (w == 2) launch_bits_w<2, 128>(c, g, col, n, record);
+    else if (nt == 256) launch_bits_w<1, 256>(c, g, col, n, record);
+    else launch_bits_w<1, 128>(c, g, col, n, record);
 }
 
 // one sweep of one group: one launch per colour
@@ -862,6 +871,7 @@ void ensure_scratch(gb_chains* c) {
         CUDA_CHECK(cudaStreamCreateWithPriority(&c->merge_stream, cudaStreamNonBlocking, hi));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_merge_done, cudaEventDisableTiming));
+        for (auto& e : c->ev_t) CUDA_CHECK(cudaEventCreate(&e));
     }
 }
 
@@ -906,6 +916,7 @@ void merge_snapshot(gb_chains* c) {
     const gb::HostModel& h = c->base();
     upload_skip(c);
     if (c->merge_ever) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_merge_done, 0));  // d_cnt of the previous interval has been consumed
+    CUDA_CHECK(cudaEventRecord(c->ev_t[0], c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->d_cnt, 0, ((size_t)h.total_card + 2) * sizeof(unsigned long long), c->stream));
     bool first = true;
     for (auto& g : c->groups) {
@@ -918,6 +929,7 @@ void merge_snapshot(gb_chains* c) {
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(c->ev_snap, c->stream));
     CUDA_CHECK(cudaStreamWaitEvent(c->merge_stream, c->ev_snap, 0));
+    CUDA_CHECK(cudaEventRecord(c->ev_t[1], c->merge_stream));
 }
 // phase 2, merge stream: sum over the ranks of the communicator (collective: every rank calls it; a fleet brackets
 // the calls of its devices with ncclGroupStart / ncclGroupEnd)
@@ -935,11 +947,13 @@ void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
     const gb::HostModel& h = c->base();
     const size_t bytes = (size_t)h.total_card * sizeof(double);
     const double unit = (c->flags & GB_CHAINS_RAO_BLACKWELL) ? 1.0 / gb::kRbScale : 1.0;
+    CUDA_CHECK(cudaEventRecord(c->ev_t[2], c->merge_stream));
     gb::k_merge_finalize<<<(h.total_card + 255) / 256, 256, 0, c->merge_stream>>>(c->groups[0].model->dev, c->d_cnt, c->d_skip,
                                                                                   c->d_merge, unit);
     c->launches++;
     CUDA_CHECK(cudaGetLastError());
     c->merge_staged = false;
+    CUDA_CHECK(cudaEventRecord(c->ev_t[3], c->merge_stream));
     if (out) {
         cudaPointerAttributes attr{};
         const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -954,6 +968,7 @@ void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
     }
     CUDA_CHECK(cudaMemcpyAsync(c->h_tail, c->d_cnt + h.total_card, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                c->merge_stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_t[4], c->merge_stream));
     CUDA_CHECK(cudaEventRecord(c->ev_merge_done, c->merge_stream));
     c->merge_out = out;
     c->merge_col_out = collapsed_out;
@@ -1620,6 +1635,14 @@ int gb_chains_merge_end(gb_chains* c, int64_t* total_chains_out, int64_t* total_
     merge_wait(c);
     if (total_chains_out) *total_chains_out = c->global_chains;
     if (total_samples_out) *total_samples_out = c->global_samples;
+    GB_END
+}
+int gb_chains_merge_timing(gb_chains* c, float* ms_out) {
+    GB_TRY
+    GB_LOCK(c);
+    if (!c->merge_ever || c->merge_pending) throw gb::Err("no completed merge to report on");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    for (int i = 0; i < 4; i++) CUDA_CHECK(cudaEventElapsedTime(ms_out + i, c->ev_t[i], c->ev_t[i + 1]));
     GB_END
 }
 int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out) {

@@ -349,15 +349,15 @@ def bits_case(which, res):
     return gb.Model.from_arrays(*arrays, device=0), oracle.Model.create(*arrays)
 
 
-@pytest.mark.parametrize("words", ["1", "2"], ids=["W1", "W2"])
+@pytest.mark.parametrize("words", ["1,256", "2,256", "2,128", "1,128"], ids=["W1x256", "W2x256", "W2x128", "W1x128"])
 @pytest.mark.parametrize("which,n_chains,first,n_sweeps", [
     ("Grids_11", 13, 32, 6), ("Grids_11", 96, 0, 5), ("Grids_11", 2100, 64, 3), ("ising_evidence", 75, 0, 7),
     ("ising_32x48", 40, 0, 2)])
 def test_bits_sweep_bitexact(res, monkeypatch, which, n_chains, first, n_sweeps, words):
     """GB_TABLE_BITS against the oracle replaying its bit-plane Philox stream (oracle/sweep.hpp, bits = 33) with the
-    reference's float64 arithmetic: identical states and counts, ragged chain counts, both words-per-thread variants.
+    reference's float64 arithmetic: identical states and counts, ragged chain counts, every CTA shape (words per thread, threads).
     The initial state equals GB_TABLE's (same init stream)."""
-    monkeypatch.setenv("GB_BITS_W", words)
+    monkeypatch.setenv("GB_BITS_SHAPE", words)
     dm, om = bits_case(which, res)
     assert dm.bits_mode()
     order, _ = dm.schedule()
