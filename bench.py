@@ -248,22 +248,27 @@ def measure(gb, gbd, torch, dist, chains, model, args, updates_per_step, world, 
     # while the sweep of interval i + 1 runs: gb_chains_merge_begin / gb_chains_merge_end.  Every interval's result is
     # delivered inside the timed region (the last one after the last sweep).
     total_card, n_vars = model.total_card, model.n_vars
-    bufs = [(torch.empty(total_card, dtype=torch.float64).pin_memory().numpy(), np.empty(n_vars, dtype=np.int32)) for _ in range(2)]
+    rank0 = dist is None or dist.get_rank() == 0
+    # Only rank 0 reads the merged marginals on the host, as only the reference's main goroutine does (cmd/root.go:498-539):
+    # the other ranks take part in the reduction and receive the totals, but ask for no device-to-host copy.
+    bufs = [(torch.empty(total_card, dtype=torch.float64).pin_memory().numpy(), np.empty(n_vars, dtype=np.int32)) if rank0 else "none"
+            for _ in range(3)]
     for i in range(args.warmup):  # warm the interval path too (first call creates the side stream and scratch)
         chains.sweep(1, record=True)
-        chains.merge_begin(bufs[i % 2])
+        chains.merge_begin(bufs[i % 3])
         chains.merge_end()
     barrier()
     e0 = time.time()
     marks, stages = [], []
+    # two merges may be in flight: interval i's sweep AND snapshot are enqueued before the host waits for interval i - 1
     chains.sweep(1, record=True)
     chains.merge_begin(bufs[0])
     for i in range(1, args.steps):
-        chains.sweep(1, record=True)             # interval i is enqueued ...
-        merged, _, n_all, samples_all = chains.merge_end()   # ... while interval i - 1's merged marginals arrive
+        chains.sweep(1, record=True)
+        chains.merge_begin(bufs[i % 3])
+        merged, _, n_all, samples_all = chains.merge_end()   # interval i - 1's merged marginals arrive
         marks.append(time.time())
         stages.append(chains.merge_timing())
-        chains.merge_begin(bufs[i % 2])
     merged, _, n_all, samples_all = chains.merge_end()
     marks.append(time.time())
     stages.append(chains.merge_timing())
@@ -349,7 +354,7 @@ def run_native(args):
     value = world * updates_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * updates_per_step * args.steps / (e_ms * 1e-3)
     weak_intervals, weak_stages = measure.interval_ms, measure.merge_stage_ms
-    score = gb.error_suite(model.cards, np.full(total_card, 0.5), merged)  # host scoring of the read-back (untimed sanity use)
+    score = gb.error_suite(model.cards, np.full(total_card, 0.5), merged) if rank == 0 else None  # host scoring of the read-back (untimed sanity use)
 
     # ---------------- strong scaling (the SAME 65536 chains split over the N GPUs), N > 1 only
     strong = None
@@ -440,8 +445,8 @@ def run_native(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": int(total_card * 8 + 16), "ms_per_step": e_ms / args.steps, "interval_ms": weak_intervals, "merge_stage_ms": weak_stages,
-                    "path": "per step: gb_chains_sweep, gb_chains_merge_end (the previous step's merged marginals, pinned host "
-                            "buffer), gb_chains_merge_begin; in-library NCCL sum of the uint64 counts when N > 1",
+                    "path": "per step: gb_chains_sweep, gb_chains_merge_begin, gb_chains_merge_end (the previous step's merged marginals "
+                            "in rank 0's pinned host buffer); in-library NCCL sum of the uint64 counts when N > 1",
                     "note": "the interval loop of cmd/root.go has no per-interval host input: chain state is device-resident "
                             "(as each Go chain's state is resident in its goroutine); the model (CSR + tables, "
                             f"{model_bytes} bytes) is uploaded once from host arrays during setup_seconds, and the collapsed "

@@ -279,17 +279,23 @@ class Chains:
 
     def merge_begin(self, out=None):
         """MergeChains off the sweep stream: snapshot now, reduce (NCCL when a communicator is attached) and copy to the
-        host on a side stream while later sweeps run.  `out` must stay alive until merge_end()."""
-        bufs = self._merge_buffers(out)
-        check(lib().gb_chains_merge_begin(self.h, _ptr(bufs[0], _f64p), _ptr(bufs[1], _i32p)))
-        self._pending = bufs  # (only now: a refused call must not drop the buffers a pending merge still writes to)
+        host on a side stream while later sweeps run.  `out` must stay alive until the matching merge_end(); up to two
+        merges may be in flight; out="none" asks for no host copy on this rank."""
+        if isinstance(out, str):  # "none": take part in the reduction, no host copy of the marginals on this rank
+            check(lib().gb_chains_merge_begin(self.h, None, None))
+            bufs = (None, None)
+        else:
+            bufs = self._merge_buffers(out)
+            check(lib().gb_chains_merge_begin(self.h, _ptr(bufs[0], _f64p), _ptr(bufs[1], _i32p)))
+        if not hasattr(self, "_pending_q"):
+            self._pending_q = []
+        self._pending_q.append(bufs)  # (only now: a refused call must not drop the buffers a pending merge still writes to)
 
     def merge_end(self):
         """-> (merged, collapsed flags, chains over all ranks, TotalSampleCount over all ranks)"""
         n, t = C.c_int64(), C.c_int64()
         check(lib().gb_chains_merge_end(self.h, C.byref(n), C.byref(t)))
-        out, col = self._pending
-        self._pending = None
+        out, col = self._pending_q.pop(0)  # merges complete in the order they began
         return out, col, n.value, t.value
 
     def merge_timing(self):

@@ -259,13 +259,24 @@ struct gb_chains {
     // run on `merge_stream` behind a snapshot event, so the sweeps enqueued after gb_chains_merge_begin overlap with it
     gb_comm* comm = nullptr;                 // borrowed; nullptr or world == 1: no collective
     cudaStream_t merge_stream = nullptr;
-    cudaEvent_t ev_snap = nullptr, ev_merge_done = nullptr;
-    cudaEvent_t ev_t[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing marks of the interval path (gb_chains_merge_timing)
-    unsigned long long* d_cnt = nullptr;     // [total_card + 2]: summed counts, chain count, TotalSampleCount
-    unsigned long long* h_tail = nullptr;    // pinned [2]: the (all-reduced) tail of d_cnt
-    bool merge_pending = false, merge_ever = false, merge_staged = false;
-    double* merge_out = nullptr;             // destination of the pending merge
-    int32_t* merge_col_out = nullptr;
+    // Up to kMergeSlots merges are in flight at once (begin, begin, end, begin, end, ...): the host can enqueue the next
+    // round's sweeps AND its snapshot before it waits for the previous round's result, so the device never runs dry even
+    // when a merge takes about as long as a round (its NCCL kernel only gets SMs at a sweep kernel's boundary).
+    static constexpr int kMergeSlots = 2;
+    struct MergeSlot {
+        cudaEvent_t ev_snap = nullptr, ev_done = nullptr;
+        cudaEvent_t ev_t[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing marks (gb_chains_merge_timing)
+        unsigned long long* d_cnt = nullptr;   // [total_card + 2]: summed counts, chain count, TotalSampleCount
+        double* d_out = nullptr;               // [total_card] marginals on the device
+        unsigned long long* h_tail = nullptr;  // pinned [2]: the (all-reduced) tail of d_cnt
+        double* h_stage = nullptr;             // pinned staging buffer when the destination is pageable
+        bool pending = false, ever = false, staged = false;
+        double* out = nullptr;                 // destination of the pending merge
+        int32_t* col_out = nullptr;
+    } slots[kMergeSlots];
+    int slot_head = 0, slot_tail = 0, slots_pending = 0;  // next slot to begin / to end
+    int last_done_slot = -1;
+    bool merge_ever = false;
     int64_t global_chains = -1, global_samples = -1;  // tail of the last completed merge
     // GB_TABLE_BITS: tile counters of the dynamically scheduled sweep launches (a ring, re-zeroed when it wraps)
     unsigned int* d_tile_ring = nullptr;
@@ -293,13 +304,17 @@ struct gb_chains {
         cudaFree(d_wb);
         cudaFree(d_skip);
         cudaFree(d_merged_in);
-        cudaFree(d_cnt);
-        if (h_tail) cudaFreeHost(h_tail);
+        for (auto& sl : slots) {
+            cudaFree(sl.d_cnt);
+            cudaFree(sl.d_out);
+            if (sl.h_tail) cudaFreeHost(sl.h_tail);
+            if (sl.h_stage) cudaFreeHost(sl.h_stage);
+            if (sl.ev_snap) cudaEventDestroy(sl.ev_snap);
+            if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+            for (auto e : sl.ev_t)
+                if (e) cudaEventDestroy(e);
+        }
         if (merge_stream) cudaStreamDestroy(merge_stream);
-        if (ev_snap) cudaEventDestroy(ev_snap);
-        if (ev_merge_done) cudaEventDestroy(ev_merge_done);
-        for (auto e : ev_t)
-            if (e) cudaEventDestroy(e);
         if (h_merge) cudaFreeHost(h_merge);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -863,15 +878,18 @@ void ensure_scratch(gb_chains* c) {
     if (!c->d_merged_in) CUDA_CHECK(cudaMalloc(&c->d_merged_in, (size_t)h.total_card * sizeof(double)));
     if (!c->d_wb) CUDA_CHECK(cudaMalloc(&c->d_wb, ((size_t)2 * h.n_vars + 1) * sizeof(double)));  // + the chain count
     if (!c->d_skip) CUDA_CHECK(cudaMalloc(&c->d_skip, (size_t)h.n_vars));
-    if (!c->d_cnt) CUDA_CHECK(cudaMalloc(&c->d_cnt, ((size_t)h.total_card + 2) * sizeof(unsigned long long)));
-    if (!c->h_tail) CUDA_CHECK(cudaMallocHost(&c->h_tail, 2 * sizeof(unsigned long long)));
     if (!c->merge_stream) {
         int lo = 0, hi = 0;  // highest priority: its small kernels and the NCCL kernel take the first free SM slots
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_CHECK(cudaStreamCreateWithPriority(&c->merge_stream, cudaStreamNonBlocking, hi));
-        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_merge_done, cudaEventDisableTiming));
-        for (auto& e : c->ev_t) CUDA_CHECK(cudaEventCreate(&e));
+        for (auto& sl : c->slots) {
+            CUDA_CHECK(cudaMalloc(&sl.d_cnt, ((size_t)h.total_card + 2) * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMalloc(&sl.d_out, (size_t)h.total_card * sizeof(double)));
+            CUDA_CHECK(cudaMallocHost(&sl.h_tail, 2 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_snap, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+            for (auto& e : sl.ev_t) CUDA_CHECK(cudaEventCreate(&e));
+        }
     }
 }
 
@@ -911,69 +929,80 @@ bool has_peers(const gb_chains* c) { return c->comm && c->comm->world > 1; }
 // phase 1, sweep stream: snapshot = integer sums of the groups' counts (+ chain count, TotalSampleCount)
 void merge_snapshot(gb_chains* c) {
     CUDA_CHECK(cudaSetDevice(c->device));
-    if (c->merge_pending) throw gb::Err("a merge is already pending on this handle: call gb_chains_merge_end first");
+    if (c->slots_pending >= gb_chains::kMergeSlots)
+        throw gb::Err("too many merges are already pending on this handle (" + std::to_string(gb_chains::kMergeSlots) +
+                      "): call gb_chains_merge_end first");
     ensure_scratch(c);
     const gb::HostModel& h = c->base();
     upload_skip(c);
-    if (c->merge_ever) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_merge_done, 0));  // d_cnt of the previous interval has been consumed
-    CUDA_CHECK(cudaEventRecord(c->ev_t[0], c->stream));
-    CUDA_CHECK(cudaMemsetAsync(c->d_cnt, 0, ((size_t)h.total_card + 2) * sizeof(unsigned long long), c->stream));
+    auto& sl = c->slots[c->slot_head];
+    if (sl.ever) CUDA_CHECK(cudaStreamWaitEvent(c->stream, sl.ev_done, 0));  // the slot's previous merge has been consumed
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[0], c->stream));
+    CUDA_CHECK(cudaMemsetAsync(sl.d_cnt, 0, ((size_t)h.total_card + 2) * sizeof(unsigned long long), c->stream));
     bool first = true;
     for (auto& g : c->groups) {
         gb::k_merge_counts<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(
-            g.model->dev, g.d_counts, c->d_skip, c->d_cnt, first ? (unsigned long long)local_chains(c) : 0ull,
+            g.model->dev, g.d_counts, c->d_skip, sl.d_cnt, first ? (unsigned long long)local_chains(c) : 0ull,
             first ? (unsigned long long)c->total_samples : 0ull);
         first = false;
     }
     c->launches += (int64_t)c->groups.size();
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaEventRecord(c->ev_snap, c->stream));
-    CUDA_CHECK(cudaStreamWaitEvent(c->merge_stream, c->ev_snap, 0));
-    CUDA_CHECK(cudaEventRecord(c->ev_t[1], c->merge_stream));
+    CUDA_CHECK(cudaEventRecord(sl.ev_snap, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->merge_stream, sl.ev_snap, 0));
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[1], c->merge_stream));
 }
 // phase 2, merge stream: sum over the ranks of the communicator (collective: every rank calls it; a fleet brackets
 // the calls of its devices with ncclGroupStart / ncclGroupEnd)
 void merge_reduce(gb_chains* c) {
     if (!has_peers(c)) return;
     CUDA_CHECK(cudaSetDevice(c->device));
-    NCCL_CHECK(gbn::api().AllReduce(c->d_cnt, c->d_cnt, (size_t)c->base().total_card + 2, gbn::kNcclUint64, gbn::kNcclSum,
+    auto& sl = c->slots[c->slot_head];
+    NCCL_CHECK(gbn::api().AllReduce(sl.d_cnt, sl.d_cnt, (size_t)c->base().total_card + 2, gbn::kNcclUint64, gbn::kNcclSum,
                                     c->comm->nccl, c->merge_stream));
 }
 // phase 3, merge stream: counts -> marginals (every chain starts at uniform 1/card, model/variable.go:45) -> host.
 // A page-locked destination (cudaHostAlloc / cudaHostRegister / a pinned torch tensor) receives the DMA directly; a
-// pageable one goes through the handle's pinned staging buffer.  out == nullptr: keep the result on the device only.
+// pageable one goes through the slot's pinned staging buffer.  out == nullptr: no host copy of the marginals (a rank
+// that only takes part in the reduction; the totals still arrive).
 void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const gb::HostModel& h = c->base();
+    auto& sl = c->slots[c->slot_head];
     const size_t bytes = (size_t)h.total_card * sizeof(double);
     const double unit = (c->flags & GB_CHAINS_RAO_BLACKWELL) ? 1.0 / gb::kRbScale : 1.0;
-    CUDA_CHECK(cudaEventRecord(c->ev_t[2], c->merge_stream));
-    gb::k_merge_finalize<<<(h.total_card + 255) / 256, 256, 0, c->merge_stream>>>(c->groups[0].model->dev, c->d_cnt, c->d_skip,
-                                                                                  c->d_merge, unit);
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[2], c->merge_stream));
+    // few small CTAs (64 threads, grid-stride): they fit into the register / thread slots the resident sweep kernel
+    // leaves on every SM, so the conversion does not have to wait for a sweep kernel to end
+    gb::k_merge_finalize<<<std::min(296, (h.total_card + 63) / 64), 64, 0, c->merge_stream>>>(c->groups[0].model->dev, sl.d_cnt, c->d_skip,
+                                                                                             sl.d_out, unit);
     c->launches++;
     CUDA_CHECK(cudaGetLastError());
-    c->merge_staged = false;
-    CUDA_CHECK(cudaEventRecord(c->ev_t[3], c->merge_stream));
+    sl.staged = false;
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[3], c->merge_stream));
     if (out) {
         cudaPointerAttributes attr{};
         const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();  // (older drivers report an unregistered host pointer as an error)
         if (pinned) {
-            CUDA_CHECK(cudaMemcpyAsync(out, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
+            CUDA_CHECK(cudaMemcpyAsync(out, sl.d_out, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
         } else {
-            if (!c->h_merge) CUDA_CHECK(cudaMallocHost(&c->h_merge, bytes));
-            CUDA_CHECK(cudaMemcpyAsync(c->h_merge, c->d_merge, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
-            c->merge_staged = true;
+            if (!sl.h_stage) CUDA_CHECK(cudaMallocHost(&sl.h_stage, bytes));
+            CUDA_CHECK(cudaMemcpyAsync(sl.h_stage, sl.d_out, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
+            sl.staged = true;
         }
     }
-    CUDA_CHECK(cudaMemcpyAsync(c->h_tail, c->d_cnt + h.total_card, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+    CUDA_CHECK(cudaMemcpyAsync(sl.h_tail, sl.d_cnt + h.total_card, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                c->merge_stream));
-    CUDA_CHECK(cudaEventRecord(c->ev_t[4], c->merge_stream));
-    CUDA_CHECK(cudaEventRecord(c->ev_merge_done, c->merge_stream));
-    c->merge_out = out;
-    c->merge_col_out = collapsed_out;
-    c->merge_pending = true;
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[4], c->merge_stream));
+    CUDA_CHECK(cudaEventRecord(sl.ev_done, c->merge_stream));
+    sl.out = out;
+    sl.col_out = collapsed_out;
+    sl.pending = true;
+    sl.ever = true;
     c->merge_ever = true;
+    c->slot_head = (c->slot_head + 1) % gb_chains::kMergeSlots;
+    c->slots_pending++;
 }
 // host side of the merge on an already-reduced vector: collapsed-in-any variables take the first such chain's local marginal
 void merge_overrides(gb_chains* c, double* out, int32_t* collapsed_out) {
@@ -989,18 +1018,24 @@ void merge_overrides(gb_chains* c, double* out, int32_t* collapsed_out) {
         for (int k = 0; k < h.card[v]; k++) out[h.card_off[v] + k] = m[k];
     }
 }
+// completes the OLDEST pending merge
 void merge_wait(gb_chains* c) {
-    if (!c->merge_pending) throw gb::Err("no merge is pending on this handle: call gb_chains_merge_begin first");
+    if (c->slots_pending == 0) throw gb::Err("no merge is pending on this handle: call gb_chains_merge_begin first");
     CUDA_CHECK(cudaSetDevice(c->device));
-    CUDA_CHECK(cudaEventSynchronize(c->ev_merge_done));
-    c->merge_pending = false;
+    auto& sl = c->slots[c->slot_tail];
+    CUDA_CHECK(cudaEventSynchronize(sl.ev_done));
+    sl.pending = false;
+    c->last_done_slot = c->slot_tail;
+    c->slot_tail = (c->slot_tail + 1) % gb_chains::kMergeSlots;
+    c->slots_pending--;
     const gb::HostModel& h = c->base();
-    if (c->merge_staged) std::memcpy(c->merge_out, c->h_merge, (size_t)h.total_card * sizeof(double));
-    c->global_chains = (int64_t)c->h_tail[0];
-    c->global_samples = (int64_t)c->h_tail[1];
-    merge_overrides(c, c->merge_out, c->merge_col_out);
+    if (sl.staged) std::memcpy(sl.out, sl.h_stage, (size_t)h.total_card * sizeof(double));
+    c->global_chains = (int64_t)sl.h_tail[0];
+    c->global_samples = (int64_t)sl.h_tail[1];
+    merge_overrides(c, sl.out, sl.col_out);
 }
 void merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out) {
+    while (c->slots_pending) merge_wait(c);  // (a blocking merge drains the asynchronous ones first: results arrive in order)
     merge_snapshot(c);
     merge_reduce(c);
     merge_collect(c, out, collapsed_out);
@@ -1640,9 +1675,10 @@ int gb_chains_merge_end(gb_chains* c, int64_t* total_chains_out, int64_t* total_
 int gb_chains_merge_timing(gb_chains* c, float* ms_out) {
     GB_TRY
     GB_LOCK(c);
-    if (!c->merge_ever || c->merge_pending) throw gb::Err("no completed merge to report on");
+    if (c->last_done_slot < 0) throw gb::Err("no completed merge to report on");
     CUDA_CHECK(cudaSetDevice(c->device));
-    for (int i = 0; i < 4; i++) CUDA_CHECK(cudaEventElapsedTime(ms_out + i, c->ev_t[i], c->ev_t[i + 1]));
+    const auto& sl = c->slots[c->last_done_slot];
+    for (int i = 0; i < 4; i++) CUDA_CHECK(cudaEventElapsedTime(ms_out + i, sl.ev_t[i], sl.ev_t[i + 1]));
     GB_END
 }
 int gb_chains_merge_partial_dev(gb_chains* c, double** dev_ptr_out, int64_t* n_out) {
@@ -1936,7 +1972,7 @@ int gb_chains_attach_comm(gb_chains* c, gb_comm* cm) {
     GB_TRY
     GB_LOCK(c);
     if (cm && cm->device != c->device) throw gb::Err("communicator rank is bound to a different device than the chains");
-    if (c->merge_pending) throw gb::Err("a merge is pending on this handle");
+    if (c->slots_pending) throw gb::Err("a merge is pending on this handle");
     c->comm = cm;
     GB_END
 }

@@ -1509,14 +1509,15 @@ k_merge_counts(const DevModel m, const unsigned long long* __restrict__ counts, 
     if (skip[m.entry_var[i]] & 1) return;
     sum[i] += counts[i];
 }
-static __global__ void __launch_bounds__(256)
+// (64-thread CTAs, grid-stride: small enough to share an SM with the resident sweep CTAs, see merge_collect)
+static __global__ void __launch_bounds__(64)
 k_merge_finalize(const DevModel m, const unsigned long long* __restrict__ sum, const uint8_t* __restrict__ skip,
                  double* __restrict__ out, const double count_unit) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.total_card) return;
-    const int v = m.entry_var[i];
     const double n_chains = (double)sum[m.total_card];
-    out[i] = (skip[v] & 1) ? 0.0 : n_chains * (1.0 / (double)m.card[v]) + (double)sum[i] * count_unit;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total_card; i += gridDim.x * blockDim.x) {
+        const int v = m.entry_var[i];
+        out[i] = (skip[v] & 1) ? 0.0 : n_chains * (1.0 / (double)m.card[v]) + (double)sum[i] * count_unit;
+    }
 }
 
 }  // namespace gb

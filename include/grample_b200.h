@@ -217,7 +217,10 @@ int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out
  * (integer sums over this device's groups, NCCL sum over the communicator's ranks when one is attached, conversion to
  * marginals, copy to `out`) on a side stream; sweeps enqueued afterwards run concurrently with it.  _end blocks until
  * `out` / `collapsed_out` of the matching _begin are complete and returns the chain count and TotalSampleCount summed
- * over all ranks (either may be NULL).  One merge may be pending per handle; `out` must stay valid until _end.
+ * over all ranks (either may be NULL).  Up to two merges may be pending per handle (begin, begin, end, begin, end, ...:
+ * the host enqueues the next round and its snapshot before it waits for the previous result, so the device never runs
+ * dry); _end completes the oldest.  `out` must stay valid until its _end; out == NULL takes part in the reduction
+ * without a host copy of the marginals (ranks other than the reporting one).
  * The counts travel as 64-bit integers and the chains' uniform start mass is added once, after the reduction, so the
  * result is bit-identical however the chains are sharded over devices. */
 int gb_chains_merge_begin(gb_chains* c, double* out, int32_t* collapsed_out);

@@ -119,7 +119,7 @@ int main(int argc, char** argv) {
     std::printf("fleet_test: %d device(s)\n", n_dev);
     {
         const std::string uai = res + "/Grids_11.uai";
-        const int32_t ragged = 8 * (2 * n_dev + 1) - 3;  // shards of different sizes, the last one not a multiple of 8
+        const int32_t ragged = 16 * n_dev - 3;  // two blocks of 8 chains per device, the last shard ragged
         compare("TestFleetSimpleF64", run(uai, nullptr, 1, &one, ragged, GB_F64, false), run(uai, nullptr, n_dev, devs.data(), ragged, GB_F64, false));
         compare("TestFleetSimpleTable", run(uai, nullptr, 1, &one, 4096, GB_TABLE, false), run(uai, nullptr, n_dev, devs.data(), 4096, GB_TABLE, false));
     }

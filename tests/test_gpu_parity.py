@@ -965,12 +965,21 @@ def test_async_merge_and_single_rank_communicator(res):
     assert n_all == 32 and samples == 30 * (len(dm.schedule()[0]) * 24 + len(nm.schedule()[0]) * 8)
     with pytest.raises(gb.GrampleError, match="no merge is pending"):
         ch.merge_end()
+    # two merges may be in flight (the host enqueues the next round and its snapshot before waiting for the previous
+    # result); they complete in order, each with its own snapshot
+    ch.merge_begin()
+    ch.sweep(5)
     ch.merge_begin()
     with pytest.raises(gb.GrampleError, match="already pending"):
         ch.merge_begin()
-    ch.merge_end()
+    first, _, _, s1 = ch.merge_end()
+    second, _, _, s2 = ch.merge_end()
+    per_sweep = len(dm.schedule()[0]) * 24 + len(nm.schedule()[0]) * 8
+    assert s1 == 230 * per_sweep and s2 == 235 * per_sweep and second.sum() > first.sum()
+    ch.merge_begin("none")  # a rank that only takes part in the reduction: no host copy, totals still arrive
+    assert ch.merge_end()[:2] == (None, None)
     later, _ = ch.merged_marginals()
-    assert later.sum() > ref.sum()
+    assert np.array_equal(later, second) and later.sum() > ref.sum()
     comm = gb.Comm.init_rank(None, 1, 0, 0)
     assert comm.info == (1, 0, 0)
     ch.attach_comm(comm)
