@@ -271,6 +271,7 @@ struct gb_chains {
         unsigned long long* h_tail = nullptr;  // pinned [2]: the (all-reduced) tail of d_cnt
         double* h_stage = nullptr;             // pinned staging buffer when the destination is pageable
         bool pending = false, ever = false, staged = false;
+        bool needs_finalize = false;           // reduced counts are (or will be) in d_cnt; conversion + host copy not enqueued yet
         double* out = nullptr;                 // destination of the pending merge
         int32_t* col_out = nullptr;
     } slots[kMergeSlots];
@@ -509,6 +510,8 @@ void launch_bits(gb_chains* c, Group& g, int col, int32_t n, int record) {
     else launch_bits_w<1, 128>(c, g, col, n, record);
 }
 
+void flush_finalizes(gb_chains* c);  // (merge path, below)
+
 // one sweep of one group: one launch per colour
 void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
     const gb::HostModel& h = g.model->h;
@@ -526,6 +529,7 @@ void sweep_group(gb_chains* c, Group& g, int record, int hist_half) {
         } else {
             gbh::lse_colour_f64(c, g, dv, n, record, hist_half);
         }
+        flush_finalizes(c);  // a pending merge's conversion goes behind this kernel; its NCCL kernel overlaps with it
     }
     g.sweep++;
     if (record) {
@@ -768,6 +772,7 @@ void run_group(gb_chains* c, Group& g, int64_t n_sweeps, int record, int32_t n_p
     const ResidentPlan plan = resident_plan(c, g);
     const gb::HostModel& h = g.model->h;
     if (plan.ch) {
+        flush_finalizes(c);  // one launch runs the whole round: a pending merge's conversion goes in front of it
         // One launch runs at most kMaxSweepsPerLaunch sweeps: the CTA's shared-memory counters are 32-bit
         // (sweeps x chains per CTA must stay below 2^31) and a single kernel should not run for minutes.
         // A later launch continues the window schedule: its n_pre is shifted (it may go negative).
@@ -961,31 +966,34 @@ void merge_reduce(gb_chains* c) {
     NCCL_CHECK(gbn::api().AllReduce(sl.d_cnt, sl.d_cnt, (size_t)c->base().total_card + 2, gbn::kNcclUint64, gbn::kNcclSum,
                                     c->comm->nccl, c->merge_stream));
 }
-// phase 3, merge stream: counts -> marginals (every chain starts at uniform 1/card, model/variable.go:45) -> host.
+// phase 3: counts -> marginals (every chain starts at uniform 1/card, model/variable.go:45) -> host.
+// The conversion kernel runs on the SWEEP stream, behind the reduction's event: a kernel on the side stream would only get
+// SMs when a (persistent, device-filling) sweep kernel ends, i.e. one more kernel boundary later.  Without peers it is
+// enqueued at once (right behind the count sums); with peers it is deferred to just after the NEXT sweep kernel launch
+// (flush_finalizes), so that the NCCL kernel — which starts the moment the count sums are done, all SMs being free then —
+// overlaps with that sweep kernel instead of holding the sweep stream up.  The copy to the host follows on the side stream.
 // A page-locked destination (cudaHostAlloc / cudaHostRegister / a pinned torch tensor) receives the DMA directly; a
 // pageable one goes through the slot's pinned staging buffer.  out == nullptr: no host copy of the marginals (a rank
 // that only takes part in the reduction; the totals still arrive).
-void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
-    CUDA_CHECK(cudaSetDevice(c->device));
+void finalize_slot(gb_chains* c, gb_chains::MergeSlot& sl) {
+    if (!sl.needs_finalize) return;
+    sl.needs_finalize = false;
     const gb::HostModel& h = c->base();
-    auto& sl = c->slots[c->slot_head];
     const size_t bytes = (size_t)h.total_card * sizeof(double);
     const double unit = (c->flags & GB_CHAINS_RAO_BLACKWELL) ? 1.0 / gb::kRbScale : 1.0;
-    CUDA_CHECK(cudaEventRecord(sl.ev_t[2], c->merge_stream));
-    // few small CTAs (64 threads, grid-stride): they fit into the register / thread slots the resident sweep kernel
-    // leaves on every SM, so the conversion does not have to wait for a sweep kernel to end
-    gb::k_merge_finalize<<<std::min(296, (h.total_card + 63) / 64), 64, 0, c->merge_stream>>>(c->groups[0].model->dev, sl.d_cnt, c->d_skip,
-                                                                                             sl.d_out, unit);
+    CUDA_CHECK(cudaStreamWaitEvent(c->stream, sl.ev_t[2], 0));  // the reduction (or, without peers, the snapshot) is done
+    gb::k_merge_finalize<<<(h.total_card + 255) / 256, 256, 0, c->stream>>>(c->groups[0].model->dev, sl.d_cnt, c->d_skip, sl.d_out, unit);
     c->launches++;
     CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[3], c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->merge_stream, sl.ev_t[3], 0));
     sl.staged = false;
-    CUDA_CHECK(cudaEventRecord(sl.ev_t[3], c->merge_stream));
-    if (out) {
+    if (sl.out) {
         cudaPointerAttributes attr{};
-        const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        const bool pinned = cudaPointerGetAttributes(&attr, sl.out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();  // (older drivers report an unregistered host pointer as an error)
         if (pinned) {
-            CUDA_CHECK(cudaMemcpyAsync(out, sl.d_out, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
+            CUDA_CHECK(cudaMemcpyAsync(sl.out, sl.d_out, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
         } else {
             if (!sl.h_stage) CUDA_CHECK(cudaMallocHost(&sl.h_stage, bytes));
             CUDA_CHECK(cudaMemcpyAsync(sl.h_stage, sl.d_out, bytes, cudaMemcpyDeviceToHost, c->merge_stream));
@@ -996,13 +1004,24 @@ void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
                                c->merge_stream));
     CUDA_CHECK(cudaEventRecord(sl.ev_t[4], c->merge_stream));
     CUDA_CHECK(cudaEventRecord(sl.ev_done, c->merge_stream));
+}
+void flush_finalizes(gb_chains* c) {
+    if (!c->slots_pending) return;
+    for (int i = 0; i < gb_chains::kMergeSlots; i++) finalize_slot(c, c->slots[(c->slot_tail + i) % gb_chains::kMergeSlots]);
+}
+void merge_collect(gb_chains* c, double* out, int32_t* collapsed_out) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    auto& sl = c->slots[c->slot_head];
+    CUDA_CHECK(cudaEventRecord(sl.ev_t[2], c->merge_stream));  // behind the NCCL kernel (or right behind the snapshot)
     sl.out = out;
     sl.col_out = collapsed_out;
     sl.pending = true;
     sl.ever = true;
+    sl.needs_finalize = true;
     c->merge_ever = true;
     c->slot_head = (c->slot_head + 1) % gb_chains::kMergeSlots;
     c->slots_pending++;
+    if (!has_peers(c)) finalize_slot(c, sl);
 }
 // host side of the merge on an already-reduced vector: collapsed-in-any variables take the first such chain's local marginal
 void merge_overrides(gb_chains* c, double* out, int32_t* collapsed_out) {
@@ -1023,6 +1042,7 @@ void merge_wait(gb_chains* c) {
     if (c->slots_pending == 0) throw gb::Err("no merge is pending on this handle: call gb_chains_merge_begin first");
     CUDA_CHECK(cudaSetDevice(c->device));
     auto& sl = c->slots[c->slot_tail];
+    finalize_slot(c, sl);  // (no sweep followed the merge: nothing has flushed it yet)
     CUDA_CHECK(cudaEventSynchronize(sl.ev_done));
     sl.pending = false;
     c->last_done_slot = c->slot_tail;
