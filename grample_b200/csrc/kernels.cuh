@@ -1509,8 +1509,7 @@ k_merge_counts(const DevModel m, const unsigned long long* __restrict__ counts, 
     if (skip[m.entry_var[i]] & 1) return;
     sum[i] += counts[i];
 }
-// (64-thread CTAs, grid-stride: small enough to share an SM with the resident sweep CTAs, see merge_collect)
-static __global__ void __launch_bounds__(64)
+static __global__ void __launch_bounds__(256)
 k_merge_finalize(const DevModel m, const unsigned long long* __restrict__ sum, const uint8_t* __restrict__ skip,
                  double* __restrict__ out, const double count_unit) {
     const double n_chains = (double)sum[m.total_card];
