@@ -58,6 +58,30 @@ static __global__ void __launch_bounds__(256) k_init_bits(const DevModel m, cons
     }
 }
 
+// Philox4x32-10 with the ten round keys (key + r * Weyl constants) precomputed on the host and passed as a kernel
+// parameter: they sit in the constant bank and feed the round's 3-input XOR directly, so the key schedule costs no
+// instruction (left to the compiler it is either hoisted into 20 registers or recomputed every call).
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+inline PhiloxKeys philox_keys(const uint32_t seed_lo, const uint32_t seed_hi) {
+    PhiloxKeys k;
+    for (int r = 0; r < 10; r++) {
+        k.k0[r] = seed_lo + (uint32_t)r * 0x9E3779B9u;
+        k.k1[r] = seed_hi + (uint32_t)r * 0xBB67AE85u;
+    }
+    return k;
+}
+__device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.k0[r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.k1[r];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 __device__ __forceinline__ uint32_t mux32(const uint32_t sel, const uint32_t hi, const uint32_t lo) { return (sel & hi) | (~sel & lo); }
 
 // one undecided word of one variable: decide every chain in `eq` with the tie bits; returns the bits to set
@@ -87,7 +111,7 @@ template <int W, int NT>  // W state words per thread, NT threads per CTA: a chu
 __global__ void __launch_bounds__(NT, NT == 128 ? (W == 2 ? 6 : 8) : 0)  // 256 threads: the compiler's own choice (80 / 48 registers); 128: the same warps per SM
 k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __restrict__ bits, const int32_t n_words,
              const int32_t j_begin, const int32_t n_vars_c, const uint32_t sweep, const int record,
-             unsigned int* __restrict__ tile_counter) {
+             unsigned int* __restrict__ tile_counter, const PhiloxKeys keys) {
     constexpr int VB = kBitsVB;
     __shared__ __align__(16) int2 s_coef[VB * 8 * 8];   // [position][plane 7..0][pair k]: {a_k, b_k}
     __shared__ __align__(16) int32_t s_rec[VB * kBitsRec];
@@ -158,11 +182,11 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
             // read-only for the whole launch)
             uint32_t nx[W][4];
             auto load_nbrs = [&](const int j) {
-                const uint4 lo = *reinterpret_cast<const uint4*>(&s_row[j * 4]), hi = *reinterpret_cast<const uint4*>(&s_row[j * 4 + 2]);
-                const uint32_t* r0 = reinterpret_cast<const uint32_t*>((uint64_t)lo.x | (uint64_t)lo.y << 32);
-                const uint32_t* r1 = reinterpret_cast<const uint32_t*>((uint64_t)lo.z | (uint64_t)lo.w << 32);
-                const uint32_t* r2 = reinterpret_cast<const uint32_t*>((uint64_t)hi.x | (uint64_t)hi.y << 32);
-                const uint32_t* r3 = reinterpret_cast<const uint32_t*>((uint64_t)hi.z | (uint64_t)hi.w << 32);
+                const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(&s_row[j * 4]), hi = *reinterpret_cast<const ulonglong2*>(&s_row[j * 4 + 2]);
+                const uint32_t* r0 = reinterpret_cast<const uint32_t*>(lo.x);
+                const uint32_t* r1 = reinterpret_cast<const uint32_t*>(lo.y);
+                const uint32_t* r2 = reinterpret_cast<const uint32_t*>(hi.x);
+                const uint32_t* r3 = reinterpret_cast<const uint32_t*>(hi.y);
 #pragma unroll
                 for (int u = 0; u < W; u++) {
                     nx[u][0] = __ldg(r0 + wi[u]);
@@ -194,7 +218,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                             uint32_t d[W][4];
 #pragma unroll
                             for (int u = 0; u < W; u++) {
-                                const Philox4 r = philox_wide((uint32_t)ra.x, sweep, gw0 + (uint32_t)wi[u], half ? kTagPlaneB : kTagPlaneA, seed_lo, seed_hi);
+                                const Philox4 r = philox_keyed((uint32_t)ra.x, sweep, gw0 + (uint32_t)wi[u], half ? kTagPlaneB : kTagPlaneA, keys);
                                 d[u][0] = r.x; d[u][1] = r.y; d[u][2] = r.z; d[u][3] = r.w;
                             }
 #pragma unroll

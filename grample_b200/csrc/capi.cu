@@ -492,7 +492,7 @@ void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
     const int64_t tiles = (int64_t)((g.n_words + NT * W - 1) / (NT * W)) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
     gb::k_sweep_bits<W, NT><<<grid, NT, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
-                                                         record, c->d_tile_ring + slot);
+                                                         record, c->d_tile_ring + slot, gb::philox_keys(g.dev.seed_lo, g.dev.seed_hi));
     c->launches++;
 }
 // CTA shape by population: two words per thread amortise the warp-uniform coefficient reads; a chunk (NT * W words) must
