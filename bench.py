@@ -165,7 +165,11 @@ def samples_to_hellinger(gb, dev, threshold=0.01):
     pseudo-count included).  Counting estimator (the reference's) and the Rao-Blackwell estimator, same trajectory."""
     res = os.path.join(ROOT, "tests", "golden", "res")
     out = {"problem": "ObjectDetection_11", "chains": 16, "precision": "f32", "threshold": threshold, "check_every_updates": 16 * 40 * 60,
-           "reference_algorithm_cpu": {"value": 1017360, "source": "profiles/r01_accuracy_objectdetection_rao_blackwell.json (oracle, 4 chains, random scan)"}}
+           "reference_algorithm_cpu": {"value": 1278000, "se": 45000, "chains": 16, "seeds": 8,
+                                       "source": "profiles/r02_accuracy_equal_chains.json: oracle (reference algorithm, random scan) with the SAME 16 chains, "
+                                                 "mean +- s.e. over 8 seeds; device float64 1.33e6 +- 1.1e5, float32 1.37e6 +- 1.1e5 (equal within 1 s.e.); "
+                                                 "with 8 chains on both sides: oracle 1.007e6 +- 3.3e4, device 1.02e6 +- 7.2e4.  The chain count is part of the "
+                                                 "estimator: every chain adds a uniform 1/card pseudo-count (model/variable.go:45)"}}
     try:
         m = gb.Model.from_uai(os.path.join(res, "ObjectDetection_11.uai"), device=dev)
         cards, mar = gb.mar_load(os.path.join(res, "ObjectDetection_11.uai.MAR"))

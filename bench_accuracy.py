@@ -87,15 +87,104 @@ def device_curve(gb, model, mar_cards, mar, n_chains, burn_sweeps, sweeps_per_po
     return out
 
 
+def interp_at(samples, values, at):
+    """value of the error curve at exactly `at` recorded updates (linear between the neighbouring checkpoints)"""
+    s, v = np.asarray(samples, dtype=float), np.asarray(values, dtype=float)
+    if at <= s[0]:
+        return float(v[0])
+    if at >= s[-1]:
+        return float(v[-1])
+    return float(np.interp(at, s, v))
+
+
+def mean_se(xs):
+    xs = [x for x in xs if x is not None]
+    if not xs:
+        return {"n": 0, "mean": None, "se": None}
+    a = np.asarray(xs, dtype=float)
+    return {"n": int(a.size), "mean": float(a.mean()), "se": float(a.std(ddof=1) / np.sqrt(a.size)) if a.size > 1 else 0.0}
+
+
+def equal_chains_study(gb, oracle, n_seeds, quick):
+    """'error no worse at equal samples', measured properly — the SAME chain count on both sides
+    (MergeChains adds one uniform 1/card pseudo-count per chain, model/variable.go:45, so the chain count is part of the
+    estimator), the reference's counting estimator on both sides, >= 8 seeds per side, mean +- standard error of
+      * recorded updates until the mean Hellinger distance to .MAR first drops below 0.01 (ObjectDetection_11), and
+      * the mean Hellinger distance at a fixed number of recorded updates (1e6 ObjectDetection_11, 2e6 Grids_11).
+    Oracle = CPU restatement of the reference (random scan, MT19937-64, float64); its checkpoints are its rounds, so it
+    runs with a short convergence window (cw = 20: the window only sets the round length, not the chain).  Device =
+    systematic colour sweep, Philox, float64 log-sum-exp kernels (and the table kernels on Grids_11)."""
+    out = {"seeds": n_seeds, "estimator": "counts + one uniform 1/card pseudo-count per chain (the reference's MergeChains)", "problems": {}}
+    for name, at, thr, precisions in (("ObjectDetection_11.uai", 1_000_000, 0.01, (("f64", gb.F64), ("f32", gb.F32))),
+                                     ("Grids_11.uai", 2_000_000, None, (("f64", gb.F64), ("table", gb.TABLE), ("bits", gb.TABLE_BITS)))):
+        cards, mar = gb.mar_load(os.path.join(RES, name + ".MAR"))
+        om = oracle.Model.load(os.path.join(RES, name))
+        sol = oracle.solution_load(os.path.join(RES, name + ".MAR"))
+        dm = gb.Model.from_uai(os.path.join(RES, name), device=0)
+        n_free = len(dm.schedule()[0])
+        horizon = int(at * (3 if thr else 1.05))
+        entry = {"at_updates": at, "threshold": thr, "by_chains": {}}
+        for n_chains in ((8,) if quick else (8, 16)):
+            rows = {"oracle": {"hellinger_at": [], "samples_to_threshold": []}}
+            for label, _ in precisions:
+                rows["device_" + label] = {"hellinger_at": [], "samples_to_threshold": []}
+            for seed in range(1, n_seeds + 1):
+                r = oracle.run(om, sol, kind=oracle.SIMPLE, n_chains=n_chains, burn_in=2000 * dm.n_vars, cw=20, max_iters=horizon,
+                               seed=1000 * seed, lean=True, n_threads=0)["curve"]
+                rows["oracle"]["hellinger_at"].append(interp_at(r["samples"], r["mean_hellinger"], at))
+                if thr:
+                    rows["oracle"]["samples_to_threshold"].append(first_below(r["samples"], r["mean_hellinger"], thr))
+                sweeps_per_point = max(1, int(round(np.median(np.diff(r["samples"])) / (n_free * n_chains))))  # same checkpoint spacing
+                for label, prec in precisions:
+                    ch = gb.Chains(dm, n_chains, seed=1000 * seed + 7, precision=prec, device=0)
+                    ch.burnin(2000)
+                    ss, hh = [], []
+                    while not ss or ss[-1] < horizon:
+                        ch.sweep(sweeps_per_point)
+                        merged, _ = ch.merged_marginals()
+                        ss.append(ch.total_samples)
+                        hh.append(gb.error_suite(cards, mar, merged)["MeanHellinger"])
+                    rows["device_" + label]["hellinger_at"].append(interp_at(ss, hh, at))
+                    if thr:
+                        rows["device_" + label]["samples_to_threshold"].append(first_below(ss, hh, thr))
+            summary = {}
+            for k, v in rows.items():
+                summary[k] = {"mean_hellinger_at": mean_se(v["hellinger_at"]), "per_seed_hellinger_at": v["hellinger_at"]}
+                if thr:
+                    summary[k]["samples_to_threshold"] = mean_se(v["samples_to_threshold"])
+                    summary[k]["per_seed_samples_to_threshold"] = v["samples_to_threshold"]
+            o = summary["oracle"]["mean_hellinger_at"]
+            for k in summary:
+                if k != "oracle":
+                    d = summary[k]["mean_hellinger_at"]
+                    se = float(np.hypot(d["se"], o["se"]))
+                    summary[k]["vs_oracle"] = {"difference_of_means": d["mean"] - o["mean"], "se_of_difference": se,
+                                               "no_worse_within_1_se": bool(d["mean"] - o["mean"] <= se)}
+            entry["by_chains"][str(n_chains)] = summary
+        out["problems"][name.replace(".uai", "")] = entry
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--equal-chains", type=int, default=0, metavar="SEEDS",
+                    help="run only the equal-chain-count study (device vs oracle, mean +- s.e. over SEEDS seeds)")
     ap.add_argument("--configs", default="0,1,2,3", help="comma-separated BASELINE config numbers to run")
     args = ap.parse_args()
     sel = {int(x) for x in args.configs.split(",")}
     import grample_b200 as gb
     import oracle
+
+    if args.equal_chains:
+        doc = equal_chains_study(gb, oracle, args.equal_chains, args.quick)
+        text = json.dumps(doc, indent=1)
+        if args.out:
+            with open(args.out, "w") as f:
+                f.write(text)
+        print(text if not args.out else f"wrote {args.out}")
+        return
 
     q = 4 if args.quick else 1
     doc = {"note": "equal recorded single-variable updates; errors vs res/*.uai.MAR; 'not reached' = None", "configs": {}}

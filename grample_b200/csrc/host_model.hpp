@@ -58,7 +58,7 @@ struct HostModel {
     std::vector<int32_t> prog_off, prog;           // per-variable update program (see kernels.cuh)
     std::vector<int32_t> pw_off, pw_rec;           // pairwise fast path: per variable 4-word records, pw_off = -1 when a factor has arity > 2
     // ---- tabulated-conditional fast path (binary sampled variables, <= 256 neighbour configurations)
-    bool tab_ok = false, tab_all = false;
+    bool tab_ok = false, tab_all = false, tab_all_binary = true;
     std::string tab_why;                           // why the fast path does not apply
     bool bits_ok = false;                          // GB_TABLE_BITS applies: tab_ok and every sampled variable has <= 4 free neighbours, all binary
     std::string bits_why;
@@ -134,11 +134,13 @@ struct HostModel {
         build_tab_programs();
     }
 
-    // Tabulated conditionals: for a sampled binary variable whose distinct free neighbours span
-    // C <= 256 joint configurations, the whole conditional (gibbs-simple.go:171-258) depends only
-    // on that configuration, so it is evaluated once per configuration (k_build_thresholds) and the
-    // sweep becomes: gather neighbour bytes -> configuration index -> threshold -> compare.
+    // Tabulated conditionals: for a sampled variable of cardinality <= 4 whose distinct free neighbours span few joint
+    // configurations, the whole conditional (gibbs-simple.go:171-258) depends only on that configuration, so it is
+    // evaluated once per configuration (k_build_thresholds) and stored as card - 1 cumulative 32-bit inverse-CDF
+    // thresholds; the sweep becomes: gather neighbour bytes -> configuration index -> thresholds -> compare.
     // Fixed neighbours are folded into the table (their value never changes).
+    //   GB_TABLE  (tab_ok):  every sampled variable BINARY with <= 256 configurations (the integer bench kernels)
+    //   GB_HYBRID (tp_off):  per variable, cardinality <= 4 and <= kTabWideCfg configurations; the rest by log-sum-exp
     void build_tab_programs() {
         tab_ok = true;
         tab_why.clear();
@@ -148,13 +150,16 @@ struct HostModel {
         n_thresholds = 0;
         n_tab_vars = 0;
         tab_max_nbr = 0;
+        tab_all_binary = true;
         for (int v : order) {
             std::string why;
-            if (card[v] != 2)
+            if (card[v] != 2) {
                 why = "variable " + std::to_string(v) + " has cardinality " + std::to_string(card[v]) + " (table mode needs binary sampled variables)";
+                tab_all_binary = false;
+            }
             int64_t cfgs = 1;
             std::vector<int32_t> words;
-            if (why.empty())
+            if (card[v] <= 4)
                 for (int32_t u : nbrs[v]) {
                     if (u == v || fixed[u] >= 0 || card[u] == 1) continue;  // constant neighbours fold into the table
                     words.push_back(u);
@@ -164,35 +169,39 @@ struct HostModel {
                 }
             if (why.empty() && cfgs > 256) why = "variable " + std::to_string(v) + " has more than 256 neighbour configurations";
             if (!why.empty() && tab_ok) {
-                tab_ok = false;  // GB_TABLE needs every sampled variable narrow; GB_HYBRID takes what qualifies
+                tab_ok = false;  // GB_TABLE needs every sampled variable binary and narrow; GB_HYBRID takes what qualifies
                 tab_why = why;
             }
-            if (card[v] != 2 || cfgs > kTabWideCfg) continue;
+            if (card[v] > 4 || cfgs > kTabWideCfg) continue;
             tp_off[v] = (int32_t)tprog.size();
             tprog.push_back((int32_t)words.size() / 2);
             tprog.push_back((int32_t)n_thresholds);
             tprog.insert(tprog.end(), words.begin(), words.end());
-            n_thresholds += cfgs;
+            n_thresholds += cfgs * (card[v] - 1);  // card - 1 cumulative thresholds per configuration
             n_tab_vars++;
         }
         // tab_all: every sampled variable has a table (any width) — the resident table kernel can run the whole
-        // model (wide variables through their variable-length tprog entry); tab_ok additionally has them all narrow
+        // model (wide variables through their variable-length tprog entry); tab_ok additionally has them all binary and narrow
         tab_all = n_tab_vars == (int32_t)order.size() && n_tab_vars > 0;
         if (!tab_all) return;
-        // fixed-size record per sweep position: {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
-        // (2^n_nbr <= 256 configurations => n_nbr <= 8)
+        // fixed-size record per sweep position: {v, thr_off, n_nbr | card << 8, card_off, nbr[8], stride[8]}
+        // (narrow = at most 8 neighbours and 256 configurations: the index fits the byte-packed arithmetic)
         trec.assign(order.size() * 20, 0);
         for (size_t j = 0; j < order.size(); j++) {
             const int v = order[j];
             const int32_t* tp = tprog.data() + tp_off[v];
             int32_t* r = trec.data() + j * 20;
+            int64_t cfgs = 1;
+            for (int i = 0; i < tp[0]; i++) cfgs *= card[tp[2 + 2 * i]];
+            const bool wide = tp[0] > 8 || cfgs > 256;
             r[0] = v;
             r[1] = tp[1];
-            r[2] = tp[0];
-            tab_max_nbr = std::max(tab_max_nbr, (int)tp[0]);
+            r[2] = (wide ? std::max(tp[0], 9) : tp[0]) | (card[v] << 8);  // a wide record reports more than 8 neighbours
+            tab_max_nbr = std::max(tab_max_nbr, wide ? std::max((int)tp[0], 9) : (int)tp[0]);
             r[3] = card_off[v];
-            if (tp[0] > 8) {  // wide variable: the record only points at its tprog entry
+            if (wide) {  // wide variable: the record only points at its tprog entry
                 r[4] = tp_off[v];
+                r[5] = tp[0];
                 continue;
             }
             for (int i = 0; i < 8; i++) {
@@ -205,11 +214,12 @@ struct HostModel {
         bits_why = tab_why;
         for (size_t j = 0; j < order.size() && bits_ok; j++) {
             const int32_t* r = trec.data() + j * 20;
-            if (r[2] > 4) {
+            const int nn = r[2] & 0xff;
+            if (nn > 4) {
                 bits_ok = false;
                 bits_why = "variable " + std::to_string(r[0]) + " has more than 4 free neighbours";
             }
-            for (int i = 0; i < r[2] && bits_ok; i++)
+            for (int i = 0; i < nn && bits_ok; i++)
                 if (card[r[4 + i]] != 2 || r[12 + i] != (1 << i)) {
                     bits_ok = false;
                     bits_why = "variable " + std::to_string(r[0]) + " has a non-binary neighbour";
