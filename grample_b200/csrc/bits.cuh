@@ -145,7 +145,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
             if (f == 0) val = __ldg(r);
             else if (f == 1) val = __ldg(r + 3);
             else if (f == 2) val = __ldg(r + 1);
-            else if (f == 3) val = (1 << __ldg(r + 2)) - 1;
+            else if (f == 3) val = (1 << (__ldg(r + 2) & 0xff)) - 1;
             else val = __ldg(r + f);  // nbr[f - 4]; slots past n_nbr hold the variable itself (its bits are masked out of cfg)
             s_rec[i] = val;
         }

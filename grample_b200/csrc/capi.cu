@@ -183,7 +183,7 @@ struct gb_model {
         tab.trec = up(h.trec);
         tab_built = true;
     }
-    // hybrid mode tabulates what qualifies (binary, <= 65536 configurations) in models whose cardinalities are <= 4
+    // hybrid mode tabulates what qualifies (cardinality <= 4, <= 65536 configurations) in models whose cardinalities are <= 4
     bool hybrid_tables() const { return h.max_card <= 4 && h.n_tab_vars > 0; }
     // hybrid mode on a model where EVERY sampled variable got a table (plain binary models and their
     // single-collapsed variants): the resident table kernel runs it, wide variables through their tprog entry
@@ -749,11 +749,12 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
     size_t smem = 0;
     const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
-    static size_t configured_dev[2][kMaxDevices] = {};  // function attributes are per device
-    const bool wide = h.tab_max_nbr > 8;
+    static size_t configured_dev[4][kMaxDevices] = {};  // function attributes are per device
+    const bool wide = h.tab_max_nbr > 8, multi = !h.tab_all_binary;
     std::lock_guard<std::mutex> cfg_lock(g_cfg_mu);
-    size_t& configured = configured_dev[wide][c->device];
-    auto kernel = wide ? gb::k_sweep_tab_resident<true> : gb::k_sweep_tab_resident<false>;
+    size_t& configured = configured_dev[2 * multi + wide][c->device];
+    auto kernel = multi ? (wide ? gb::k_sweep_tab_resident<true, true> : gb::k_sweep_tab_resident<false, true>)
+                        : (wide ? gb::k_sweep_tab_resident<true, false> : gb::k_sweep_tab_resident<false, false>);
     if (smem > configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -1404,9 +1405,9 @@ int gb_model_thresholds(gb_model* m, int32_t var, int32_t* n_out, uint32_t* out)
     GB_TRY
     if (var < 0 || var >= m->h.n_vars) throw gb::Err("Invalid variable index");
     m->ensure_thresholds();
-    if (m->h.tp_off[var] < 0) throw gb::Err("variable has no threshold table (not sampled, not binary, or too many neighbour configurations)");
+    if (m->h.tp_off[var] < 0) throw gb::Err("variable has no threshold table (not sampled, cardinality above 4, or too many neighbour configurations)");
     const int32_t* tp = m->h.tprog.data() + m->h.tp_off[var];
-    int n = 1;
+    int n = m->h.card[var] - 1;  // card - 1 cumulative thresholds per configuration
     for (int i = 0; i < tp[0]; i++) n *= m->h.card[tp[2 + 2 * i]];
     if (n_out) *n_out = n;
     if (out) CUDA_CHECK(cudaMemcpy(out, m->tab.thr + tp[1], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));

@@ -502,8 +502,8 @@ __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __r
 // draw, same tie rule and Philox fields as the table kernels — and every other variable by the float64
 // log-sum-exp path.  One variable x 4 consecutive chains; tpo = the variable's offset in DevTab::tprog.
 __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t tpo, const uint8_t* row, const uint32_t stride,
-                                                const int v, const uint32_t chain0, const uint32_t sweep, const uint32_t seed_lo,
-                                                const uint32_t seed_hi, int (&x)[4]) {
+                                                const int v, const int card, const uint32_t chain0, const uint32_t sweep,
+                                                const uint32_t seed_lo, const uint32_t seed_hi, int (&x)[4]) {
     const int32_t* __restrict__ tp = t.tprog + tpo;
     const int nn = __ldg(tp), thr_off = __ldg(tp + 1);
     uint32_t idx[4] = {0u, 0u, 0u, 0u};
@@ -518,6 +518,21 @@ __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t t
     const bool second = (chain0 >> 2) & 1u;
     const Philox4 a = philox_wide((uint32_t)v, sweep, chain0 >> 3, kTagDraw16Hi, seed_lo, seed_hi);
     const uint32_t wa[2] = {second ? a.z : a.x, second ? a.w : a.y};
+    if (card > 2) {
+        // ternary / quaternary variable: card - 1 cumulative thresholds per configuration, full 32-bit draws
+        // (value = number of thresholds the draw exceeds)
+        const Philox4 b = philox_wide((uint32_t)v, sweep, chain0 >> 3, kTagDraw16Lo, seed_lo, seed_hi);
+        const uint32_t wb[2] = {second ? b.z : b.x, second ? b.w : b.y};
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++) {
+            const uint32_t u = (((wa[ci >> 1] >> (16 * (ci & 1))) & 0xffffu) << 16) | ((wb[ci >> 1] >> (16 * (ci & 1))) & 0xffffu);
+            const uint32_t* __restrict__ T = t.thr + thr_off + idx[ci] * (uint32_t)(card - 1);
+            int val = 0;
+            for (int j = 0; j < card - 1; j++) val += u > __ldg(T + j) ? 1 : 0;
+            x[ci] = val;
+        }
+        return;
+    }
     uint32_t T[4], hi[4];
     bool tie = false;
 #pragma unroll
@@ -562,7 +577,7 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
         int x[4];
         const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
         if (tpo >= 0)
-            tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
+            tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x);
         else {
             const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - 4 * q);
             lse_update_quad<Real, MAXC, CW, true, Rec>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep,
@@ -784,7 +799,7 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     int x[4];
                     const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
                     if (tpo >= 0)
-                        tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, chain0, sweep, g.seed_lo, g.seed_hi, x);
+                        tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x);
                     else {
                         const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain);
                         lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS, Rec>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0,
@@ -829,45 +844,75 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
 // by k_build_thresholds and stored as the largest 32-bit draw that still selects value 0 under
 // the reference's inverse-CDF rule (sampler.go:115-123: r = U*tot, r <= e0).  The sweep itself is
 // integer work: gather neighbour bytes -> configuration index -> threshold -> compare.
+// sampler.go:107-123 for a 32-bit draw u (U = u * 2^-32): re-sum, r = U * tot, first k with r <= w[k] (the fall-through
+// selects the last value, as everywhere on the device).  Monotone non-decreasing in u.
+template <int CARD>
+__device__ __forceinline__ int tab_select(const double (&w)[CARD], const uint32_t u) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < CARD; k++) tot += w[k];
+    double r = ((double)u * (1.0 / 4294967296.0)) * tot;
+#pragma unroll
+    for (int k = 0; k < CARD - 1; k++) {
+        if (r <= w[k]) return k;
+        r -= w[k];
+    }
+    return CARD - 1;
+}
+// thresholds of one configuration: thr[j] = the largest 32-bit draw that still selects a value <= j (j < CARD - 1), found
+// by bisection on the reference's own predicate, so value = #{j : u > thr[j]} reproduces the inverse CDF exactly
+template <int CARD>
+__device__ __forceinline__ void tab_thresholds(const DevModel& m, const int32_t* __restrict__ prog, const int32_t* __restrict__ tp,
+                                               const int nn, const int cfg, uint32_t* __restrict__ out) {
+    double w[CARD];
+#pragma unroll
+    for (int k = 0; k < CARD; k++) w[k] = 0.0;
+    const int nf = prog[0];
+    const int32_t* p = prog + 1;
+    for (int f = 0; f < nf; f++) {
+        const int tab_off = p[0], sv = p[1], no = p[2];
+        p += 3;
+        int b = tab_off;
+        for (int o = 0; o < no; o++, p += 2) {
+            const int ov = p[0];
+            int sv_o = m.fixed[ov];
+            if (sv_o < 0) {
+                for (int i = 0; i < nn; i++)
+                    if (tp[2 + 2 * i] == ov) sv_o = (cfg / tp[3 + 2 * i]) % m.card[ov];
+            }
+            b += sv_o * p[1];
+        }
+#pragma unroll
+        for (int k = 0; k < CARD; k++) w[k] += m.tab64[b + k * sv];
+    }
+    stabilise_exp_floor<double, CARD>(w, CARD);
+#pragma unroll
+    for (int j = 0; j < CARD - 1; j++) {
+        uint32_t lo = 0u, hi = 0xffffffffu;  // invariant: select(lo) <= j (u = 0 always selects value 0: r = 0 <= w[0])
+        while (lo < hi) {
+            const uint32_t mid = lo + (uint32_t)(((uint64_t)hi - lo + 1) >> 1);
+            if (tab_select<CARD>(w, mid) <= j) lo = mid;
+            else hi = mid - 1u;
+        }
+        out[j] = lo;
+    }
+}
+
 static __global__ void __launch_bounds__(128)
 k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__ order, const int32_t n_order) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_order; j += gridDim.x * blockDim.x) {
         const int v = order[j];
         if (t.tp_off[v] < 0) continue;  // hybrid mode: this variable is sampled by the log-sum-exp path
         const int32_t* tp = t.tprog + t.tp_off[v];
-        const int nn = tp[0], thr_off = tp[1];
+        const int nn = tp[0], thr_off = tp[1], card = m.card[v];
         int n_cfg = 1;
         for (int i = 0; i < nn; i++) n_cfg *= m.card[tp[2 + 2 * i]];
         const int32_t* prog = m.prog + m.prog_off[v];
-        const int nf = prog[0];
         for (int cfg = 0; cfg < n_cfg; cfg++) {
-            double w[2] = {0.0, 0.0};
-            const int32_t* p = prog + 1;
-            for (int f = 0; f < nf; f++) {
-                const int tab_off = p[0], sv = p[1], no = p[2];
-                p += 3;
-                int b = tab_off;
-                for (int o = 0; o < no; o++, p += 2) {
-                    const int ov = p[0];
-                    int sv_o = m.fixed[ov];
-                    if (sv_o < 0) {
-                        for (int i = 0; i < nn; i++)
-                            if (tp[2 + 2 * i] == ov) sv_o = (cfg / tp[3 + 2 * i]) % m.card[ov];
-                    }
-                    b += sv_o * p[1];
-                }
-                w[0] += m.tab64[b];
-                w[1] += m.tab64[b + sv];
-            }
-            stabilise_exp_floor<double, 2>(w, 2);
-            const double tot = w[0] + w[1];  // WeightedSample re-sums (sampler.go:107-113)
-            // largest t with (t * 2^-32) * tot <= e0 — the reference predicate evaluated exactly
-            auto pred = [&](uint32_t tt) { return ((double)tt * (1.0 / 4294967296.0)) * tot <= w[0]; };
-            double c = (w[0] / tot) * 4294967296.0;
-            uint32_t tt = c >= 4294967295.0 ? 4294967295u : (uint32_t)c;
-            while (tt < 4294967295u && pred(tt + 1u)) tt++;
-            while (tt > 0u && !pred(tt)) tt--;
-            t.thr[thr_off + cfg] = tt;
+            uint32_t* out = t.thr + thr_off + (size_t)cfg * (card - 1);
+            if (card == 2) tab_thresholds<2>(m, prog, tp, nn, cfg, out);
+            else if (card == 3) tab_thresholds<3>(m, prog, tp, nn, cfg, out);
+            else tab_thresholds<4>(m, prog, tp, nn, cfg, out);
         }
     }
 }
@@ -878,7 +923,7 @@ k_build_thresholds(const DevModel m, const DevTab t, const int32_t* __restrict__
 // consecutive variables hit L1.  Per tile the position records and the 16-bit high halves of the
 // thresholds are staged in shared memory.  One Philox call yields the high halves of 8 draws; the
 // low halves are generated only when a high half ties with its threshold (probability 2^-16).
-constexpr int kTabRec = 20;  // {v, thr_off, n_nbr, card_off, nbr[8], stride[8]}
+constexpr int kTabRec = 20;  // {v, thr_off, n_nbr | card << 8, card_off, nbr[8], stride[8]}; wide (n_nbr > 8): {.., tprog offset, true n_nbr}
 
 // NN = neighbour slots read per variable (4 or 8); records pad unused slots with the variable
 // itself at stride 0, so the loads are unconditional and branch-free.
@@ -1120,7 +1165,10 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
 // Work item = (sweep position, unit of 8 chains); same records, thresholds, Philox stream and tie rule
 // as k_sweep_tab, so the two paths produce identical trajectories.  Records and thresholds are read
 // through L1 (they are a few KB and shared by every CTA).
-template <bool WIDE>  // WIDE: some variable has more than 8 free neighbours (variable-length records, 32-bit configuration indices)
+// WIDE: some variable has more than 8 free neighbours or 256 configurations (variable-length records, 32-bit configuration
+// indices).  MULTI: some sampled variable is ternary / quaternary (card - 1 cumulative thresholds per configuration,
+// full 32-bit draws, value = number of thresholds the draw exceeds); binary variables keep the 16-bit fast path.
+template <bool WIDE, bool MULTI>
 __global__ void __launch_bounds__(256)
 k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ colour_off,
                      const int32_t n_colours, const int32_t ch_per_cta, const uint32_t sweep0, const int32_t n_sweeps,
@@ -1156,15 +1204,18 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
             for (int item = threadIdx.x; item < nvc * units; item += blockDim.x) {
                 const int j = item >> unit_shift, q = item & (units - 1);  // units is a power of two (CH = 8..64)
                 const int4* r = reinterpret_cast<const int4*>(t.trec + (size_t)(c0 + j) * kTabRec);
-                const int4 hd = __ldg(r);  // v, thr_off, n_nbr, card_off
+                const int4 hd = __ldg(r);  // v, thr_off, n_nbr | card << 8, card_off
+                const int nn = hd.z & 0xff;
+                [[maybe_unused]] const int card = hd.z >> 8;
                 uint32_t cfg_lo = 0, cfg_hi = 0;
                 [[maybe_unused]] uint32_t idxw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                const bool wide = WIDE && hd.z > 8;
+                const bool wide = WIDE && nn > 8;
                 if (wide) {
-                    // wide variable (more than 8 free neighbours, e.g. the neighbours of a collapsed variable): the
-                    // record points at its variable-length tprog entry and the configuration index needs 32 bits
+                    // wide variable (more than 8 free neighbours or 256 configurations, e.g. the neighbours of a collapsed
+                    // variable): the record points at its variable-length tprog entry and the index needs 32 bits
                     const int32_t* __restrict__ tp = t.tprog + __ldg(&r[1].x) + 2;
-                    for (int i = 0; i < hd.z; i++) {
+                    const int n_true = __ldg(&r[1].y);
+                    for (int i = 0; i < n_true; i++) {
                         const int ov = __ldg(tp + 2 * i);
                         const uint32_t os = (uint32_t)__ldg(tp + 2 * i + 1);
                         const uint2 w = *reinterpret_cast<const uint2*>(s_state + (size_t)ov * CH + 8 * q);
@@ -1185,7 +1236,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                             cfg_hi += w.y * (uint32_t)sb[i];
                         }
                     }
-                    if (hd.z > 4) {
+                    if (nn > 4) {
                         const int4 na = __ldg(r + 2), sa = __ldg(r + 4);
                         const int nb[4] = {na.x, na.y, na.z, na.w}, sb[4] = {sa.x, sa.y, sa.z, sa.w};
 #pragma unroll
@@ -1200,6 +1251,31 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                 const uint32_t chain_blk = (uint32_t)((g.first_chain + (uint64_t)lchain) >> 3);
                 const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+                if constexpr (MULTI) {
+                    if (card > 2) {  // ternary / quaternary variable
+                        const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
+                        const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+                        const int nvalid = record ? max(0, min(8, g.n_chains - lchain)) : 0;
+                        uint32_t outb[2] = {0u, 0u};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
+                            if constexpr (WIDE) idx = wide ? idxw[i] : idx;
+                            const uint32_t u = (((wa[i >> 1] >> (16 * (i & 1))) & 0xffffu) << 16) | ((wb[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                            const uint32_t* __restrict__ T = t.thr + hd.y + idx * (uint32_t)(card - 1);
+                            int val = 0;
+                            for (int k = 0; k < card - 1; k++) val += u > __ldg(T + k) ? 1 : 0;
+                            outb[i >> 2] |= (uint32_t)val << (8 * (i & 3));
+                            if (i < nvalid) {
+                                atomicAdd(&s_counts[hd.w + val], 1u);
+                                if (hist_half >= 0 && g.hist)  // (the shared-memory histograms hold the ones of binary variables only)
+                                    hist_add(nullptr, g, m.total_card, hist_half, hd.w + val, CH, 0, lchain + i);
+                            }
+                        }
+                        *reinterpret_cast<uint2*>(s_state + (size_t)hd.x * CH + 8 * q) = make_uint2(outb[0], outb[1]);
+                        continue;
+                    }
+                }
                 // same compare as k_sweep_tab: d = threshold high half - draw high half (both < 2^16), sign bit set <=> the
                 // draw is above the threshold; a zero d is a tie, found with 3-input unsigned minima
                 uint32_t T[8], dd[8], xbits = 0;
@@ -1264,6 +1340,9 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
             const int half = e >= t.n_order ? 1 : 0, pos = e - half * t.n_order;
             const int nvalid = min(8, g.n_chains - (cta_chain + 8 * u));
             if (n_rec[half] == 0 || nvalid <= 0) continue;  // nothing recorded / padding
+            if constexpr (MULTI) {
+                if ((__ldg(t.trec + (size_t)pos * kTabRec + 2) >> 8) != 2) continue;  // non-binary: recorded in global memory directly
+            }
             const uint4 ones = *reinterpret_cast<const uint4*>(s_hist + (size_t)e * CH + 8 * u);
             const uint4 lanes = spread_bits16(nvalid >= 8 ? 0xffu : ((1u << nvalid) - 1u));  // 1 in the lanes of existing chains
             const uint32_t nr = (uint32_t)n_rec[half];

@@ -53,11 +53,13 @@ enum gb_measure { GB_MAX_ABS = 0, GB_MEAN_ABS = 1, GB_HELLINGER = 2, GB_JS = 3 }
  *            stored as 32-bit inverse-CDF thresholds; the sweep is integer work (gather, index,
  *            compare) with 32-bit draws.  Applies when every sampled variable is binary with at
  *            most 256 joint configurations of its free neighbours (gb_model_table_mode). */
-/*   GB_HYBRID per variable: binary variables with at most 65536 joint configurations of their free
+/*   GB_HYBRID per variable: variables of cardinality <= 4 with at most 65536 joint configurations of their free
  *            neighbours are sampled from threshold tables as in GB_TABLE (float64 conditional per
- *            configuration, 32-bit draws), every other variable by the GB_F64 path (53-bit draws) —
+ *            configuration, stored as card - 1 cumulative 32-bit inverse-CDF thresholds; 32-bit draws, value =
+ *            number of thresholds the draw exceeds), every other variable by the GB_F64 path (53-bit draws) —
  *            reference float64 arithmetic throughout, for models GB_TABLE rejects (collapsed variants
- *            with wide blankets, mixed cardinalities).  Models with a cardinality above 4 run as GB_F64. */
+ *            with wide blankets, ternary / quaternary variables).  When every sampled variable has a table the whole
+ *            model runs on the integer kernels.  Models with a cardinality above 4 run as GB_F64. */
 /*   GB_TABLE_BITS the arithmetic and the law of GB_TABLE (float64 conditional per configuration, 32-bit thresholds,
  *            32-bit draws) on chain state packed one bit per chain, updated 32 chains at a time with bit-sliced
  *            logic (csrc/bits.cuh).  Applies when every sampled variable is binary with at most 4 free neighbours,
@@ -117,9 +119,11 @@ int gb_model_hybrid_mask(const gb_model* m, int32_t* mask_out);
 int gb_model_table_mode(gb_model* m, int32_t* ok_out, int64_t* n_thresholds_out);
 /* whether GB_TABLE_BITS applies to this model */
 int gb_model_bits_mode(const gb_model* m, int32_t* ok_out);
-/* the tabulated thresholds of one sampled variable (builds the tables on first use): value 0 is
- * drawn iff the 32-bit draw <= threshold[configuration]; configuration = sum(state[nbr_i] * stride_i)
- * over the variable's free neighbours in ascending id order.  Pass out = NULL to query n. */
+/* the tabulated thresholds of one sampled variable (builds the tables on first use): card - 1 cumulative thresholds
+ * per configuration, out[configuration * (card - 1) + j] = the largest 32-bit draw that still selects a value <= j, so
+ * the value drawn is the number of thresholds the draw exceeds (binary: value 0 iff draw <= threshold[configuration]);
+ * configuration = sum(state[nbr_i] * stride_i) over the variable's free neighbours in ascending id order.
+ * Pass out = NULL to query n = configurations * (card - 1). */
 int gb_model_thresholds(gb_model* m, int32_t var, int32_t* n_out, uint32_t* out);
 
 /* (*GibbsCollapsed).Collapse (sampler/gibbs-collapsed.go:98-314) as a pure function: returns a NEW

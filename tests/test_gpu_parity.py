@@ -445,7 +445,9 @@ def test_resident_launch_chunking_keeps_the_window_schedule(res, monkeypatch):
 @pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
 @pytest.mark.parametrize("name,evid,collapse", [("Pedigree_11.uai", True, None), ("Pedigree_11.uai", True, "random"),
                                                 ("Promedus_11.uai", True, "random"), ("Grids_11.uai", False, None),
-                                                ("dv-rel_1.uai", True, None), ("ObjectDetection_11.uai", False, None)])
+                                                ("dv-rel_1.uai", True, None), ("ObjectDetection_11.uai", False, None),
+                                                ("Pedigree_11.uai", False, None), ("Pedigree_11.uai", False, "random"),
+                                                ("dv-rel_1.uai", False, None)])
 def test_hybrid_sweep_bitexact(res, name, evid, collapse, per_colour):
     """GB_HYBRID: tabulated variables (32-bit draws against float64 thresholds) and log-sum-exp variables
     (53-bit draws) in one sweep, on plain models and collapsed variants (wide blankets), both launch paths,
@@ -459,8 +461,12 @@ def test_hybrid_sweep_bitexact(res, name, evid, collapse, per_colour):
     order, _ = dm.schedule()
     if name.startswith("ObjectDetection"):
         assert not mask.any()  # cardinality 11: hybrid == f64
-    elif name.startswith("Grids"):
+    elif name.startswith("Grids") or (not collapse and not evid):
+        # Pedigree_11 (23 ternary variables) and dv-rel_1 (cardinalities up to 4) WITHOUT evidence: every sampled variable
+        # is tabulated (card - 1 cumulative thresholds), so the whole model runs on the integer kernels
         assert mask[order].all()
+        if not name.startswith("Grids"):
+            assert (dm.cards[order] > 2).any()
     else:
         assert mask[order].any()
     if collapse:  # the variant's wide-blanket variables: more than 256 configurations still tabulated, or log-sum-exp
@@ -509,6 +515,64 @@ def test_hybrid_all_table_variants_run_on_the_table_kernel(res, monkeypatch):
     ost, ocounts = samp.sweep_run(order, 77, 16, out[0][0], 0, 7, record=True, var_bits=np.where(mask, 32, 53))
     assert np.array_equal(ost, out[0][1])
     assert np.array_equal(ocounts, out[0][2].astype(np.float64))
+
+
+def test_hybrid_ternary_tables(res, monkeypatch):
+    """table mode for cardinality 3 / 4 (Pedigree_11 without evidence: 23 ternary variables): (a) the card - 1 cumulative
+    thresholds of a configuration are exactly the reference's inverse CDF (sampler.go:107-123) on the 32-bit grid;
+    (b) the resident table kernel (binary fast path + ternary path, histories of ternary variables in global memory)
+    gives the states, counts and half-window histograms of the hybrid log-sum-exp kernels and of the oracle."""
+    dm, om = load_pair(res, "Pedigree_11.uai", False)
+    samp = oracle.Sampler(oracle.Generator(3), om, collapsed=True)
+    order, _ = dm.schedule()
+    cards = dm.cards
+    mask = dm.hybrid_mask()
+    assert mask[order].all()
+    ternary = [int(v) for v in order if cards[v] == 3]
+    assert len(ternary) == 23
+
+    def select(e, u):
+        r = (u * 2.0 ** -32) * e.sum()
+        for k in range(len(e) - 1):
+            if r <= e[k]:
+                return k
+            r -= e[k]
+        return len(e) - 1
+
+    rng = np.random.default_rng(8)
+    for v in ternary[:6]:
+        nb = [u for u in samp.neighbors(v) if u != v and dm.fixed[u] < 0]
+        n_cfg = int(np.prod([cards[u] for u in nb]))
+        thr = dm.thresholds(v).reshape(n_cfg, 2)
+        assert (thr[:, 0] <= thr[:, 1]).all()
+        for cfg in rng.choice(n_cfg, size=min(n_cfg, 12), replace=False):
+            st = np.zeros(dm.n_vars, dtype=np.int32)
+            rem = int(cfg)
+            for u in nb:
+                st[u] = rem % cards[u]
+                rem //= cards[u]
+            e = samp.conditional(v, st)
+            for t in thr[cfg]:
+                for u in {int(t), min(int(t) + 1, 2 ** 32 - 1), 0, 2 ** 32 - 1}:
+                    assert select(e, u) == int((u > thr[cfg]).sum()), (v, cfg, u)
+    out = []
+    for knob in (None, "1"):
+        if knob:
+            monkeypatch.setenv("GB_HYBRID_NO_TAB_KERNEL", knob)
+        ch = gb.Chains(dm, 40, seed=5, first_chain_id=8, precision=gb.HYBRID, history=True, device=0)
+        st0 = ch.get_state(0, 40)
+        ch.advance(8)
+        out.append((st0, ch.get_state(0, 40), ch.group_counts(0), ch.group_history(0, 40), ch.convergence(gb.HELLINGER)))
+    monkeypatch.delenv("GB_HYBRID_NO_TAB_KERNEL")
+    for a, b in zip(out[0][:4], out[1][:4]):
+        assert np.array_equal(a, b)
+    assert np.allclose(out[0][4], out[1][4], rtol=1e-12)
+    ost, ocounts = samp.sweep_run(order, 5, 8, out[0][0], 0, 9, record=True, var_bits=np.where(mask, 32, 53))
+    assert np.array_equal(ost, out[0][1])
+    assert np.array_equal(ocounts, out[0][2].astype(np.float64))
+    offs = np.concatenate([[0], np.cumsum(cards)])
+    for v in ternary:
+        assert (out[0][3][:, offs[v]:offs[v + 1], :].sum(1) == 4).all()  # every half window holds cw / 2 samples
 
 
 # ------------------------------------------------------------------ synthetic models: every cardinality bucket of the LSE kernels
