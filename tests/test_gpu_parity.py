@@ -465,8 +465,8 @@ def test_hybrid_sweep_bitexact(res, name, evid, collapse, per_colour):
         # Pedigree_11 (23 ternary variables) and dv-rel_1 (cardinalities up to 4) WITHOUT evidence: every sampled variable
         # is tabulated (card - 1 cumulative thresholds), so the whole model runs on the integer kernels
         assert mask[order].all()
-        if not name.startswith("Grids"):
-            assert (dm.cards[order] > 2).any()
+        if name.startswith("Pedigree"):
+            assert (dm.cards[order] == 3).sum() == 23
     else:
         assert mask[order].any()
     if collapse:  # the variant's wide-blanket variables: more than 256 configurations still tabulated, or log-sum-exp
@@ -639,6 +639,21 @@ def test_synthetic_mixed_cardinalities_bitexact(label, cards, n_pair, n_triple, 
     ost, ocounts = samp.sweep_run(order, seed, first, st0, 0, n_sweeps, bits=53, record=True)
     assert np.array_equal(ost, ch.get_state(0, n_chains)), label
     assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64)), label
+    if max(cards) <= 4:
+        # hybrid mode: cardinalities 2, 3 and 4 sampled from cumulative threshold tables (32-bit draws), wide records
+        # (more than 256 configurations) included; with every variable tabulated the resident table kernel runs it
+        mask = dm.hybrid_mask()
+        assert mask[order].any() and (cards_a[order][mask[order] > 0] == 4).any()
+        hy = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.HYBRID, history=True, device=0, per_colour=per_colour)
+        hy.set_state(0, st0)
+        hy.advance(4)
+        hst, hcounts = samp.sweep_run(order, seed, first, st0, 0, 5, record=True, var_bits=np.where(mask, 32, 53))
+        assert np.array_equal(hst, hy.get_state(0, n_chains)), label
+        assert np.array_equal(hcounts, hy.group_counts(0).astype(np.float64)), label
+        hh = hy.group_history(0, n_chains)
+        offs = np.concatenate([[0], np.cumsum(cards_a)])
+        for v in order:
+            assert (hh[:, offs[v]:offs[v + 1], :].sum(1) == 2).all(), (label, int(v))
     # Rao-Blackwell bins of the same trajectory
     rb = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=gb.F64, device=0, per_colour=per_colour,
                    rao_blackwell=True)
