@@ -141,11 +141,14 @@ def small_model_rates(gb, dev, sweeps=500):
     on-chip resident: these are issue/latency-bound, not HBM-bound, and are not the headline)"""
     res = os.path.join(ROOT, "tests", "golden", "res")
     out = {}
-    for name, evid, n_chains in (("Promedus_11.uai", True, 4096), ("Pedigree_11.uai", True, 8192), ("ObjectDetection_11.uai", False, 8192)):
+    for name, evid, n_chains in (("Promedus_11.uai", True, 4096), ("Pedigree_11.uai", True, 8192), ("Pedigree_11.uai", False, 8192),
+                                 ("ObjectDetection_11.uai", False, 8192)):
         try:
             m = gb.Model.from_uai(os.path.join(res, name), use_evidence=evid, device=dev)
             n_free = len(m.schedule()[0])
-            modes = [("f32", gb.F32), ("f64", gb.F64)] + ([("table", gb.TABLE)] if m.table_mode()[0] else [])
+            # hybrid = the hosts' default precision: threshold tables where a variable qualifies (cardinality <= 4), float64
+            # log-sum-exp elsewhere (ObjectDetection_11: cardinality 11, so hybrid == f64 there)
+            modes = [("f32", gb.F32), ("f64", gb.F64), ("hybrid", gb.HYBRID)] + ([("table", gb.TABLE)] if m.table_mode()[0] else [])
             entry = {"chains": n_chains, "free_vars": n_free}
             for label, prec in modes:
                 ch = gb.Chains(m, n_chains, seed=1, precision=prec, device=dev)
@@ -155,6 +158,54 @@ def small_model_rates(gb, dev, sweeps=500):
             out[name.replace(".uai", "") + ("+evid" if evid else "")] = entry
         except Exception as e:  # never lose the headline line over a secondary number
             out[name] = {"error": str(e)[:200]}
+    return out
+
+
+def config3_collapsed(gb, gbd, torch, dist, dev, rank, world, total_chains=65536, cw=2000, rounds=3):
+    """BASELINE.json configs[3]: ObjectDetection_11 (cardinality 11), collapsed Gibbs, chains sharded over the N GPUs.
+    Two collapsed variants (one collapsed variable each, gibbs-collapsed.go:98-314) x total_chains / 2 replicas; one
+    "round" is the loop body of cmd/root.go:475-539 + 640-668: AdvanceChain of every chain (cw + 1 recorded sweeps with
+    half-window histograms), MergeChains and ChainConvergence over ALL ranks (in-library NCCL), read on rank 0.
+    Wall time per round, max over ranks."""
+    res = os.path.join(ROOT, "tests", "golden", "res")
+    out = {"problem": "ObjectDetection_11", "sampler": "collapsed", "variants": 2, "chains_total": total_chains, "cw": cw, "rounds": rounds}
+    try:
+        m = gb.Model.from_uai(os.path.join(res, "ObjectDetection_11.uai"), device=dev)
+        picks = [v for v in range(m.n_vars) if m.blanket_size(v) <= 5][:2]  # small blankets: the new factor stays in shared memory
+        variants = [m.collapse(v)[0] for v in picks]
+        out["collapsed_variables"] = [int(v) for v in picks]
+        per_variant = total_chains // 2
+        first, n_local = gbd.shard(per_variant, world, rank)
+        stride = (per_variant + 7) // 8 * 8
+        for label, prec in (("f32", gb.F32), ("hybrid_f64", gb.HYBRID)):
+            ch = gb.Chains(variants[0], n_local, seed=3, first_chain_id=first, precision=prec, history=True, device=dev)
+            ch.add_group(variants[1], n_local, stride + first)
+            gbd.attach(ch, dist)
+            ch.burnin(200)
+            ch.advance(cw)
+            ch.merged_marginals()
+            ch.synchronize()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.time()
+            for _ in range(rounds):
+                ch.advance(cw)
+                merged, col = ch.merged_marginals()
+                conv = ch.convergence(gb.HELLINGER, merged)
+            ch.synchronize()
+            secs = time.time() - t0
+            if dist is not None:
+                t = torch.tensor([secs], device=f"cuda:{dev}", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                secs = float(t.item())
+            n_free = sum(len(v.schedule()[0]) for v in variants) / 2.0
+            updates = rounds * (cw + 1) * n_free * total_chains
+            out[label] = {"updates_per_sec": updates / secs, "updates_per_sec_per_gpu": updates / secs / world,
+                          "seconds_per_round": secs / rounds, "us_per_sweep": 1e6 * secs / (rounds * (cw + 1)),
+                          "chains_per_gpu": 2 * n_local, "finite_scores": bool(np.isfinite(conv).all())}
+            del ch
+    except Exception as e:  # never lose the headline line over a secondary number
+        out["error"] = str(e)[:300]
     return out
 
 
@@ -411,9 +462,15 @@ def run_native(args):
         except Exception:
             pass
 
+    # ---------------- BASELINE configs[3] at this N (collective: every rank takes part)
+    cfg3 = None
+    if not args.no_secondary:
+        del chains
+        chains = None
+        cfg3 = config3_collapsed(gb, gbd, torch, dist, dev, rank, world)
+
     if rank != 0:
         if dist is not None:
-            del chains
             dist.destroy_process_group()
         return
 
@@ -421,7 +478,6 @@ def run_native(args):
     # the same workload, and the bundled UAI problems of BASELINE.json configs[1..3] at their chain counts
     secondary = None
     if world == 1 and not args.no_secondary:
-        del chains
         secondary = {}
         if args.precision == "bits":
             secondary["table_u8"] = other_rate(gb, model, args, dev, n_vars, peak, gb.TABLE, "k_sweep_tab<64,4,false,3>", 3)
@@ -460,6 +516,9 @@ def run_native(args):
         line["strong"] = strong
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if cfg3 is not None:
+        secondary = secondary or {}
+        secondary["config3_objectdetection_collapsed"] = cfg3
     if secondary is not None:
         line["secondary"] = secondary
     emit(line)
