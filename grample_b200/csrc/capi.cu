@@ -634,25 +634,32 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
     constexpr size_t kSmemPerSm = 220 * 1024, kSmemPerCta = 200 * 1024;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    // 1) tables staged in shared memory, if every CTA of the launch is still co-resident (these models
-    //    expose little parallelism per colour, so a second wave of CTAs costs more than LDS tables gain)
-    if (!no_ts)
+    // 1) tables staged in shared memory.  Preferably with every CTA of the launch co-resident (these models expose little
+    //    parallelism per colour, so chains per CTA grow only as far as that needs); a population too large for that runs
+    //    64 chains per CTA in several waves — a CTA carries its chains through the whole round on its own, so waves cost
+    //    only the partly filled last one, far less than reading the tables through L1 (BASELINE configs[3] at 32768
+    //    chains per GPU: 217 -> us per sweep)
+    if (!no_ts) {
+        ResidentPlan waves;
         for (int ch : {8, 16, 32, 64}) {
             if (g.n_pad % ch) continue;
             const size_t smem = base(ch) + tab_bytes;
             if (smem > kSmemPerCta) break;
             const int64_t per_sm = std::min<int64_t>(8, (int64_t)(kSmemPerSm / (smem + 1024)));
+            waves.ch = ch; waves.smem = smem; waves.ts = true;
+            waves.n_stage = (int32_t)(((size_t)h.log_tab.size() + 3) & ~(size_t)3);
             if (ch < 64 && ctas(ch) > per_sm * sms) continue;
             if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
-            p.ch = ch; p.smem = smem; p.ts = true;
-            p.n_stage = (int32_t)(((size_t)h.log_tab.size() + 3) & ~(size_t)3);
-            return p;
+            return waves;
         }
+        if (waves.ch && ctas(waves.ch) >= 2 * sms) return waves;  // (at least a couple of CTAs per SM: not a tiny launch that merely failed to fit)
+    }
     // 1b) one-thread-per-chain kernels (cardinality >= 8): stage the longest PREFIX of the tables that fits and ends on
     //     a factor boundary.  A collapsed variant keeps the model's small factors first and appends the large factor
     //     over the collapsed variable's blanket (up to 11^6 entries on ObjectDetection_11), so every small factor is
     //     served from shared memory and only the large one goes through L1/L2.
-    if (!no_ts && h.max_card >= 8)
+    if (!no_ts && h.max_card >= 8) {
+        ResidentPlan waves;
         for (int ch : {8, 16, 32, 64}) {
             if (g.n_pad % ch) continue;
             if (base(ch) + 4096 > kSmemPerCta) break;
@@ -665,11 +672,13 @@ ResidentPlan resident_plan(const gb_chains* c, const Group& g) {
             if (n == 0) break;
             const size_t smem = base(ch) + 16 + (size_t)((n + 3) & ~(int64_t)3) * real_bytes;
             const int64_t per_sm = std::min<int64_t>(8, (int64_t)(kSmemPerSm / (smem + 1024)));
+            waves.ch = ch; waves.smem = smem; waves.ts = false; waves.n_stage = (int32_t)n;
             if (ch < 64 && ctas(ch) > per_sm * sms) continue;
             if ((int64_t)(g.n_pad / ch) > per_sm * sms) break;
-            p.ch = ch; p.smem = smem; p.n_stage = (int32_t)n;
-            return p;
+            return waves;
         }
+        if (waves.ch && ctas(waves.ch) >= 2 * sms) return waves;
+    }
     // 2) tables through L1: few chains per CTA = many CTAs = better SM fill and latency hiding; grow the
     //    CTA's chain count only when that would exceed ~16 CTAs per SM
     for (int ch : {8, 16, 32}) {

@@ -553,6 +553,9 @@ __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t t
     }
 }
 
+__device__ __forceinline__ void hist_add(uint16_t* s_hist, const DevGroup& g, const int total_card, const int half,
+                                         const int entry, const int CH, const int cc, const int lchain);
+
 // One launch = one colour of one group.  Work item = (variable of the colour, quad of 4 chains);
 // consecutive threads take consecutive quads of the same variable.
 template <typename Real, int MAXC, int CW, bool RB = false>  // RB: Rao-Blackwell bins instead of counts (g.rb is set)
@@ -612,10 +615,7 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
             if (hist_half >= 0 && g.hist) {
 #pragma unroll
                 for (int ci = 0; ci < 4; ci++)
-                    if (ci < nvalid) {
-                        uint16_t* h = g.hist + ((size_t)hist_half * m.total_card + coff + x[ci]) * g.n_pad + 4 * q + ci;
-                        *h = (uint16_t)(*h + 1);
-                    }
+                    if (ci < nvalid) hist_add(nullptr, g, m.total_card, hist_half, coff + x[ci], 0, 0, 4 * q + ci);
             }
         }
     }
@@ -630,8 +630,11 @@ __device__ __forceinline__ void hist_add(uint16_t* s_hist, const DevGroup& g, co
         uint16_t* h = s_hist + ((size_t)half * total_card + entry) * CH + cc;
         *h = (uint16_t)(*h + 1);
     } else {
-        uint16_t* h = g.hist + ((size_t)half * total_card + entry) * g.n_pad + lchain;
-        *h = (uint16_t)(*h + 1);
+        // global memory: a fire-and-forget 32-bit reduction on the word that holds this chain's 16-bit counter (two
+        // chains per word; a half window holds < 65536 samples, so the low lane never carries into the high one) —
+        // no load to wait for, unlike a 2-byte read-modify-write
+        unsigned int* w = reinterpret_cast<unsigned int*>(g.hist + ((size_t)half * total_card + entry) * g.n_pad + (lchain & ~1));
+        atomicAdd(w, 1u << (16 * (lchain & 1)));
     }
 }
 // Table kernels: the 8 chains of a work unit are contiguous, and a binary variable has two histogram rows, so the 16
@@ -651,6 +654,13 @@ __device__ __forceinline__ void add_row16(uint4* row, const uint4 inc) {
     h.x += inc.x; h.y += inc.y; h.z += inc.z; h.w += inc.w;
     *row = h;
 }
+__device__ __forceinline__ void red_row16(uint16_t* row, const uint4 inc) {  // the same on global memory, without the load
+    unsigned int* w = reinterpret_cast<unsigned int*>(row);
+    if (inc.x) atomicAdd(w, inc.x);
+    if (inc.y) atomicAdd(w + 1, inc.y);
+    if (inc.z) atomicAdd(w + 2, inc.z);
+    if (inc.w) atomicAdd(w + 3, inc.w);
+}
 __device__ __forceinline__ void hist_add8_binary(uint16_t* s_hist, const DevGroup& g, const int total_card, const int half,
                                                  const int coff, const int CH, const int cc0, const int lchain0,
                                                  const uint32_t ones, const uint32_t zeros) {
@@ -660,8 +670,8 @@ __device__ __forceinline__ void hist_add8_binary(uint16_t* s_hist, const DevGrou
         add_row16(reinterpret_cast<uint4*>(r0 + CH), spread_bits16(ones));
     } else {
         uint16_t* r0 = g.hist + ((size_t)half * total_card + coff) * g.n_pad + lchain0;
-        add_row16(reinterpret_cast<uint4*>(r0), spread_bits16(zeros));
-        add_row16(reinterpret_cast<uint4*>(r0 + g.n_pad), spread_bits16(ones));
+        red_row16(r0, spread_bits16(zeros));
+        red_row16(r0 + g.n_pad, spread_bits16(ones));
     }
 }
 __device__ __forceinline__ uint16_t* hist_begin(uint8_t* smem, const int32_t hist_off, const DevGroup& g, const int total_card,
