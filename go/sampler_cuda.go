@@ -71,14 +71,9 @@ func chainFlags() C.uint32_t {
 	return f
 }
 
-// chainPrecision: the Rao-Blackwell estimator accumulates log-sum-exp conditionals, so it runs GB_F64
-// unless the caller chose GB_F32.
-func chainPrecision() C.int {
-	if RaoBlackwell && Precision != C.GB_F32 {
-		return C.GB_F64
-	}
-	return C.int(Precision)
-}
+// chainPrecision: the Rao-Blackwell estimator is available under every precision the shim offers
+// (tabulated conditionals are read back from their thresholds).
+func chainPrecision() C.int { return C.int(Precision) }
 
 func lastErr(what string) error { return errors.Errorf("%s: %s", what, C.GoString(C.gb_last_error())) }
 

@@ -245,8 +245,8 @@ def _sample(args, out, mon, start, dist=None, rank=0, world=1):
         # ONE default for every host of the boundary (this CLI, the C++ mirror grample.hpp, the Go shim): GB_HYBRID =
         # the reference's float64 arithmetic throughout — variables whose conditional can be tabulated are sampled from
         # float64-derived thresholds, the rest by the float64 log-sum-exp kernels.  float32 is an explicit opt-in
-        # (--precision f32).  The Rao-Blackwell estimator accumulates log-sum-exp conditionals, hence GB_F64 with it.
-        args.precision = "f64" if args.rao_blackwell else "hybrid"
+        # (--precision f32).  The Rao-Blackwell estimator works under it too (tabulated conditionals are read back from the thresholds).
+        args.precision = "hybrid"
         out.write("Precision: %s\n" % args.precision)
     prec = {"f64": F64, "f32": F32, "table": TABLE, "hybrid": HYBRID}[args.precision]
     n, cards, fixed = mod.n_vars, mod.cards, mod.fixed

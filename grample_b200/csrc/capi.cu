@@ -452,6 +452,9 @@ void launch_tab_variant(gb_chains* c, Group& g, int col, int32_t n, int record, 
 }
 
 void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist_half) {
+    if (g.dev.rb)
+        throw gb::Err("GB_CHAINS_RAO_BLACKWELL under GB_TABLE needs a model small enough for the shared-memory-resident table kernel "
+                      "(the per-colour table kernel keeps only threshold halves): use GB_HYBRID");
     const bool hist = g.d_hist != nullptr && hist_half >= 0;
     // GB_TAB_PF=0 selects the register-prefetch variant (kept for A/B measurements; default: cp.async ring, depth 3)
     static const bool reg_prefetch = std::getenv("GB_TAB_PF") && std::atoi(std::getenv("GB_TAB_PF")) == 0;
@@ -1515,8 +1518,8 @@ int gb_chains_create(int32_t n_groups, gb_model* const* models, const int32_t* c
     if (n_groups < 1) throw gb::Err("at least one chain group is required");
     if (precision != GB_F64 && precision != GB_F32 && precision != GB_TABLE && precision != GB_HYBRID && precision != GB_TABLE_BITS)
         throw gb::Err("unknown precision");
-    if ((flags & GB_CHAINS_RAO_BLACKWELL) && precision != GB_F64 && precision != GB_F32)
-        throw gb::Err("GB_CHAINS_RAO_BLACKWELL needs precision GB_F64 or GB_F32 (the estimator accumulates the log-sum-exp conditionals)");
+    if ((flags & GB_CHAINS_RAO_BLACKWELL) && precision == GB_TABLE_BITS)
+        throw gb::Err("GB_CHAINS_RAO_BLACKWELL is not available under GB_TABLE_BITS (its thresholds are bit-sliced): use GB_TABLE or GB_HYBRID");
     require_device(device);
     auto c = std::make_unique<gb_chains>();
     c->device = device;

@@ -501,9 +501,17 @@ __device__ __forceinline__ int lse_update_one(const DevModel& m, const Real* __r
 // neighbours) is updated from the table — float64 conditional evaluated once per configuration, 32-bit
 // draw, same tie rule and Philox fields as the table kernels — and every other variable by the float64
 // log-sum-exp path.  One variable x 4 consecutive chains; tpo = the variable's offset in DevTab::tprog.
+// Rao-Blackwell bins from a threshold table (GB_CHAINS_RAO_BLACKWELL under GB_TABLE / GB_HYBRID): a threshold is the
+// cumulative float64 conditional on the 32-bit grid, T_j = floor(P(value <= j) 2^32), so the bins take p_0 = T_0 / 2^32,
+// p_k = (T_k - T_{k-1}) / 2^32, p_last = 1 - T_last / 2^32, each rounded to the bins' unit of 2^-24 like RbRecord rounds
+// the log-sum-exp weights: floor((T + 128) / 256) = floor(p 2^24 + 1/2), the same integer the float64 value rounds to
+// (binary variables: identical bins; cumulative differences of floors may be one grid step off, a unit now and then)
+__device__ __forceinline__ uint32_t rb_units(const uint64_t p32) { return (uint32_t)((p32 + 128u) >> 8); }
+
 __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t tpo, const uint8_t* row, const uint32_t stride,
                                                 const int v, const int card, const uint32_t chain0, const uint32_t sweep,
-                                                const uint32_t seed_lo, const uint32_t seed_hi, int (&x)[4]) {
+                                                const uint32_t seed_lo, const uint32_t seed_hi, int (&x)[4],
+                                                unsigned long long* __restrict__ rb_bins = nullptr, const int rb_valid = 0) {
     const int32_t* __restrict__ tp = t.tprog + tpo;
     const int nn = __ldg(tp), thr_off = __ldg(tp + 1);
     uint32_t idx[4] = {0u, 0u, 0u, 0u};
@@ -528,7 +536,16 @@ __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t t
             const uint32_t u = (((wa[ci >> 1] >> (16 * (ci & 1))) & 0xffffu) << 16) | ((wb[ci >> 1] >> (16 * (ci & 1))) & 0xffffu);
             const uint32_t* __restrict__ T = t.thr + thr_off + idx[ci] * (uint32_t)(card - 1);
             int val = 0;
-            for (int j = 0; j < card - 1; j++) val += u > __ldg(T + j) ? 1 : 0;
+            uint64_t prev = 0;  // cumulative probability below the current value, in units of 2^-32
+            for (int j = 0; j < card - 1; j++) {
+                const uint32_t Tj = __ldg(T + j);
+                val += u > Tj ? 1 : 0;
+                if (rb_bins && ci < rb_valid) {
+                    atomicAdd(rb_bins + j, (unsigned long long)rb_units((uint64_t)Tj - prev));
+                    prev = (uint64_t)Tj;
+                }
+            }
+            if (rb_bins && ci < rb_valid) atomicAdd(rb_bins + card - 1, (unsigned long long)rb_units(4294967296ull - prev));
             x[ci] = val;
         }
         return;
@@ -541,6 +558,16 @@ __device__ __forceinline__ void tab_update_quad(const DevTab& t, const int32_t t
         hi[ci] = (wa[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
         x[ci] = hi[ci] > (T[ci] >> 16) ? 1 : 0;
         tie |= hi[ci] == (T[ci] >> 16);
+    }
+    if (rb_bins) {
+        unsigned long long q0 = 0;
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++)
+            if (ci < rb_valid) q0 += rb_units((uint64_t)T[ci]);
+        if (rb_valid > 0) {
+            atomicAdd(rb_bins, q0);
+            atomicAdd(rb_bins + 1, (unsigned long long)min(rb_valid, 4) * 16777216ull - q0);
+        }
     }
     if (tie) {  // draw > threshold <=> high halves equal and lo16 > (T & 0xffff)
         const Philox4 b = philox_wide((uint32_t)v, sweep, chain0 >> 3, kTagDraw16Lo, seed_lo, seed_hi);
@@ -580,7 +607,8 @@ k_sweep_colour(const DevModel m, const DevGroup g, const int32_t* __restrict__ v
         int x[4];
         const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
         if (tpo >= 0)
-            tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x);
+            tab_update_quad(t, tpo, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x,
+                            (RB && record) ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - 4 * q);
         else {
             const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - 4 * q);
             lse_update_quad<Real, MAXC, CW, true, Rec>(m, tab, g.state + 4 * (size_t)q, (uint32_t)g.n_pad, v, card, chain0, sweep,
@@ -809,7 +837,8 @@ k_sweep_resident(const DevModel m, const DevGroup g, const int32_t* __restrict__
                     int x[4];
                     const int32_t tpo = hybrid ? __ldg(t.tp_off + v) : -1;
                     if (tpo >= 0)
-                        tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x);
+                        tab_update_quad(t, tpo, s_state + 4 * q, (uint32_t)CH, v, card, chain0, sweep, g.seed_lo, g.seed_hi, x,
+                                        (RB && record) ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain);
                     else {
                         const Rec rec(record ? g.counts + __ldg(m.card_off + v) : nullptr, g.n_chains - lchain);
                         lse_update_quad<Real, MAXC, (CW == 0 ? 1 : CW), !TS, Rec>(m, tab, s_state + 4 * q, (uint32_t)CH, v, card, chain0,
@@ -1274,10 +1303,19 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                             const uint32_t u = (((wa[i >> 1] >> (16 * (i & 1))) & 0xffffu) << 16) | ((wb[i >> 1] >> (16 * (i & 1))) & 0xffffu);
                             const uint32_t* __restrict__ T = t.thr + hd.y + idx * (uint32_t)(card - 1);
                             int val = 0;
-                            for (int k = 0; k < card - 1; k++) val += u > __ldg(T + k) ? 1 : 0;
+                            uint64_t prev = 0;
+                            for (int k = 0; k < card - 1; k++) {
+                                const uint32_t Tk = __ldg(T + k);
+                                val += u > Tk ? 1 : 0;
+                                if (g.rb && i < nvalid) {
+                                    atomicAdd(g.counts + hd.w + k, (unsigned long long)rb_units((uint64_t)Tk - prev));
+                                    prev = (uint64_t)Tk;
+                                }
+                            }
+                            if (g.rb && i < nvalid) atomicAdd(g.counts + hd.w + card - 1, (unsigned long long)rb_units(4294967296ull - prev));
                             outb[i >> 2] |= (uint32_t)val << (8 * (i & 3));
                             if (i < nvalid) {
-                                atomicAdd(&s_counts[hd.w + val], 1u);
+                                if (!g.rb) atomicAdd(&s_counts[hd.w + val], 1u);
                                 if (hist_half >= 0 && g.hist)  // (the shared-memory histograms hold the ones of binary variables only)
                                     hist_add(nullptr, g, m.total_card, hist_half, hd.w + val, CH, 0, lchain + i);
                             }
@@ -1319,8 +1357,19 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                     const int nvalid = max(0, min(8, g.n_chains - lchain));
                     const uint32_t vmask = (nvalid >= 8) ? 0xffu : ((1u << nvalid) - 1u);
                     const int ones = __popc(xbits & vmask);
-                    if (ones) atomicAdd(&s_counts[hd.w + 1], (unsigned)ones);
-                    if (nvalid - ones) atomicAdd(&s_counts[hd.w], (unsigned)(nvalid - ones));
+                    if (g.rb) {  // Rao-Blackwell bins: the conditionals themselves (thresholds), not the draws
+                        unsigned long long q0 = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (i < nvalid) q0 += rb_units((uint64_t)T[i]);
+                        if (nvalid > 0) {
+                            atomicAdd(g.counts + hd.w, q0);
+                            atomicAdd(g.counts + hd.w + 1, (unsigned long long)nvalid * 16777216ull - q0);
+                        }
+                    } else {
+                        if (ones) atomicAdd(&s_counts[hd.w + 1], (unsigned)ones);
+                        if (nvalid - ones) atomicAdd(&s_counts[hd.w], (unsigned)(nvalid - ones));
+                    }
                     if (hist_half >= 0 && g.hist) {
                         if (s_hist)
                             add_row16(reinterpret_cast<uint4*>(s_hist + ((size_t)hist_half * t.n_order + c0 + j) * CH + 8 * q),

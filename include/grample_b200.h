@@ -74,7 +74,9 @@ enum gb_precision { GB_F64 = 0, GB_F32 = 1, GB_TABLE = 2, GB_HYBRID = 3, GB_TABL
  * the conditional it sampled from, p_k = e[k] / sum(e) (gibbs-simple.go:239-258 weights), to every bin of the variable
  * instead of Marginal[value] += 1 (chain.go:235).  Same expectation, lower variance.  Bins are 64-bit fixed point in
  * units of 2^-24 (gb_chains_group_counts returns them raw); merged marginals, TotalSampleCount, histories and
- * convergence scores keep their meaning.  GB_F64 / GB_F32 only. */
+ * convergence scores keep their meaning.  GB_F64 / GB_F32: the floored log-sum-exp weights; GB_TABLE / GB_HYBRID: the
+ * same conditional read back from the thresholds, p_0 = T_0 / 2^32, p_k = (T_k - T_{k-1}) / 2^32 (within 2^-32 of
+ * the float64 value).  Not under GB_TABLE_BITS, nor for GB_TABLE models too large for the resident table kernel. */
 #define GB_CHAINS_RAO_BLACKWELL 4u
 
 const char* gb_last_error(void);

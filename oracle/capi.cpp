@@ -607,7 +607,7 @@ int orc_sweep_run_mixed(void* sampler, const int* order, int n_order, unsigned l
     size_t nv = h->model->vars.size();
     for (int c = 0; c < n_chains; c++)
         sweep_chain(*h->simple, ord, seed, chain0 + (unsigned)c, sweep0, n_sweeps, 53, record != 0,
-                    states + (size_t)c * nv, off, counts, var_bits);
+                    states + (size_t)c * nv, off, counts, var_bits, record == 2);  // record 2 = Rao-Blackwell bins
     ORC_END
 }
 

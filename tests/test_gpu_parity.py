@@ -733,11 +733,57 @@ def test_rao_blackwell_lowers_the_error_at_equal_samples(res):
         assert errs[1] < 0.95 * errs[0], errs  # measured: 0.0213 -> 0.0187
 
 
-def test_rao_blackwell_rejects_table_precisions_and_scan(res):
+@pytest.mark.parametrize("name,evid,collapse,prec", [("Grids_11.uai", False, None, "table"), ("Grids_11.uai", False, None, "hybrid"),
+                                                     ("Pedigree_11.uai", False, None, "hybrid"), ("Promedus_11.uai", True, "random", "hybrid"),
+                                                     ("dv-rel_1.uai", True, None, "hybrid")])
+@pytest.mark.parametrize("per_colour", [False, True], ids=["resident", "per-colour"])
+def test_rao_blackwell_bins_from_threshold_tables(res, name, evid, collapse, prec, per_colour):
+    """GB_CHAINS_RAO_BLACKWELL under GB_TABLE / GB_HYBRID: a tabulated update adds the conditional read back from its
+    thresholds, p_0 = T_0 / 2^32, p_k = (T_k - T_{k-1}) / 2^32 (binary, ternary and wide variables; hybrid models mix
+    them with log-sum-exp variables).  Same trajectory as the plain run.  For a binary variable floor((T + 128) / 256) is
+    exactly the integer the oracle's float64 p_k 2^24 rounds to; a ternary variable's differences of floors and the
+    log-sum-exp variables' libm-vs-CUDA exp may be a unit off per update now and then."""
+    if prec == "table" and per_colour:
+        pytest.skip("the per-colour table kernel keeps threshold halves only: RB is refused there (checked below)")
+    dm, om = load_pair(res, name, evid)
+    samp = oracle.Sampler(oracle.Generator(1), om, collapsed=collapse is not None)
+    if collapse:
+        dm, v, _ = dm.collapse(-1, seed=11)
+        samp.collapse(v)
+    mask = dm.hybrid_mask()
+    order, _ = dm.schedule()
+    seed, first, n_chains, n_sweeps = 31, 8, 21, 5
+    p = gb.TABLE if prec == "table" else gb.HYBRID
+    plain = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=p, device=0, per_colour=per_colour)
+    st0 = plain.get_state(0, n_chains)
+    plain.sweep(n_sweeps)
+    rb = gb.Chains(dm, n_chains, seed=seed, first_chain_id=first, precision=p, device=0, per_colour=per_colour, rao_blackwell=True)
+    rb.sweep(n_sweeps)
+    assert np.array_equal(rb.get_state(0, n_chains), plain.get_state(0, n_chains))
+    var_bits = np.where(mask, 32, 53) if prec == "hybrid" else np.full(dm.n_vars, 32)
+    ost, obins = samp.sweep_run(order, seed, first, st0, 0, n_sweeps, record=2, var_bits=var_bits)
+    assert np.array_equal(ost, rb.get_state(0, n_chains))
+    bins = rb.group_counts(0).astype(np.float64)
+    offs = np.concatenate([[0], np.cumsum(dm.cards)])
+    diff = np.abs(bins - obins)
+    binary_tab = [v for v in order if dm.cards[v] == 2 and var_bits[v] == 32]
+    assert max(diff[offs[v]:offs[v + 1]].max() for v in binary_tab) <= 1.0  # (a threshold at an exact tie of the predicate)
+    assert diff.max() <= 8.0 + 0.05 * n_sweeps * n_chains, diff.max()
+    for v in order[:50]:  # every recorded update adds one unit of probability mass (2^24) up to rounding
+        assert abs(bins[offs[v]:offs[v + 1]].sum() - n_sweeps * n_chains * 2.0 ** 24) <= 4 * n_sweeps * n_chains
+    merged, _ = rb.merged_marginals()
+    expect = bins * 2.0 ** -24 + np.concatenate([np.full(c, n_chains / c) for c in dm.cards])
+    for v in order:  # (a collapsed variable is reported with its local marginal instead)
+        assert np.allclose(merged[offs[v]:offs[v + 1]], expect[offs[v]:offs[v + 1]], rtol=1e-12)
+
+
+def test_rao_blackwell_rejects_bit_sliced_and_per_colour_table_and_scan(res):
     dm, _ = load_pair(res, "Grids_11.uai", False)
-    for prec in (gb.TABLE, gb.HYBRID):
-        with pytest.raises(gb.GrampleError, match="RAO_BLACKWELL"):
-            gb.Chains(dm, 8, precision=prec, device=0, rao_blackwell=True)
+    with pytest.raises(gb.GrampleError, match="RAO_BLACKWELL"):
+        gb.Chains(dm, 32, precision=gb.TABLE_BITS, device=0, rao_blackwell=True)
+    big = gb.Chains(dm, 8, precision=gb.TABLE, device=0, rao_blackwell=True, per_colour=True)  # the per-colour table kernel
+    with pytest.raises(gb.GrampleError, match="RAO_BLACKWELL"):
+        big.sweep(1)
     ch = gb.Chains(dm, 8, precision=gb.F64, device=0, rao_blackwell=True)
     with pytest.raises(gb.GrampleError, match="RAO_BLACKWELL"):
         ch.scan(10)
@@ -1309,12 +1355,12 @@ def test_cli_sample_adaptive(res, tmp_path):
 
 def test_cli_precision_auto(res):
     """--precision auto = the one default of every host of the boundary: hybrid (float64 reference arithmetic, threshold
-    tables where a variable qualifies, float64 log-sum-exp elsewhere); float64 with the Rao-Blackwell estimator"""
+    tables where a variable qualifies, float64 log-sum-exp elsewhere), with or without the Rao-Blackwell estimator"""
     import io
 
     from grample_b200 import cli
     for argv, want in ((["-m", res("Grids_11.uai")], "hybrid"), (["-m", res("ObjectDetection_11.uai")], "hybrid"),
-                       (["-m", res("Grids_11.uai"), "--rao-blackwell"], "f64")):
+                       (["-m", res("Grids_11.uai"), "--rao-blackwell"], "hybrid")):
         args = cli.build_parser().parse_args(["sample"] + argv + ["-o", "-b", "200", "-w", "10", "-i", "20000", "--replicas", "8"])
         out = io.StringIO()
         final, _ = cli.sample(args, out)
