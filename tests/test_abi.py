@@ -85,6 +85,25 @@ def test_model_errors(res, tmp_path):
     # table larger than maxTabSize (function.go:77-79)
     with pytest.raises(gb.GrampleError):
         gb.Model.from_arrays([2] * 24, [-1] * 24, [0, 24], list(range(24)), [0, 1 << 24], np.ones(1 << 24), device=-1)
+    # a scope that names a variable twice: the reference reads both slots from the state (only the diagonal is reachable);
+    # the fast paths assume distinct scope variables, so it is refused with a clear message instead of sampled inconsistently
+    with pytest.raises(gb.GrampleError, match="appears twice"):
+        gb.Model.from_arrays([2, 2], [-1, -1], [0, 1, 3], [1, 0, 0], [0, 2, 6], [0.5, 0.5, 1, 2, 3, 4], device=-1)
+
+
+def test_table_programs_cover_cardinality_up_to_four(res):
+    """host side of table mode for cardinality 3 / 4 (function.go:180-202 index space): Pedigree_11 without evidence has 23
+    ternary variables; every sampled variable gets a threshold table, so GB_HYBRID runs it on the integer kernels; GB_TABLE
+    (binary only) and the bit-sliced mode still refuse it; Grids_11 qualifies for all three."""
+    ped = gb.Model.from_uai(res("Pedigree_11.uai"), device=-1)
+    order, _ = ped.schedule()
+    assert (ped.cards[order] == 3).sum() == 23
+    assert ped.hybrid_mask()[order].all()
+    assert not ped.table_mode()[0] and not ped.bits_mode()
+    grid = gb.Model.from_uai(res("Grids_11.uai"), device=-1)
+    assert grid.table_mode() == (True, 1600) and grid.bits_mode()
+    od = gb.Model.from_uai(res("ObjectDetection_11.uai"), device=-1)
+    assert not od.hybrid_mask().any() and not od.bits_mode()
 
 
 def test_schedule_is_proper_colouring(res):
