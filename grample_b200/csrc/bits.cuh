@@ -105,8 +105,9 @@ __device__ __forceinline__ uint32_t bits_resolve(const DevTab& t, const int32_t*
 }
 
 // CTA tile = (chunk of 256 * W consecutive state words = 8192 * W chains) x (kBitsVB consecutive sweep positions of the
-// colour); tiles are handed out by an atomic counter (`tile_counter`, zeroed before the launch), so a CTA that starts
-// late — e.g. behind the NCCL kernel of an overlapped merge — simply takes fewer tiles.
+// colour); tiles are handed out by an atomic counter (`tile_counter[0]`, zero at launch; `tile_counter[1]` counts the
+// CTAs that have left), so a CTA that starts late — e.g. behind the NCCL kernel of an overlapped merge — simply takes
+// fewer tiles.
 template <int W, int NT>  // W state words per thread, NT threads per CTA: a chunk is NT * W words = 32 * NT * W chains
 __global__ void __launch_bounds__(NT, NT == 128 ? (W == 2 ? 6 : 8) : 0)  // 256 threads: the compiler's own choice (80 / 48 registers); 128: the same warps per SM
 k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __restrict__ bits, const int32_t n_words,
@@ -133,7 +134,14 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
         __syncthreads();
         const int64_t tile = s_tile;
-        if (tile >= n_tiles) break;
+        if (tile >= n_tiles) {
+            // the last CTA to leave re-arms the group's counter pair {next tile, CTAs done} for the group's next launch
+            if (tid == 0 && atomicAdd(tile_counter + 1, 1u) == gridDim.x - 1) {
+                tile_counter[0] = 0u;
+                tile_counter[1] = 0u;
+            }
+            break;
+        }
         const int chunk = (int)(tile / n_vb), vb = (int)(tile - (int64_t)chunk * n_vb);
         const int nv = min(VB, n_vars_c - vb * VB);
         const int j0 = j_begin + vb * VB;

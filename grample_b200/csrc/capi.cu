@@ -212,6 +212,7 @@ struct Group {
     bool window_filled = false; // the group has been through an AdvanceChain round (its half-window histograms are valid)
     uint8_t* d_state = nullptr;
     uint32_t* d_bits = nullptr;  // GB_TABLE_BITS: [n_vars][n_words] one bit per chain (d_state stays null)
+    unsigned int* d_tile_ctr = nullptr;  // GB_TABLE_BITS: {next tile, CTAs done} of the dynamically scheduled sweep launches
     int32_t n_words = 0;
     unsigned long long* d_counts = nullptr;
     uint16_t* d_hist = nullptr;
@@ -279,9 +280,7 @@ struct gb_chains {
     int last_done_slot = -1;
     bool merge_ever = false;
     int64_t global_chains = -1, global_samples = -1;  // tail of the last completed merge
-    // GB_TABLE_BITS: tile counters of the dynamically scheduled sweep launches (a ring, re-zeroed when it wraps)
-    unsigned int* d_tile_ring = nullptr;
-    uint32_t tile_slot = 0;
+
     // groups are independent between monitor intervals (like the reference's goroutine per chain,
     // chain.go:197-215): their launches fan out over side streams and join back on `stream`
     std::vector<cudaStream_t> side;
@@ -296,11 +295,11 @@ struct gb_chains {
         for (auto& g : groups) {
             cudaFree(g.d_state);
             cudaFree(g.d_bits);
+            cudaFree(g.d_tile_ctr);
             cudaFree(g.d_counts);
             cudaFree(g.d_hist);
             if (g.owns_model) delete g.model;
         }
-        cudaFree(d_tile_ring);
         cudaFree(d_merge);
         cudaFree(d_wb);
         cudaFree(d_skip);
@@ -375,8 +374,13 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     const gb::HostModel& h = model->h;
     g.n_words = (g.n_chains + 31) / 32;
     try {
-        if (bits) CUDA_CHECK(cudaMalloc(&g.d_bits, (size_t)h.n_vars * g.n_words * sizeof(uint32_t)));
-        else CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
+        if (bits) {
+            CUDA_CHECK(cudaMalloc(&g.d_bits, (size_t)h.n_vars * g.n_words * sizeof(uint32_t)));
+            CUDA_CHECK(cudaMalloc(&g.d_tile_ctr, 2 * sizeof(unsigned int)));
+            CUDA_CHECK(cudaMemsetAsync(g.d_tile_ctr, 0, 2 * sizeof(unsigned int), c->stream));
+        } else {
+            CUDA_CHECK(cudaMalloc(&g.d_state, (size_t)h.n_vars * g.n_pad));
+        }
         CUDA_CHECK(cudaMalloc(&g.d_counts, (size_t)h.total_card * sizeof(unsigned long long)));
         CUDA_CHECK(cudaMemsetAsync(g.d_counts, 0, (size_t)h.total_card * sizeof(unsigned long long), c->stream));
         if (c->flags & GB_CHAINS_HISTORY) {
@@ -387,6 +391,7 @@ void add_group(gb_chains* c, gb_model* model, int32_t n_chains, uint64_t first_c
     } catch (...) {  // a failed allocation must not leak the ones before it
         cudaFree(g.d_state);
         cudaFree(g.d_bits);
+        cudaFree(g.d_tile_ctr);
         cudaFree(g.d_counts);
         cudaFree(g.d_hist);
         throw;
@@ -487,15 +492,13 @@ void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
         }
         resident = r;
     }
-    constexpr uint32_t kRing = 1024;
-    if (!c->d_tile_ring) CUDA_CHECK(cudaMalloc(&c->d_tile_ring, kRing * sizeof(unsigned int)));
-    const uint32_t slot = c->tile_slot++ % kRing;
-    if (slot == 0) CUDA_CHECK(cudaMemsetAsync(c->d_tile_ring, 0, kRing * sizeof(unsigned int), c->stream));  // earlier launches of this stream are done with it
+    // the group's counter pair {next tile, CTAs done}: zero at every launch because the last CTA of the previous launch
+    // re-armed it, and a group's launches are ordered (one stream at a time, joined to the handle's stream in between)
     const gb::HostModel& h = g.model->h;
     const int64_t tiles = (int64_t)((g.n_words + NT * W - 1) / (NT * W)) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
     gb::k_sweep_bits<W, NT><<<grid, NT, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
-                                                         record, c->d_tile_ring + slot, gb::philox_keys(g.dev.seed_lo, g.dev.seed_hi));
+                                                         record, g.d_tile_ctr, gb::philox_keys(g.dev.seed_lo, g.dev.seed_hi));
     c->launches++;
 }
 // CTA shape by population: two words per thread amortise the warp-uniform coefficient reads; a chunk (NT * W words) must

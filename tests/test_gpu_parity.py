@@ -398,6 +398,21 @@ def test_bits_tie_path_and_set_state(res):
     assert np.array_equal(ocounts, ch.group_counts(0).astype(np.float64))
 
 
+def test_bits_groups_on_side_streams_and_counter_reuse(res):
+    """several bit-sliced groups of one handle run concurrently on side streams, each with its own tile-counter pair that
+    the last CTA of a launch re-arms; the host enqueues hundreds of launches ahead of the device: every group must still
+    equal its own single-group run (a shared ring of counters double-counted tiles here)"""
+    dm, _ = load_pair(res, "Grids_11.uai", False)
+    n, seed, sweeps = 64, 3, 300
+    multi = gb.Chains([dm, dm, dm], [n, n, n], seed=seed, precision=gb.TABLE_BITS, device=0)
+    multi.sweep(sweeps)
+    for g in range(3):
+        single = gb.Chains(dm, n, seed=seed, first_chain_id=g * n, precision=gb.TABLE_BITS, device=0)
+        single.sweep(sweeps)
+        assert np.array_equal(single.get_state(0, n), multi.get_state(g, n))
+        assert np.array_equal(single.group_counts(0), multi.group_counts(g))
+
+
 def test_bits_mode_rejections_and_statistics(res):
     dm, _ = load_pair(res, "Promedus_11.uai", True)
     assert not dm.bits_mode()
