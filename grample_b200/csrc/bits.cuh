@@ -108,7 +108,11 @@ __device__ __forceinline__ uint32_t bits_resolve(const DevTab& t, const int32_t*
 // colour); tiles are handed out by an atomic counter (`tile_counter[0]`, zero at launch; `tile_counter[1]` counts the
 // CTAs that have left), so a CTA that starts late — e.g. behind the NCCL kernel of an overlapped merge — simply takes
 // fewer tiles.
-template <int W, int NT>  // W state words per thread, NT threads per CTA: a chunk is NT * W words = 32 * NT * W chains
+// W state words per thread, NT threads per CTA.  S = 1: a chunk is NT * W words (32 NT W chains) and every thread walks all
+// positions of the tile; S = 2: the two halves of the CTA take the two halves of the tile's positions for a chunk of
+// NT * W / 2 words — the shape for populations of one such chunk (8192 chains per GPU = the 8-way split of 65536), which
+// keeps 256-thread CTAs and their register allocation instead of a separately compiled 128-thread kernel.
+template <int W, int NT, int S = 1>
 __global__ void __launch_bounds__(NT, NT == 128 ? (W == 2 ? 6 : 8) : 0)  // 256 threads: the compiler's own choice (80 / 48 registers); 128: the same warps per SM
 k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __restrict__ bits, const int32_t n_words,
              const int32_t j_begin, const int32_t n_vars_c, const uint32_t sweep, const int record,
@@ -123,13 +127,15 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
     __shared__ uint2 s_q[kBitsQueue];                    // deferred ties: {position << 16 | word slot, eq}
     __shared__ unsigned int s_qn;
     __shared__ int s_tile;
-    const int chunk_words = NT * W;
+    constexpr int NTS = NT / S;        // threads that share a position
+    const int chunk_words = NTS * W;
     const int chunks = (n_words + chunk_words - 1) / chunk_words;
     const int n_vb = (n_vars_c + VB - 1) / VB;
     const int64_t n_tiles = (int64_t)chunks * n_vb;
     const uint32_t seed_lo = g.seed_lo, seed_hi = g.seed_hi;
     const uint32_t gw0 = (uint32_t)(g.first_chain >> 5);
     const int tid = threadIdx.x;
+    const int lane_t = tid % NTS, part = tid / NTS;  // word slot within the chunk; which part of the tile's positions
     for (;;) {
         if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
         __syncthreads();
@@ -178,13 +184,14 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
         uint32_t valid[W];
 #pragma unroll
         for (int u = 0; u < W; u++) {
-            wi[u] = chunk * chunk_words + u * NT + tid;
+            wi[u] = chunk * chunk_words + u * NTS + lane_t;
             const int64_t first = 32ll * wi[u];
             const int64_t left = (int64_t)g.n_chains - first;
             valid[u] = wi[u] >= n_words || left <= 0 ? 0u : (left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u));
             if (wi[u] >= n_words) wi[u] = n_words - 1;  // padding threads redo the last word, stores masked off
         }
-        const bool any_word = chunk * chunk_words + (tid & ~31) < n_words;  // the warp owns at least one real word
+        const bool any_word = chunk * chunk_words + (lane_t & ~31) < n_words;  // the warp owns at least one real word
+        const int j_lo = min(nv, part * (VB / S)), j_hi = min(nv, (part + 1) * (VB / S));  // this thread's positions of the tile
         if (any_word) {
             // neighbour words of the NEXT position are in flight while this one computes (rows of the other colour:
             // read-only for the whole launch)
@@ -203,13 +210,13 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                     nx[u][3] = __ldg(r3 + wi[u]);
                 }
             };
-            load_nbrs(0);
-            for (int jg = 0; jg < nv; jg += 2) {
+            load_nbrs(min(j_lo, nv - 1));
+            for (int jg = j_lo; jg < j_hi; jg += 2) {
                 uint32_t acc = 0;  // ones of positions jg (low half) and jg + 1 (high half) over this thread's chains
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int j = jg + h;
-                    if (j < nv) {
+                    if (j < j_hi) {
                         const int4 ra = *reinterpret_cast<const int4*>(&s_rec[j * kBitsRec]);      // v, card_off, thr_off, cfg mask
                         uint32_t n[W][4], gt[W], eq[W];
 #pragma unroll
@@ -219,7 +226,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                             gt[u] = 0u;
                             eq[u] = 0xffffffffu;
                         }
-                        load_nbrs(min(j + 1, nv - 1));
+                        load_nbrs(min(j + 1, j_hi - 1));
                         uint32_t* const own = bits + (size_t)ra.x * n_words;
 #pragma unroll
                         for (int half = 0; half < 2; half++) {
@@ -256,7 +263,7 @@ k_sweep_bits(const DevModel m, const DevTab t, const DevGroup g, uint32_t* __res
                             if (eq[u] & valid[u]) {  // undecided after 8 planes (2^-8 per chain): resolve after the tile
                                 const unsigned slot = atomicAdd(&s_qn, 1u);
                                 if (slot < (unsigned)kBitsQueue) {
-                                    s_q[slot] = make_uint2((uint32_t)j << 16 | (uint32_t)(u * NT + tid), eq[u] & valid[u]);
+                                    s_q[slot] = make_uint2((uint32_t)j << 16 | (uint32_t)(u * NTS + lane_t), eq[u] & valid[u]);
                                 } else {
                                     const uint32_t add = bits_resolve(t, &s_rec[j * kBitsRec], bits, n_words, wi[u], gw0 + (uint32_t)wi[u], sweep,
                                                                       seed_lo, seed_hi, eq[u] & valid[u]);

@@ -477,7 +477,7 @@ void launch_tab(gb_chains* c, Group& g, int col, int32_t n, int record, int hist
 }
 
 // GB_TABLE_BITS: one colour of one group on bit-packed state; W = state words per thread, NT = threads per CTA
-template <int W, int NT>
+template <int W, int NT, int S = 1>
 void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
     static int resident_dev[kMaxDevices] = {};  // per device: CTAs that fit at once (persistent CTAs, tiles handed out by an atomic counter)
     int resident;
@@ -487,7 +487,7 @@ void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
         if (!r) {
             int per_sm = 0, sms = 0;
             CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_bits<W, NT>, NT, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb::k_sweep_bits<W, NT, S>, NT, 0));
             r = std::max(1, per_sm * sms);
         }
         resident = r;
@@ -495,22 +495,26 @@ void launch_bits_w(gb_chains* c, Group& g, int col, int32_t n, int record) {
     // the group's counter pair {next tile, CTAs done}: zero at every launch because the last CTA of the previous launch
     // re-armed it, and a group's launches are ordered (one stream at a time, joined to the handle's stream in between)
     const gb::HostModel& h = g.model->h;
-    const int64_t tiles = (int64_t)((g.n_words + NT * W - 1) / (NT * W)) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
+    constexpr int chunk_words = NT * W / S;
+    const int64_t tiles = (int64_t)((g.n_words + chunk_words - 1) / chunk_words) * ((n + gb::kBitsVB - 1) / gb::kBitsVB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, resident));
-    gb::k_sweep_bits<W, NT><<<grid, NT, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
+    gb::k_sweep_bits<W, NT, S><<<grid, NT, 0, c->stream>>>(g.model->dev, g.model->tab, g.dev, g.d_bits, g.n_words, h.colour_off[col], n, g.sweep,
                                                          record, g.d_tile_ctr, gb::philox_keys(g.dev.seed_lo, g.dev.seed_hi));
     c->launches++;
 }
-// CTA shape by population: two words per thread amortise the warp-uniform coefficient reads; a chunk (NT * W words) must
-// not exceed the row, or threads idle — 8192 chains per GPU (the 8-GPU split of 65536) are 256 words = one chunk of 128 x 2
+// CTA shape by population: two words per thread amortise the warp-uniform coefficient reads; a chunk must not exceed the
+// row, or threads idle — 8192 chains per GPU (the 8-way split of 65536) are 256 words = one chunk of the split shape
+// (256 threads x 2 words, the CTA's halves taking half of the tile's positions each)
 void launch_bits(gb_chains* c, Group& g, int col, int32_t n, int record) {
-    const char* env = std::getenv("GB_BITS_SHAPE");  // A/B and test knob: "W,NT"
-    int w = g.n_words >= 256 ? 2 : 1, nt = g.n_words >= 512 ? 256 : 128;
+    const char* env = std::getenv("GB_BITS_SHAPE");  // A/B and test knob: "W,NT" or "W,NT,S"
+    int w = g.n_words >= 256 ? 2 : 1, nt = g.n_words >= 256 ? 256 : 128, sp = (g.n_words >= 256 && g.n_words < 512) ? 2 : 1;
     if (env && std::strlen(env) >= 3) {
         w = env[0] - '0';
         nt = std::atoi(env + 2);
+        sp = std::strlen(env) >= 7 ? env[6] - '0' : 1;
     }
-    if (w == 2 && nt == 256) launch_bits_w<2, 256>(c, g, col, n, record);
+    if (w == 2 && nt == 256 && sp == 2) launch_bits_w<2, 256, 2>(c, g, col, n, record);
+    else if (w == 2 && nt == 256) launch_bits_w<2, 256>(c, g, col, n, record);
     else if (w == 2) launch_bits_w<2, 128>(c, g, col, n, record);
     else if (nt == 256) launch_bits_w<1, 256>(c, g, col, n, record);
     else launch_bits_w<1, 128>(c, g, col, n, record);

@@ -349,7 +349,7 @@ def bits_case(which, res):
     return gb.Model.from_arrays(*arrays, device=0), oracle.Model.create(*arrays)
 
 
-@pytest.mark.parametrize("words", ["1,256", "2,256", "2,128", "1,128"], ids=["W1x256", "W2x256", "W2x128", "W1x128"])
+@pytest.mark.parametrize("words", ["1,256", "2,256", "2,128", "1,128", "2,256,2"], ids=["W1x256", "W2x256", "W2x128", "W1x128", "W2x256split"])
 @pytest.mark.parametrize("which,n_chains,first,n_sweeps", [
     ("Grids_11", 13, 32, 6), ("Grids_11", 96, 0, 5), ("Grids_11", 2100, 64, 3), ("ising_evidence", 75, 0, 7),
     ("ising_32x48", 40, 0, 2)])
