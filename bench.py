@@ -415,7 +415,7 @@ def run_native(args):
     strong = None
     if world > 1:
         del chains
-        per = args.chains // world // 8 * 8
+        per = args.chains // world // 32 * 32  # (a bit-packed state word holds 32 chains: shards start on multiples of 32)
         sch = gb.Chains(model, per, seed=20260101, first_chain_id=rank * per, precision=prec, device=dev)
         gbd.attach(sch, dist)
         sch.synchronize()

@@ -1331,6 +1331,43 @@ def test_ising_full_baseline_size():
     assert np.array_equal(big.get_state(0, 64)[32:48], small.get_state(0, 16))
 
 
+def test_ising_full_baseline_size_bit_sliced():
+    """the bench configuration itself — BASELINE configs[4], 1024x1024 variables x 65536 chains, bit-packed (8 GiB) —
+    through size-independent invariants, and a bit-exact oracle replay of 4 chains over the full 1 M-variable model on a
+    shard (the stream is keyed by the global chain id: a 32-chain shard IS those chains of the big run, checked shard
+    against shard; the full state is never copied to the host: it would be 256 GiB of int32)."""
+    import torch  # only to skip when the device is too small
+    if torch.cuda.get_device_properties(0).total_memory < 40 * 2**30:
+        pytest.skip("needs a large device")
+    H = W = 1024
+    arrays = gb.ising_torus(H, W, wmax=4.9)
+    dm = gb.Model.from_arrays(*arrays, device=0)
+    assert dm.bits_mode()
+    order, coff = dm.schedule()
+    n_chains, seed, lo = 65536, 20260101, 40000
+    ch = gb.Chains(dm, n_chains, seed=seed, precision=gb.TABLE_BITS, device=0)
+    ch.sweep(2)
+    counts = ch.group_counts(0).reshape(-1, 2)
+    assert np.all(counts.sum(1) == 2 * n_chains)          # every variable recorded once per sweep per chain
+    assert ch.total_samples == 2 * H * W * n_chains
+    merged, col = ch.merged_marginals()
+    assert not col.any() and np.array_equal(merged.reshape(-1, 2).sum(1), np.full(H * W, 3.0 * n_chains))
+    del ch
+    base = lo - lo % 32
+    one = gb.Chains(dm, 32, seed=seed, first_chain_id=base, precision=gb.TABLE_BITS, device=0)       # one state word
+    three = gb.Chains(dm, 96, seed=seed, first_chain_id=base - 32, precision=gb.TABLE_BITS, device=0)  # its neighbours too
+    st0 = one.get_state(0, 32)
+    one.sweep(2)
+    three.sweep(2)
+    st1 = one.get_state(0, 32)
+    assert np.array_equal(three.get_state(0, 96)[32:64], st1)
+    om = oracle.Model.create(*arrays)
+    samp = oracle.Sampler(oracle.Generator(1), om)
+    k = lo % 32
+    ost, _ = samp.sweep_run(order, seed, lo, st0[k:k + 4], 0, 2, bits=33, record=False)
+    assert np.array_equal(ost, st1[k:k + 4])
+
+
 # ------------------------------------------------------------------ CLI (cmd/root.go flags and report format)
 def test_cli_sample_adaptive(res, tmp_path):
     import io
