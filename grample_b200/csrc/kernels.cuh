@@ -9,6 +9,10 @@
 //   K4    k_chain_dist        sampler/chain.go:253-290 (ChainDist) + model/error.go:81-249
 //   K5    k_conditional       sampler/gibbs-simple.go:171-258 for caller-supplied states
 //   K6    k_init_state        sampler/gibbs-simple.go:103-111 (uniform start, FixedVal honoured)
+//   table modes (same SampleVar + WeightedSample, the float64 conditional evaluated once per neighbour configuration):
+//         k_build_thresholds, k_sweep_tab (byte state, per colour), k_sweep_tab_resident (small models), and — in bits.cuh —
+//         k_sweep_bits (bit-packed state, bit-sliced compare: the bench kernel)
+//   merge k_merge_counts / k_merge_finalize   sampler/chain.go:96-148 (MergeChains) as integer sums + one rounding
 //
 // Data layout: state[var][chain] uint8, chain fastest, rows padded to a multiple of 4 chains so a
 // thread reads the states of 4 consecutive chains of one neighbour with one 32-bit load and a
