@@ -1169,6 +1169,34 @@ def test_single_step_sample(res):
     assert 0.70 < ones / 1024 < 0.80
 
 
+def test_fleet_python_binding_on_the_visible_gpus(res):
+    """gb.Fleet (gb_fleet_*): every visible GPU holds a shard of the chains; merged marginals equal one handle holding all
+    chains bit for bit, convergence scores to rounding (the C++ host tests/fleet_test.cpp covers Adapt as well)."""
+    n_dev = min(gb.device_count(), 4)
+    total, seed, cw = 32 * n_dev, 19, 12
+    models = [gb.Model.from_uai(res("Grids_11.uai"), device=d) for d in range(n_dev)]
+    fleet = gb.Fleet(list(range(n_dev)))
+    shards = []
+    for d in range(n_dev):
+        ch = gb.Chains(models[d], 32, seed=seed, first_chain_id=32 * d, precision=gb.HYBRID, history=True, device=d)
+        fleet.attach(d, ch)
+        shards.append(ch)
+    one = gb.Chains(models[0], total, seed=seed, precision=gb.HYBRID, history=True, device=0)
+    fleet.sweep(5, record=False)
+    one.burnin(5)
+    fleet.advance(cw)
+    one.advance(cw)
+    m_f, c_f = fleet.merged_marginals()
+    m_1, c_1 = one.merged_marginals()
+    assert np.array_equal(m_f, m_1) and np.array_equal(c_f, c_1)
+    fleet.merge_begin()
+    out, _, n_all, samples = fleet.merge_end()
+    assert np.array_equal(out, m_1) and n_all == total and samples == one.total_samples
+    assert np.allclose(fleet.convergence(gb.HELLINGER, m_f), one.convergence(gb.HELLINGER, m_1), rtol=1e-10)
+    fleet.synchronize()
+    del shards, fleet
+
+
 def test_convergence_requires_history_and_chains(res):
     dm, _ = load_pair(res, "sample.uai", False)
     ch = gb.Chains(dm, 4, seed=1, history=False, device=0)
