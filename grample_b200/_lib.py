@@ -84,6 +84,7 @@ _SIGS = {
     "gb_comm_init_rank": (C.c_int, [C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int, C.POINTER(_vp)]),
     "gb_comm_info": (C.c_int, [_vp, _i32p, _i32p, C.POINTER(C.c_int)]),
     "gb_comm_destroy": (None, [_vp]),
+    "gb_shard": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), _i32p]),
     "gb_chains_attach_comm": (C.c_int, [_vp, _vp]),
     "gb_fleet_create": (C.c_int, [C.c_int32, C.POINTER(C.c_int), C.POINTER(_vp)]),
     "gb_fleet_destroy": (None, [_vp]),

@@ -2008,6 +2008,12 @@ void gb_comm_destroy(gb_comm* cm) {
     }
     delete cm;
 }
+int gb_shard(int64_t total_chains, int32_t world, int32_t rank, uint64_t* first_out, int32_t* n_out) {
+    GB_TRY
+    if (total_chains < 0 || world < 1 || rank < 0 || rank >= world) throw gb::Err("invalid shard request");
+    shard_chains(total_chains, world, rank, first_out, n_out);
+    GB_END
+}
 int gb_chains_attach_comm(gb_chains* c, gb_comm* cm) {
     GB_TRY
     GB_LOCK(c);

@@ -304,6 +304,10 @@ int gb_comm_init_rank(const uint8_t* id /*[GB_COMM_ID_BYTES], may be NULL when w
                       int device, gb_comm** out);
 int gb_comm_info(const gb_comm* comm, int32_t* world_out, int32_t* rank_out, int* device_out);
 void gb_comm_destroy(gb_comm* comm);
+/* the shard of `total_chains` chains that rank `rank` of `world` holds: contiguous, first id a multiple of 8 (chains share
+ * Philox calls in blocks of 8), covering [0, total) over the ranks — the rule gb_chains_adapt / gb_fleet_adapt apply to a
+ * new variant's chains, exposed so that a host shards its base chains the same way (pure host arithmetic) */
+int gb_shard(int64_t total_chains, int32_t world, int32_t rank, uint64_t* first_out, int32_t* n_out);
 /* comm may be NULL (detach).  The handle borrows the communicator: destroy the chains first. */
 int gb_chains_attach_comm(gb_chains* c, gb_comm* comm);
 /* One process, several GPUs (a Go or C++ host like cmd/root.go): a fleet owns a single-process communicator over

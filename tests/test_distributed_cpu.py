@@ -32,6 +32,21 @@ def test_shard_covers_all_chains_block_aligned():
                     pos += n
 
 
+def test_library_shards_like_the_python_plumbing():
+    """gb_shard — the rule the library applies to a new variant's chains under a communicator or a fleet
+    (gb_chains_adapt / gb_fleet_adapt) — is the rule `distributed.shard` applies to the base chains"""
+    import ctypes as C
+    from grample_b200 import _lib
+    for total in (1, 7, 8, 20, 64, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                first, n = C.c_uint64(), C.c_int32()
+                _lib.check(_lib.lib().gb_shard(total, world, rank, C.byref(first), C.byref(n)))
+                assert (first.value, n.value) == gbd.shard(total, world, rank)
+    first, n = C.c_uint64(), C.c_int32()
+    assert _lib.lib().gb_shard(8, 2, 2, C.byref(first), C.byref(n)) != 0
+
+
 def simulate_rank(first, n):
     """what one rank's device would hold after one advance(CW) round over chains [first, first+n)"""
     path = os.path.join(RES, "Grids_11.uai")
