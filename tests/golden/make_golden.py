@@ -37,20 +37,43 @@ def random_states(rng, cards, fixed, n):
 
 
 def greedy_schedule(model):
-    """colour-sorted sweep schedule: greedy colouring in id order over the sampled variables (the rule
-    HostModel::build_colouring implements; variables inside a colour in ascending id)"""
+    """colour-sorted sweep schedule (the rule HostModel::build_colouring implements, stated independently): greedy colouring
+    of the sampled variables in id order, or — when that needs strictly fewer colours — greedy in smallest-last order
+    (repeatedly remove a variable of least remaining degree, ties by smallest id; colour in reverse removal order).
+    Variables inside a colour in ascending id."""
+    import heapq
     samp = oracle.Sampler(oracle.Generator(1), model, collapsed=True)
     fixed = model.fixed
     n = model.n_vars
-    colour = [-1] * n
-    for v in range(n):
-        if fixed[v] >= 0:
+    free = [v for v in range(n) if fixed[v] < 0]
+    adj = {v: [u for u in samp.neighbors(v) if u != v and fixed[u] < 0] for v in free}
+
+    def greedy(seq):
+        colour = [-1] * n
+        for v in seq:
+            used = {colour[u] for u in adj[v] if colour[u] >= 0}
+            c = 0
+            while c in used:
+                c += 1
+            colour[v] = c
+        return colour
+
+    deg = {v: len(adj[v]) for v in free}
+    heap = [(deg[v], v) for v in free]
+    heapq.heapify(heap)
+    removed, seq = set(), []
+    while heap:
+        d, v = heapq.heappop(heap)
+        if v in removed or d != deg[v]:
             continue
-        used = {colour[u] for u in samp.neighbors(v) if u != v and colour[u] >= 0}
-        c = 0
-        while c in used:
-            c += 1
-        colour[v] = c
+        removed.add(v)
+        seq.append(v)
+        for u in adj[v]:
+            if u not in removed:
+                deg[u] -= 1
+                heapq.heappush(heap, (deg[u], u))
+    by_id, by_sl = greedy(free), greedy(seq[::-1])
+    colour = by_sl if max(by_sl) < max(by_id) else by_id
     n_col = max(colour) + 1
     return [[v for v in range(n) if colour[v] == c] for c in range(n_col)]
 

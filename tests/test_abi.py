@@ -107,11 +107,11 @@ def test_table_programs_cover_cardinality_up_to_four(res):
 
 
 def test_schedule_is_proper_colouring(res):
-    for name, evid, ncol in (("Grids_11.uai", False, 2), ("Promedus_11.uai", True, 4), ("Pedigree_11.uai", True, 5),
+    for name, evid, ncol in (("Grids_11.uai", False, 2), ("Promedus_11.uai", True, 4), ("Pedigree_11.uai", True, 4),
                              ("ObjectDetection_11.uai", False, 7)):
         dm = gb.Model.from_uai(res(name), use_evidence=evid, device=-1)
         order, coff = dm.schedule()
-        assert len(coff) - 1 == ncol
+        assert len(coff) - 1 == ncol  # SURVEY §8a (Pedigree_11: 5 with the id-order greedy colouring, 4 with smallest-last)
         fixed = dm.fixed
         assert sorted(order.tolist()) == [v for v in range(dm.n_vars) if fixed[v] < 0]
         colour = {}
