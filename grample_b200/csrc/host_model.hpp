@@ -231,8 +231,8 @@ struct HostModel {
     // schedule): greedy in id order, or — when that needs strictly fewer colours — greedy in smallest-last
     // (degeneracy) order: repeatedly remove a variable of least remaining degree (ties: smallest id), colour in reverse
     // removal order.  A sweep costs one barrier-to-barrier step per colour on the resident kernels, so a colour saved is
-    // a step saved (Pedigree_11: 5 -> 4 colours); the id-order colouring stays wherever it is as good (the torus grids
-    // keep their checkerboard).  tests/golden/make_golden.py states the same rule independently.
+    // a step saved (Pedigree_11 + evidence: 5 -> 4 colours); the id-order colouring stays wherever it is as good by
+    // sweep_cost (the torus grids keep their checkerboard).  tests/golden/make_golden.py states the same rule independently.
     int greedy_colouring(const std::vector<int32_t>& seq, std::vector<int32_t>& col) const {
         col.assign(n_vars, -1);
         int n_col = 0;
@@ -280,15 +280,36 @@ struct HostModel {
         std::reverse(seq.begin(), seq.end());
         return seq;
     }
+    // What a sweep costs on the resident kernels, in units of one binary update: every colour is one barrier-to-barrier step
+    // that lasts as long as its slowest update, and a non-binary variable's update (full-width draws, card - 1 thresholds
+    // or a log-sum-exp) takes about 2.5 binary ones.  Pedigree_11 without evidence keeps its 5 id-order colours for this
+    // reason: smallest-last needs 4 but spreads the 23 ternary variables over all of them (measured 15.0 vs 18.9 us/sweep).
+    double sweep_cost(const std::vector<int32_t>& col, const int n_col) const {
+        std::vector<double> worst(std::max(n_col, 1), 0.0);
+        bool mixed = false;  // cardinalities differ among the sampled variables
+        const int32_t c0 = card[order_probe(col)];
+        for (int v = 0; v < n_vars; v++)
+            if (col[v] >= 0 && card[v] != c0) mixed = true;
+        for (int v = 0; v < n_vars; v++)
+            if (col[v] >= 0) worst[col[v]] = std::max(worst[col[v]], (mixed && card[v] > 2) ? 2.5 : 1.0);
+        double total = 0.0;
+        for (double w : worst) total += w;
+        return total;
+    }
+    int order_probe(const std::vector<int32_t>& col) const {  // any sampled variable (reference cardinality for `mixed`)
+        for (int v = 0; v < n_vars; v++)
+            if (col[v] >= 0) return v;
+        return 0;
+    }
     void build_colouring() {
         std::vector<int32_t> by_id;
         for (int v = 0; v < n_vars; v++)
             if (sampled(v)) by_id.push_back(v);
         int n_col = greedy_colouring(by_id, colour);
-        {
+        if (!std::getenv("GB_COLOURING_ID_ORDER")) {  // (A/B knob: keep the id-order colouring)
             std::vector<int32_t> alt;
             const int n_alt = greedy_colouring(smallest_last_order(), alt);
-            if (n_alt < n_col) {
+            if (sweep_cost(alt, n_alt) < sweep_cost(colour, n_col)) {
                 colour.swap(alt);
                 n_col = n_alt;
             }

@@ -38,7 +38,8 @@ def random_states(rng, cards, fixed, n):
 
 def greedy_schedule(model):
     """colour-sorted sweep schedule (the rule HostModel::build_colouring implements, stated independently): greedy colouring
-    of the sampled variables in id order, or — when that needs strictly fewer colours — greedy in smallest-last order
+    of the sampled variables in id order, or — when that makes a sweep cheaper (fewer colour steps, weighted by the slowest
+    update of each) — greedy in smallest-last order
     (repeatedly remove a variable of least remaining degree, ties by smallest id; colour in reverse removal order).
     Variables inside a colour in ascending id."""
     import heapq
@@ -73,7 +74,13 @@ def greedy_schedule(model):
                 deg[u] -= 1
                 heapq.heappush(heap, (deg[u], u))
     by_id, by_sl = greedy(free), greedy(seq[::-1])
-    colour = by_sl if max(by_sl) < max(by_id) else by_id
+    cards = model.cards
+    mixed = len({int(cards[v]) for v in free}) > 1
+
+    def sweep_cost(colour):  # one step per colour, as long as its slowest update (a non-binary update ~ 2.5 binary ones)
+        return sum(max((2.5 if mixed and cards[v] > 2 else 1.0) for v in free if colour[v] == c) for c in range(max(colour) + 1))
+
+    colour = by_sl if sweep_cost(by_sl) < sweep_cost(by_id) else by_id
     n_col = max(colour) + 1
     return [[v for v in range(n) if colour[v] == c] for c in range(n_col)]
 
