@@ -768,12 +768,17 @@ void launch_tab_resident(gb_chains* c, Group& g, const ResidentPlan& p, int32_t 
     const int threads = (int)std::min<int64_t>(256, (items + 31) / 32 * 32);  // whole warps, no idle ones at the colour barrier
     size_t smem = 0;
     const int32_t hist_off = place_histograms(c, g, p, n_half, &smem);
-    static size_t configured_dev[4][kMaxDevices] = {};  // function attributes are per device
-    const bool wide = h.tab_max_nbr > 8, multi = !h.tab_all_binary;
+    static size_t configured_dev[8][kMaxDevices] = {};  // function attributes are per device
+    const bool wide = h.tab_max_nbr > 8, multi = !h.tab_all_binary, rb = g.dev.rb != 0;
     std::lock_guard<std::mutex> cfg_lock(g_cfg_mu);
-    size_t& configured = configured_dev[2 * multi + wide][c->device];
-    auto kernel = multi ? (wide ? gb::k_sweep_tab_resident<true, true> : gb::k_sweep_tab_resident<false, true>)
-                        : (wide ? gb::k_sweep_tab_resident<true, false> : gb::k_sweep_tab_resident<false, false>);
+    size_t& configured = configured_dev[4 * rb + 2 * multi + wide][c->device];
+    using Kernel = void (*)(const gb::DevModel, const gb::DevTab, const gb::DevGroup, const int32_t*, const int32_t, const int32_t,
+                            const uint32_t, const int32_t, const int, const int32_t, const int32_t, const int32_t);
+    static const Kernel kernels[8] = {gb::k_sweep_tab_resident<false, false, false>, gb::k_sweep_tab_resident<true, false, false>,
+                                      gb::k_sweep_tab_resident<false, true, false>,  gb::k_sweep_tab_resident<true, true, false>,
+                                      gb::k_sweep_tab_resident<false, false, true>,  gb::k_sweep_tab_resident<true, false, true>,
+                                      gb::k_sweep_tab_resident<false, true, true>,   gb::k_sweep_tab_resident<true, true, true>};
+    const Kernel kernel = kernels[4 * rb + 2 * multi + wide];
     if (smem > configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

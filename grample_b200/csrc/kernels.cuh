@@ -1211,7 +1211,7 @@ k_sweep_tab(const DevModel m, const DevTab t, const DevGroup g, const int32_t j_
 // WIDE: some variable has more than 8 free neighbours or 256 configurations (variable-length records, 32-bit configuration
 // indices).  MULTI: some sampled variable is ternary / quaternary (card - 1 cumulative thresholds per configuration,
 // full 32-bit draws, value = number of thresholds the draw exceeds); binary variables keep the 16-bit fast path.
-template <bool WIDE, bool MULTI>
+template <bool WIDE, bool MULTI, bool RB>  // RB: Rao-Blackwell bins instead of counts (g.rb is set)
 __global__ void __launch_bounds__(256)
 k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const int32_t* __restrict__ colour_off,
                      const int32_t n_colours, const int32_t ch_per_cta, const uint32_t sweep0, const int32_t n_sweeps,
@@ -1311,15 +1311,15 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                             for (int k = 0; k < card - 1; k++) {
                                 const uint32_t Tk = __ldg(T + k);
                                 val += u > Tk ? 1 : 0;
-                                if (g.rb && i < nvalid) {
+                                if (RB && i < nvalid) {
                                     atomicAdd(g.counts + hd.w + k, (unsigned long long)rb_units((uint64_t)Tk - prev));
                                     prev = (uint64_t)Tk;
                                 }
                             }
-                            if (g.rb && i < nvalid) atomicAdd(g.counts + hd.w + card - 1, (unsigned long long)rb_units(4294967296ull - prev));
+                            if (RB && i < nvalid) atomicAdd(g.counts + hd.w + card - 1, (unsigned long long)rb_units(4294967296ull - prev));
                             outb[i >> 2] |= (uint32_t)val << (8 * (i & 3));
                             if (i < nvalid) {
-                                if (!g.rb) atomicAdd(&s_counts[hd.w + val], 1u);
+                                if (!RB) atomicAdd(&s_counts[hd.w + val], 1u);
                                 if (hist_half >= 0 && g.hist)  // (the shared-memory histograms hold the ones of binary variables only)
                                     hist_add(nullptr, g, m.total_card, hist_half, hd.w + val, CH, 0, lchain + i);
                             }
@@ -1361,7 +1361,7 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                     const int nvalid = max(0, min(8, g.n_chains - lchain));
                     const uint32_t vmask = (nvalid >= 8) ? 0xffu : ((1u << nvalid) - 1u);
                     const int ones = __popc(xbits & vmask);
-                    if (g.rb) {  // Rao-Blackwell bins: the conditionals themselves (thresholds), not the draws
+                    if constexpr (RB) {  // Rao-Blackwell bins: the conditionals themselves (thresholds), not the draws
                         unsigned long long q0 = 0;
 #pragma unroll
                         for (int i = 0; i < 8; i++)
