@@ -231,9 +231,10 @@ int gb_chains_merged_marginals(gb_chains* c, double* out, int32_t* collapsed_out
  * result is bit-identical however the chains are sharded over devices. */
 int gb_chains_merge_begin(gb_chains* c, double* out, int32_t* collapsed_out);
 int gb_chains_merge_end(gb_chains* c, int64_t* total_chains_out, int64_t* total_samples_out);
-/* device time of the last completed merge's stages, in milliseconds (measurement hook): ms_out[0] = count sums on the
- * sweep stream, [1] = NCCL sum over the ranks (includes waiting for the slowest rank), [2] = conversion to marginals,
- * [3] = copy to the host */
+/* device time between the stage marks of the last completed merge, in milliseconds (measurement hook): ms_out[0] = count
+ * sums on the sweep stream, [1] = NCCL sum over the ranks (includes waiting for SMs — the NCCL kernel starts when a
+ * device-filling sweep kernel ends — and for the slowest rank), [2] = conversion to marginals (enqueued on the sweep stream
+ * behind the next sweep kernel, so it includes that kernel when sweeps follow the merge), [3] = copy to the host */
 int gb_chains_merge_timing(gb_chains* c, float* ms_out /*[4]*/);
 /* chain count / TotalSampleCount over all ranks as of the last completed merge (cmd/root.go:488-491) */
 int gb_chains_global_totals(const gb_chains* c, int64_t* total_chains_out, int64_t* total_samples_out);
