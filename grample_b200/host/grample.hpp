@@ -209,9 +209,37 @@ struct FullSampler {  // sampler.go:16-18
     virtual ~FullSampler() = default;
     std::shared_ptr<rnd::Generator> gen;
     std::shared_ptr<model::Model> pgm;
+    uint64_t steps = 0;  // counter of the single-step Philox stream (one per Sample / SampleVar call)
+
+    // FullSampler.Sample: one single-variable update of the caller-held sample `s`, variable drawn uniformly among the
+    // free (and, for the collapsed sampler, un-collapsed) ones; returns its index (gibbs-simple.go:148-160,
+    // gibbs-collapsed.go:317-334).  One small launch per call (gb_model_sample): the API-compatibility path that the
+    // reference's tests and benchmarks drive; chains advance through Chain::AdvanceChain.
+    virtual int Sample(std::vector<int>& s) { return sample_one(-1, s); }
+
+  protected:
+    virtual bool exclude_collapsed() const { return false; }
+    int sample_one(int varIdx, std::vector<int>& s) {
+        if (s.size() != pgm->Vars.size())  // gibbs-simple.go:149-151
+            throw Error("Sample size " + std::to_string(s.size()) + " != Var size " + std::to_string(pgm->Vars.size()));
+        std::vector<int32_t> st(s.begin(), s.end());
+        int32_t v = -1;
+        const int prec = options().precision == GB_F32 ? GB_F32 : GB_F64;
+        check(gb_model_sample(pgm->dev->h, prec, varIdx, exclude_collapsed() ? 1 : 0, gen ? gen->seed : 0, ++steps, st.data(), &v),
+              "Could not sample from var in model");
+        pgm->Vars[v].State["Selections"] += 1.0;  // gibbs-simple.go:165
+        s[v] = st[v];
+        return v;
+    }
 };
 
-struct GibbsSimple : FullSampler {};
+struct GibbsSimple : FullSampler {
+    // (*GibbsSimple).SampleVar (gibbs-simple.go:163-271)
+    int SampleVar(int varIdx, std::vector<int>& s) {
+        if (varIdx < 0 || varIdx >= (int)pgm->Vars.size()) throw Error("Invalid variable index " + std::to_string(varIdx));
+        return sample_one(varIdx, s);
+    }
+};
 
 // sampler.NewGibbsSimple(gen, m): validation happened when the model was flattened
 // (gb_model_create / gb_model_load_uai); like the reference a nil model is an error.
@@ -225,6 +253,7 @@ inline std::shared_ptr<GibbsSimple> NewGibbsSimple(std::shared_ptr<rnd::Generato
 }
 
 struct GibbsCollapsed : FullSampler {
+    bool exclude_collapsed() const override { return true; }  // gibbs-collapsed.go:326
     int BlanketSize(const model::Variable& v) const {  // gibbs-collapsed.go:81-83
         int32_t n = 0;
         check(gb_model_blanket_size(pgm->dev->h, v.ID, &n), "BlanketSize");

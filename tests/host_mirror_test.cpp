@@ -44,6 +44,34 @@ static void TestWorkingGibbsSimple() {
     EXPECT(throws([&] { sampler::NewGibbsSimple(gen, nullptr); }));
 }
 
+// sampler/gibbs-simple_test.go:13-38 literally: the single-step FullSampler.Sample on one.uai returns index 0 and both
+// values appear in 1024 draws; plus the size check of gibbs-simple.go:149-151 and the collapsed sampler's exclusion rule
+static void TestSingleStepSample() {
+    auto mod = model::NewModelFromFile(RES + "/one.uai", false);
+    auto gen = rnd::NewGenerator(42);
+    auto samp = sampler::NewGibbsSimple(gen, mod);
+    std::vector<int> s(1, 0);
+    int seen[2] = {0, 0};
+    for (int i = 0; i < 1024; i++) {
+        EXPECT(samp->Sample(s) == 0);
+        EXPECT(s[0] == 0 || s[0] == 1);
+        seen[s[0]]++;
+    }
+    EXPECT(seen[0] > 0 && seen[1] > 0);
+    EXPECT(in_epsilon(0.75, seen[1] / 1024.0, 0.1));  // one.uai: a single 0.25 / 0.75 factor
+    EXPECT(mod->Vars[0].State["Selections"] == 1024.0);
+    std::vector<int> bad(2, 0);
+    EXPECT(throws([&] { samp->Sample(bad); }));
+    EXPECT(samp->SampleVar(0, s) == 0);
+    EXPECT(throws([&] { samp->SampleVar(5, s); }));
+    // collapsed sampler: a collapsed variable is never selected (gibbs-collapsed.go:317-334)
+    auto m3 = model::NewModelFromFile(RES + "/sample.uai", false);
+    auto cs = sampler::NewGibbsCollapsed(gen, m3);
+    model::Variable* cv = cs->Collapse(0);
+    std::vector<int> s3(m3->Vars.size(), 0);
+    for (int i = 0; i < 64; i++) EXPECT(cs->Sample(s3) != cv->ID);
+}
+
 // sampler/gibbs-collapsed_test.go:14-48
 static void TestWorkingGibbsCollapsed() {
     auto mod = model::NewModelFromFile(RES + "/deterministic.uai", false);
@@ -197,7 +225,8 @@ static void TestMainLoopAdaptive() {
 int main(int argc, char** argv) {
     RES = argc > 1 ? argv[1] : "tests/golden/res";
     struct { const char* name; std::function<void()> fn; } tests[] = {
-        {"TestWorkingGibbsSimple", TestWorkingGibbsSimple}, {"TestWorkingGibbsCollapsed", TestWorkingGibbsCollapsed},
+        {"TestWorkingGibbsSimple", TestWorkingGibbsSimple}, {"TestSingleStepSample", TestSingleStepSample},
+        {"TestWorkingGibbsCollapsed", TestWorkingGibbsCollapsed},
         {"TestFullGibbsCollapsed", TestFullGibbsCollapsed}, {"TestMergeChains", TestMergeChains},
         {"TestMainLoopSimple", TestMainLoopSimple},         {"TestMainLoopAdaptive", TestMainLoopAdaptive}};
     for (auto& t : tests) {

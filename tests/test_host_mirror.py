@@ -35,6 +35,6 @@ def test_host_mirror_reference_tests_pass_on_gpu():
     r = subprocess.run([build_exe(), RES], capture_output=True, text=True, timeout=600)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout
-    for name in ("TestWorkingGibbsSimple", "TestWorkingGibbsCollapsed", "TestFullGibbsCollapsed", "TestMergeChains",
+    for name in ("TestWorkingGibbsSimple", "TestSingleStepSample", "TestWorkingGibbsCollapsed", "TestFullGibbsCollapsed", "TestMergeChains",
                  "TestMainLoopSimple", "TestMainLoopAdaptive"):
         assert f"PASS {name}" in r.stdout
