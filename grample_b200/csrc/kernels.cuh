@@ -1295,33 +1295,60 @@ k_sweep_tab_resident(const DevModel m, const DevTab t, const DevGroup g, const i
                 const Philox4 a = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Hi, g.seed_lo, g.seed_hi);
                 const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
                 if constexpr (MULTI) {
-                    if (card > 2) {  // ternary / quaternary variable
-                        const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
-                        const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+                    if (card > 2) {  // ternary / quaternary variable: value = number of cumulative thresholds the 32-bit draw exceeds
                         const int nvalid = record ? max(0, min(8, g.n_chains - lchain)) : 0;
-                        uint32_t outb[2] = {0u, 0u};
+                        // first on the draws' high halves (one Philox call, like the binary path); the low halves are
+                        // generated only when a high half ties with a threshold's (probability ~ 2^-16 per comparison)
+                        uint32_t Tk[8][3], hi16[8];
+                        int val[8];
+                        bool tie = false;
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             uint32_t idx = ((i < 4 ? cfg_lo : cfg_hi) >> (8 * (i & 3))) & 0xffu;
                             if constexpr (WIDE) idx = wide ? idxw[i] : idx;
-                            const uint32_t u = (((wa[i >> 1] >> (16 * (i & 1))) & 0xffffu) << 16) | ((wb[i >> 1] >> (16 * (i & 1))) & 0xffffu);
                             const uint32_t* __restrict__ T = t.thr + hd.y + idx * (uint32_t)(card - 1);
-                            int val = 0;
-                            uint64_t prev = 0;
-                            for (int k = 0; k < card - 1; k++) {
-                                const uint32_t Tk = __ldg(T + k);
-                                val += u > Tk ? 1 : 0;
-                                if (RB && i < nvalid) {
-                                    atomicAdd(g.counts + hd.w + k, (unsigned long long)rb_units((uint64_t)Tk - prev));
-                                    prev = (uint64_t)Tk;
+                            hi16[i] = (wa[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                            val[i] = 0;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                Tk[i][k] = k < card - 1 ? __ldg(T + k) : 0xffffffffu;  // (a threshold no draw exceeds)
+                                val[i] += hi16[i] > (Tk[i][k] >> 16) ? 1 : 0;
+                                tie |= k < card - 1 && hi16[i] == (Tk[i][k] >> 16);
+                            }
+                        }
+                        if (tie) {
+                            const Philox4 b = philox_wide((uint32_t)hd.x, sweep, chain_blk, kTagDraw16Lo, g.seed_lo, g.seed_hi);
+                            const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const uint32_t u = (hi16[i] << 16) | ((wb[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                                val[i] = 0;
+#pragma unroll
+                                for (int k = 0; k < 3; k++) val[i] += (k < card - 1 && u > Tk[i][k]) ? 1 : 0;
+                            }
+                        }
+                        uint32_t outb[2] = {0u, 0u}, cpack = 0u;  // state bytes; per-value counts of the valid chains, one byte each
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            outb[i >> 2] |= (uint32_t)val[i] << (8 * (i & 3));
+                            if (i < nvalid) {
+                                cpack += 1u << (8 * val[i]);
+                                if (hist_half >= 0 && g.hist)  // (the shared-memory histograms hold the ones of binary variables only)
+                                    hist_add(nullptr, g, m.total_card, hist_half, hd.w + val[i], CH, 0, lchain + i);
+                                if constexpr (RB) {
+                                    uint64_t prev = 0;
+                                    for (int k = 0; k < card - 1; k++) {
+                                        atomicAdd(g.counts + hd.w + k, (unsigned long long)rb_units((uint64_t)Tk[i][k] - prev));
+                                        prev = (uint64_t)Tk[i][k];
+                                    }
+                                    atomicAdd(g.counts + hd.w + card - 1, (unsigned long long)rb_units(4294967296ull - prev));
                                 }
                             }
-                            if (RB && i < nvalid) atomicAdd(g.counts + hd.w + card - 1, (unsigned long long)rb_units(4294967296ull - prev));
-                            outb[i >> 2] |= (uint32_t)val << (8 * (i & 3));
-                            if (i < nvalid) {
-                                if (!RB) atomicAdd(&s_counts[hd.w + val], 1u);
-                                if (hist_half >= 0 && g.hist)  // (the shared-memory histograms hold the ones of binary variables only)
-                                    hist_add(nullptr, g, m.total_card, hist_half, hd.w + val, CH, 0, lchain + i);
+                        }
+                        if constexpr (!RB) {
+                            for (int k = 0; k < card; k++) {
+                                const uint32_t n = (cpack >> (8 * k)) & 0xffu;
+                                if (n) atomicAdd(&s_counts[hd.w + k], n);
                             }
                         }
                         *reinterpret_cast<uint2*>(s_state + (size_t)hd.x * CH + 8 * q) = make_uint2(outb[0], outb[1]);
